@@ -1,0 +1,205 @@
+"""Golden-vector generator.  TEST INFRASTRUCTURE ONLY; runs in the build container, not on the GPU box.
+
+Imports the UNMODIFIED reference modules from /root/reference through the import shims in
+oracle/ref_shims/ (SURVEY.md section 8c), runs them on seeded CPU inputs and writes small fixtures
+to tests/golden/.  The weights are not stored: both sides rebuild them with
+oracle.pidm_oracle.make_test_state_dict(cfg, seed).
+
+    python oracle/make_golden.py            # rewrites tests/golden/*.pt
+"""
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get('PIDM_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, 'ref_shims'))
+sys.path.insert(0, REF)
+warnings.filterwarnings('ignore')
+
+from oracle import pidm_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def save(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    torch.save(obj, os.path.join(OUT, name))
+    n = sum(v.numel() * v.element_size() for v in obj.values() if torch.is_tensor(v))
+    print(f'wrote {name}: {n / 1024:.1f} KiB')
+
+
+def smooth_fields(B, seed, P=64):
+    """Smooth positive-K / smooth-p fields (a few Fourier modes) used as x0 / x0_pred."""
+    g = torch.Generator().manual_seed(seed)
+    i = torch.arange(P, dtype=torch.float32) / (P - 1)
+    X, Y = torch.meshgrid(i, i, indexing='ij')
+    out = torch.zeros(B, 2, P, P)
+    for b in range(B):
+        for c in range(2):
+            f = torch.zeros(P, P)
+            for _ in range(4):
+                a, kx, ky, ph = torch.randn(1, generator=g), *torch.randint(1, 4, (2,), generator=g), torch.rand(1, generator=g)
+                f += a * torch.sin(np.pi * kx * X + ph) * torch.cos(np.pi * ky * Y)
+            out[b, c] = f if c == 0 else torch.exp(0.5 * f)
+    return out
+
+
+def write_mesh(folder, nel=64):
+    """Unit-square 65x65-node / 64x64-element mesh files in the solidspy text format read at
+    residuals_mechanics_K.py:43-49; convention documented in oracle.pidm_oracle.mechanics_mesh."""
+    nn_ = nel + 1
+    rows, cols = np.meshgrid(np.arange(nn_), np.arange(nn_), indexing='ij')
+    ids = (rows * nn_ + cols).reshape(-1)
+    nodes = np.stack([ids, cols.reshape(-1) / nel, (nel - rows.reshape(-1)) / nel, 0 * ids, 0 * ids], axis=1)
+    np.savetxt(os.path.join(folder, 'nodes.txt'), nodes, fmt='%d %.8f %.8f %d %d')
+    er, ec = np.meshgrid(np.arange(nel), np.arange(nel), indexing='ij')
+    er, ec = er.reshape(-1), ec.reshape(-1)
+    eles = np.stack([er * nel + ec, 0 * er + 1, 0 * er, (er + 1) * nn_ + ec, (er + 1) * nn_ + ec + 1,
+                     er * nn_ + ec + 1, er * nn_ + ec], axis=1)
+    np.savetxt(os.path.join(folder, 'eles.txt'), eles, fmt='%d')
+    np.savetxt(os.path.join(folder, 'mater.txt'), np.array([[1.0, 0.3]]), fmt='%.4f')
+    np.savetxt(os.path.join(folder, 'loads.txt'), np.array([[0, 0.0, 0.0]]), fmt='%d %.2f %.2f')
+
+
+def main():
+    torch.set_num_threads(8)
+    from src.unet_model import Unet3D
+    from src.denoising_utils import DenoisingDiffusion
+    from src.residuals_darcy import ResidualsDarcy
+    from src.residuals_mechanics_K import ResidualsMechanics
+
+    # ---- schedule tables (A1) -----------------------------------------------------------------
+    for n in (100, 250):
+        d = DenoisingDiffusion(n, 'cpu')
+        save(f'schedule_{n}.pt', {k: v.clone() for k, v in d.diff_dict.items()})
+
+    # ---- U-Net forward with taps (A6) ---------------------------------------------------------
+    cfg = O.unet_config(dim=32, channels=2)
+    sd = O.make_test_state_dict(cfg, seed=0)
+    model = Unet3D(dim=32, channels=2)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 2, 64, 64, generator=g)
+    t = torch.tensor([3, 77])
+    taps = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            taps[name] = out.detach().squeeze(2).clone()
+        return f
+    hs = [model.init_conv.register_forward_hook(hook('init_conv')),
+          model.time_mlp.register_forward_hook(lambda m, i, o: taps.__setitem__('time_emb', o.detach().clone())),
+          model.downs[0][0].register_forward_hook(hook('downs.0.0')),
+          model.downs[0][2].register_forward_hook(hook('downs.0.2')),
+          model.mid_spatial_attn.register_forward_hook(hook('mid_attn')),
+          model.ups[0][3].register_forward_hook(hook('ups.0'))]
+    with torch.no_grad():
+        y = model(x, t)
+        y_bxyc = model(x.permute(0, 2, 3, 1).reshape(2, 4096, 2), t)
+    for h in hs:
+        h.remove()
+    assert torch.equal(y, y_bxyc)
+    save('unet_darcy_fwd.pt', dict(x=x, t=t, y=y, **{'tap_' + k: v for k, v in taps.items()}))
+
+    # ---- Darcy residual on given fields (A7-A9) -----------------------------------------------
+    res = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True,
+                         device='cpu', bcs='none', domain_length=1.)
+    x0p = smooth_fields(3, seed=5)
+    x0p[2] = torch.randn(2, 64, 64, generator=g)          # one rough sample
+    r = res.compute_residual(x0p, pass_through=True)['residual']
+    xg = x0p.clone().requires_grad_(True)
+    rg = res.compute_residual(xg, pass_through=True)['residual']
+    wgt = torch.randn(rg.shape, generator=g)
+    (rg * wgt).sum().backward()
+    save('darcy_residual.pt', dict(x0_pred=x0p, residual=r.detach(), f_s=res.f_s.reshape(64, 64).clone(),
+                                   cotangent=wgt, grad_x0_pred=xg.grad.clone()))
+
+    # ---- full training loss + gradients, mean mode (A3) ---------------------------------------
+    diff = DenoisingDiffusion(100, 'cpu')
+    model.train()
+    x0 = smooth_fields(2, seed=9)
+    torch.manual_seed(123)
+    loss, data_l, res_l, _, _ = diff.model_estimation_loss(x0, residual_func=res, c_data=1., c_residual=1e-3,
+                                                           c_ineq=0., lambda_opt=0.)
+    model.zero_grad()
+    loss.backward()
+    torch.manual_seed(123)                                  # replay the two RNG draws (:625,:636)
+    t_l = torch.randint(0, 100, size=(2,))
+    e_l = torch.randn_like(x0)
+    keys = ['init_conv.weight', 'time_mlp.1.weight', 'downs.0.0.block1.proj.weight', 'downs.0.0.mlp.1.weight',
+            'downs.0.2.fn.fn.to_qkv.weight', 'downs.1.3.weight', 'mid_spatial_attn.fn.fn.fn.to_qkv.weight',
+            'ups.0.3.weight', 'ups.3.2.fn.norm.gamma', 'final_conv.1.weight', 'final_conv.1.bias',
+            'downs.3.1.block2.norm.weight', 'ups.1.0.res_conv.weight']
+    named = dict(model.named_parameters())
+    grads = {'grad_' + k: named[k].grad.clone() for k in keys}
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters() if p.grad is not None)).float()
+    nograd = sorted(k for k, p in named.items() if p.grad is None)
+    save('darcy_loss_mean.pt', dict(x0=x0, t=t_l, noise=e_l, loss=loss.detach(), data_loss=torch.tensor(data_l),
+                                    residual_abs=torch.tensor(res_l), grad_norm=gn, **grads))
+    with open(os.path.join(OUT, 'params_without_grad.txt'), 'w') as f:
+        f.write('\n'.join(nograd) + '\n')
+
+    # ---- sample-mode loss (A12: ddim_sample_x0, ddim_steps=0) ---------------------------------
+    res_s = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True,
+                           device='cpu', bcs='none', domain_length=1., use_ddim_x0=True, ddim_steps=0)
+    torch.manual_seed(321)
+    loss_s, data_s, res_abs_s, _, _ = diff.model_estimation_loss(x0, residual_func=res_s, c_data=1.,
+                                                                 c_residual=1e-3, c_ineq=0., lambda_opt=0.)
+    model.zero_grad()
+    loss_s.backward()
+    torch.manual_seed(321)
+    t_s = torch.randint(0, 100, size=(2,))
+    e_s = torch.randn_like(x0)
+    save('darcy_loss_sample.pt', dict(x0=x0, t=t_s, noise=e_s, loss=loss_s.detach(),
+                                      data_loss=torch.tensor(data_s), residual_abs=torch.tensor(res_abs_s),
+                                      grad_final_w=named['final_conv.1.weight'].grad.clone(),
+                                      grad_init_w=named['init_conv.weight'].grad.clone()))
+
+    # ---- ancestral sampling loop (A11), 6 diffusion steps, B=1 --------------------------------
+    model.eval()
+    d6 = DenoisingDiffusion(6, 'cpu')
+    torch.manual_seed(77)
+    (x_seq, interm), aux = d6.p_sample_loop(None, (1, 2, 64, 64), save_output=True, surpress_noise=True,
+                                            residual_func=res, eval_residuals=True)
+    torch.manual_seed(77)
+    x_T = torch.randn(1, 2, 64, 64)
+    zs = [torch.randn(1, 2, 64, 64) for _ in range(6)]
+    save('sample_loop_6.pt', dict(x_T=x_T, noises=torch.stack(zs), x_final=x_seq[-1], x_after_first=x_seq[1],
+                                  x0_pred_last=interm[-1], residual=aux['residual'].detach()))
+
+    # ---- mechanics residual on given fields (A13) ---------------------------------------------
+    with tempfile.TemporaryDirectory() as td:
+        write_mesh(td)
+        mres = ResidualsMechanics(model=None, pixels_per_dim=64, pixels_at_boundary=True, no_BC_folder=td + '/',
+                                  device='cpu', topopt_eval=False)
+        KE_ref = mres.stiffs.tot_local_stiffness[0].clone()
+        gm = torch.Generator().manual_seed(4)
+        xm = torch.randn(1, 3, 64, 64, generator=gm) * 0.1
+        xm[:, 2] = torch.sigmoid(torch.randn(1, 64, 64, generator=gm))
+        bcs = torch.zeros(1, 4, 65, 65)
+        bcs[:, 0, :, 0] = 1.
+        bcs[:, 1, :, 0] = 1.
+        bcs[:, 1, 64, 10:20] = 1.
+        bcs[:, 3, 20:24, 64] = -1.
+        bcs[:, 2, 0, 30] = 0.5
+        vf = torch.tensor([0.4])
+        xmg = xm.clone().requires_grad_(True)
+        out = mres.compute_residual((xmg, bcs, vf, None), reduce='per-batch', return_optimizer=True,
+                                    return_inequality=True, pass_through=True)
+        wr = torch.randn(out['residual'].shape, generator=gm)
+        ((out['residual'] * wr).sum() + 0.3 * out['optimizer'].sum() + 2.0 * out['inequality'].sum()).backward()
+        save('mechanics_residual.pt', dict(x0_pred=xm, bcs=bcs, vf=vf, residual=out['residual'].detach(),
+                                           compliance=out['optimizer'].detach(), inequality=out['inequality'].detach(),
+                                           KE=KE_ref, cotangent=wr, grad_x0_pred=xmg.grad.clone()))
+
+
+if __name__ == '__main__':
+    main()
