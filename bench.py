@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the PIDM training step (BASELINE.json: "train samples/s Darcy 64x64 PIDM at 1/2/4/8 B200;
+residual-kernel HBM GB/s").
+
+    python bench.py --gpus N --steps K --warmup W           # this repo's engine (libpidm kernels)
+    python bench.py --impl reference --steps K --warmup W   # the reference algorithm on the host CPU cores (oracle port)
+
+One step = one iteration of the reference training loop (main.py:157-183): q_sample -> Unet3D(dim=32) -> x0_hat ->
+Darcy residual -> data + residual loss -> backward -> clip(1.0) -> Adam(1e-4) -> EMA(0.99), batch 32 per GPU,
+synthetic 64x64 fields, random-init weights, bf16 GEMM operands / activations with fp32 accumulation.
+Prints ONE JSON line (rank 0)."""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PER_GPU_BATCH = 32
+METRIC = 'train samples/s Darcy 64x64 PIDM'
+FWD_GFLOP_PER_SAMPLE = 3.98      # SURVEY.md section 3.2 (conv3x3 2.40, 1x1 0.96, attention einsums 0.36, 4x4 0.20, rest)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_tflops=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained'),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of the local GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as ex:          # NVML missing: report that instead of inventing numbers
+            self.nv, self.err = None, repr(ex)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                 'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                    'note': 'no NVML samples' + (': ' + self.err if self.nv is None else '')}
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference training iteration on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch=PER_GPU_BATCH):
+    from oracle import pidm_oracle as O
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    cfg = O.unet_config(dim=32, channels=2)
+    sd = O.make_test_state_dict(cfg, 0)
+    sdr = {k: v.clone().requires_grad_('freqs' not in k) for k, v in sd.items()}
+    train = [v for v in sdr.values() if v.requires_grad]
+    m = [torch.zeros_like(p) for p in train]
+    v = [torch.zeros_like(p) for p in train]
+    ema = [p.detach().clone() for p in train]
+    tables = O.diffusion_tables(100)
+    torch.manual_seed(0)
+    x0 = torch.randn(batch, 2, 64, 64)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        t = torch.randint(0, 100, (batch,))
+        e = torch.randn_like(x0)
+        for p in train:
+            p.grad = None
+        loss, _ = O.darcy_training_loss(sdr, cfg, x0, t, e, tables, 1.0, 1e-3)
+        loss.backward()
+        with torch.no_grad():
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in train]
+            O.adam_ema_step(train, grads, m, v, ema, it + 1)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=batch / sec, unit='samples/s', cores=ncores, kind='port', ms_per_step=sec * 1e3,
+                sample=f'{steps} training iterations at batch {batch} after {warmup} warm-up, torch {torch.__version__} '
+                       f'CPU, {ncores} threads (oracle/pidm_oracle.py restatement of main.py:157-183)')
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    r = cpu_reference_steps(steps, warmup)
+    out = {'metric': METRIC, 'value': r['value'], 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': steps,
+           'warmup': warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+           'config': {'workload': 'Darcy 64x64 PIDM train step (mean-mode x0), Unet3D dim=32, batch 32, host CPU',
+                      'global_batch': PER_GPU_BATCH, 'note': 'bounded sample: steps/warmup clamped to <=5/<=2'},
+           'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+           'e2e': {'value': r['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------
+def conv_flops(args_tuple):
+    return 0
+
+
+def breakdown_one_step(engine, x0):
+    """Per-entry-point device time of ONE eager step, CUDA events on the launching stream around every libpidm call."""
+    from physicsinformeddiffusionmodels_b200 import _lib, ops, packing, denoising_utils, engine as eng_mod, residuals_darcy
+    records = []
+    orig = _lib.call
+
+    def timed(name, *a):
+        if name in _lib._VALUE_RETURN:
+            return orig(name, *a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(name, *a)
+        e1.record()
+        records.append((name, a, e0, e1))
+        return r
+    mods = [ops, packing, denoising_utils, eng_mod]
+    for mo in mods:
+        mo.call = timed
+    try:
+        engine._step_body(x0)
+        torch.cuda.synchronize()
+    finally:
+        for mo in mods:
+            mo.call = orig
+    agg = {}
+    for name, a, e0, e1 in records:
+        ms = e0.elapsed_time(e1)
+        flop = 0.0
+        if name in ('pidm_conv2d_tc',):
+            B, H, W, Cin, Cout, KH, KW = a[5], a[6], a[7], a[8], a[9], a[10], a[11]
+            flop = 2.0 * B * H * W * Cout * KH * KW * Cin
+        elif name == 'pidm_conv2d_simt':
+            B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[5], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
+            taps = KH * KW / (stride * stride) if tr else KH * KW       # useful taps of the transposed gather
+            flop = 2.0 * B * Ho * Wo * Cout * taps * Cin
+        elif name == 'pidm_conv2d_wgrad_simt':
+            B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[4], a[7], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
+            taps = KH * KW / (stride * stride) if tr else KH * KW
+            flop = 2.0 * B * Ho * Wo * Cout * taps * Cin
+        d = agg.setdefault(name, {'ms': 0.0, 'calls': 0, 'flop': 0.0})
+        d['ms'] += ms
+        d['calls'] += 1
+        d['flop'] += flop
+    return agg
+
+
+def residual_kernel_sweep(pk):
+    """Standalone HBM sweep of the Darcy residual kernel at B = 32768 (2.7 GB working set >> 126 MB L2)."""
+    from physicsinformeddiffusionmodels_b200 import ops
+    from physicsinformeddiffusionmodels_b200._lib import call, stream
+    Bs = 32768
+    x = torch.randn(Bs, 2, 64, 64, device='cuda')
+    fs = torch.zeros(4096, device='cuda')
+    fs[:8 * 64].view(8, 64)[:, :8] = 10.0
+    r = torch.empty(Bs, 4096, 3, device='cuda')
+    res = {}
+    for mode in ('fwd', 'loss'):
+        if mode == 'loss':
+            tgt = torch.randn_like(x)
+            t = torch.randint(0, 100, (Bs,), device='cuda')
+            tab = torch.rand(100, device='cuda') + 0.1
+            sums = torch.zeros(3, device='cuda')
+            gx = torch.empty_like(x)
+            fn = lambda: call('pidm_darcy_pidm_loss', x, x, tgt, fs, t, tab, tab, 1.0, 1e-3, sums, gx, None, Bs, 64, 1.0,
+                              1, 1, stream())
+            alg_bytes = Bs * (2 * 4096 * 4 * 3)        # read x0_hat + target, write gradient
+        else:
+            fn = lambda: call('pidm_darcy_residual_fwd', x, fs, r, Bs, 64, 1.0, 1, 1, stream())
+            alg_bytes = Bs * 81920                     # read 2*P^2*4, write 3*P^2*4 per sample
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        res[mode] = dict(ms=ms, gbs=alg_bytes / ms / 1e6, bytes=alg_bytes)
+    g = res['fwd']['gbs']
+    return {'bound': 'hbm', 'kernel': 'darcy_kernel<0> (pidm_darcy_residual_fwd), B=32768 standalone sweep',
+            'achieved': g, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': g / pk['hbm_gbs'], 'traffic': None,
+            'peak_source': pk['source'], 'ms_per_launch': res['fwd']['ms'], 'algorithmic_bytes': res['fwd']['bytes'],
+            'fused_loss_grad_variant': {'achieved': res['loss']['gbs'], 'frac': res['loss']['gbs'] / pk['hbm_gbs'],
+                                        'ms_per_launch': res['loss']['ms'], 'algorithmic_bytes': res['loss']['bytes']}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    import torch.distributed as dist
+    from physicsinformeddiffusionmodels_b200 import _lib, ops
+    from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
+    from physicsinformeddiffusionmodels_b200.engine import TrainEngine
+    from physicsinformeddiffusionmodels_b200.residuals_darcy import ResidualsDarcy
+    from physicsinformeddiffusionmodels_b200.unet_model import Unet3D
+    assert torch.cuda.is_available(), 'bench.py (b200 arm) needs a CUDA device; there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)'
+    ops.set_precision('bf16')
+    torch.manual_seed(0)                              # identical initial weights on every rank
+    model = Unet3D(dim=32, channels=2).to(dev)
+    diff = DenoisingDiffusion(100, dev)
+    res = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True, device=dev,
+                         bcs='none', domain_length=1.)
+    eng = TrainEngine(model, diff, res, lr=1e-4, max_norm=1.0, ema_mu=0.99, c_data=1.0, c_residual=1e-3,
+                      use_graph=not args.no_graph, world=world)
+    torch.manual_seed(1234 + rank)                    # different data / noise per rank
+    B = PER_GPU_BATCH
+    x0_dev = torch.randn(B, 2, 64, 64, device=dev)
+    x0_host = torch.randn(B, 2, 64, 64).pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.step(x0_dev)
+    barrier()
+    launches0 = _lib.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = eng.step(x0_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    last_loss = float(out[0].item())
+    # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ------------------------------------
+    for _ in range(3):
+        x0_dev.copy_(x0_host, non_blocking=True)
+        loss_host.copy_(eng.step(x0_dev)[0].reshape(1), non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        x0_dev.copy_(x0_host, non_blocking=True)
+        loss_host.copy_(eng.step(x0_dev)[0].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()    # the caller reads the loss every step
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    # kernels per step: count libpidm entry calls of one eager step (each call launches >= 1 kernel)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    extra = {}
+    if rank == 0:
+        pk = peaks()
+        c0 = _lib.launch_count
+        agg = breakdown_one_step(eng, x0_dev)
+        calls_per_step = _lib.launch_count - c0
+        total_ms = sum(d['ms'] for d in agg.values())
+        top = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
+        name, d = top[0]
+        tensor_names = ('pidm_conv2d_tc', 'pidm_conv2d_simt', 'pidm_conv2d_wgrad_simt')
+        if name in tensor_names and d['flop'] > 0:
+            ach = d['flop'] / (d['ms'] * 1e-3) / 1e12
+            peak = pk['bf16_sustained'] or pk['bf16_tflops']
+            roof = {'bound': 'tensor', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': ach / peak, 'traffic': None, 'launches_per_step': d['calls'],
+                    'share_of_step_kernel_time': d['ms'] / total_ms, 'peak_source': pk['source'] + ', sustained figure',
+                    'how': 'algorithmic 2*M*N*K FLOPs of every launch of this entry point in one eager step / '
+                           'CUDA-event time around those launches'}
+        else:
+            roof = {'bound': 'hbm', 'kernel': name, 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
+                    'traffic': None, 'share_of_step_kernel_time': d['ms'] / total_ms}
+        extra['roofline'] = roof
+        extra['roofline_residual'] = residual_kernel_sweep(pk)
+        extra['kernel_time_breakdown_ms'] = {k: {'ms': round(v['ms'], 4), 'calls': v['calls'],
+                                                 'tflops': (v['flop'] / (v['ms'] * 1e-3) / 1e12) if v['flop'] else None}
+                                             for k, v in top[:12]}
+        extra['gpu_launches'] = calls_per_step * args.steps * world
+        extra['launches_note'] = (f'{calls_per_step} libpidm entry-point calls per step per GPU (each issues 1-3 kernels); '
+                                  'replayed from a CUDA graph' if not args.no_graph else 'eager')
+        if not args.no_cpu_baseline:
+            cb = cpu_reference_steps(3, 1)
+            extra['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        sps = world * B * args.steps / (ms * 1e-3)
+        sps_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        tflops = 3 * FWD_GFLOP_PER_SAMPLE * 1e9 * sps / 1e12
+        out = {'metric': METRIC, 'value': sps, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+               'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+               'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+               'config': {'workload': 'Darcy 64x64 PIDM train step: q_sample + Unet3D(dim=32,ch=2) fwd/bwd + Darcy '
+                                      'residual loss + clip + Adam + EMA (configs[1])',
+                          'global_batch': world * B, 'per_gpu_batch': B, 'parallelism': f'dp{world}',
+                          'cuda_graph': not args.no_graph,
+                          'l2': 'no explicit flush: one step streams >1 GB of activations (qkv alone 201 MB) through the '
+                                '126 MB L2, so weights/activations are cold at every layer',
+                          'model_tflops_at_value': tflops, 'last_loss': last_loss},
+               'clocks': clocks,
+               'e2e': {'value': sps_e2e, 'unit': 'samples/s', 'ms_per_step': ms_e2e / args.steps,
+                       'h2d_bytes_per_step': world * x0_host.numel() * 4, 'd2h_bytes_per_step': world * 4,
+                       'api': 'pinned host batch -> TrainEngine.step -> loss read back, every step'}}
+        out.update(extra)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -18,12 +18,18 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = os.environ.get('PIDM_REFERENCE', '/root/reference')
-sys.path.insert(0, ROOT)
+# NOTE: the repo root must NOT be importable here: its `src/` drop-in package (a regular package) would shadow
+# the reference's `src/` (a namespace package) regardless of path order.
+sys.path = [p for p in sys.path if os.path.abspath(p or '.') != ROOT]
 sys.path.insert(0, os.path.join(HERE, 'ref_shims'))
 sys.path.insert(0, REF)
 warnings.filterwarnings('ignore')
 
-from oracle import pidm_oracle as O  # noqa: E402
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location('pidm_oracle', os.path.join(HERE, 'pidm_oracle.py'))
+O = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(O)
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
@@ -71,6 +77,8 @@ def write_mesh(folder, nel=64):
 def main():
     torch.set_num_threads(8)
     from src.unet_model import Unet3D
+    import src.unet_model as _ref_mod
+    assert os.path.abspath(_ref_mod.__file__).startswith(os.path.abspath(REF)), _ref_mod.__file__
     from src.denoising_utils import DenoisingDiffusion
     from src.residuals_darcy import ResidualsDarcy
     from src.residuals_mechanics_K import ResidualsMechanics
@@ -79,6 +87,11 @@ def main():
     for n in (100, 250):
         d = DenoisingDiffusion(n, 'cpu')
         save(f'schedule_{n}.pt', {k: v.clone() for k, v in d.diff_dict.items()})
+
+    # ---- default-init checksums under seed 0 (holder construction order = RNG order) --------------
+    torch.manual_seed(0)
+    m0 = Unet3D(dim=32, channels=2)
+    save('unet_init_seed0.pt', {k: torch.stack([v.double().sum(), v.double().abs().sum()]) for k, v in m0.state_dict().items()})
 
     # ---- U-Net forward with taps (A6) ---------------------------------------------------------
     cfg = O.unet_config(dim=32, channels=2)

@@ -1,0 +1,273 @@
+// Generic implicit-GEMM convolution on NHWC activations (fp32 accumulate, CUDA cores).
+// This is the geometry-complete path: any KHxKW / stride / padding, regular ("gather from input") or
+// transposed addressing, forward / dgrad / wgrad, fp32 or bf16 activations.  It is the parity anchor
+// for the tcgen05 tile kernel in conv_tc.cu (which takes the stride-1 layers that carry the FLOPs) and
+// runs the layers that kernel does not cover (7x7 stem, 4x4/s2 down, 4x4/s2 transposed up, wgrad).
+//
+//   y[m, n] = sum_k A(m, k) * Wp[n, k] (+ bias[n]) (+ residual[m, n]),  m = (b, oh, ow),  k = tap*Cin + c
+//   regular    : A(m,k) = x[b, oh*s - p + r, ow*s - p + q, c]
+//   transposed : A(m,k) = x[b, (oh + p - r)/s, (ow + p - q)/s, c]   when divisible and in range
+// Forward conv = regular; its dgrad = transposed over dy.  ConvTranspose forward = transposed; its dgrad =
+// regular over dy.  Packed weights Wp[n][tap*Cin + c] are produced by pidm_pack_weights.
+#include "common.cuh"
+#include "pidm.h"
+
+namespace pidm {
+
+struct ConvGeom {
+    int B, H, W, Cin;     // input  [B,H,W,Cin]
+    int Ho, Wo, Cout;     // output [B,Ho,Wo,Cout]
+    int KH, KW, stride, pad, transposed;
+};
+
+constexpr int CS_BM = 64, CS_BN = 64, CS_BK = 16, CS_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ void gather_a4(const T* __restrict__ x, const ConvGeom& g, bool m_ok, int b, int oh, int ow,
+                                          int k, int K, float v[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (!m_ok || k >= K) return;
+    int tap = k / g.Cin, c = k - tap * g.Cin;
+    int r = tap / g.KW, q = tap - r * g.KW;
+    int ih, iw;
+    if (!g.transposed) {
+        ih = oh * g.stride - g.pad + r;
+        iw = ow * g.stride - g.pad + q;
+        if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return;
+    } else {
+        int th = oh + g.pad - r, tw = ow + g.pad - q;
+        if (th < 0 || tw < 0) return;
+        if (g.stride > 1) {
+            if ((th % g.stride) || (tw % g.stride)) return;
+            ih = th / g.stride; iw = tw / g.stride;
+        } else { ih = th; iw = tw; }
+        if (ih >= g.H || iw >= g.W) return;
+    }
+    ld4(x + (((size_t)b * g.H + ih) * g.W + iw) * g.Cin + c, v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS) conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ wp,
+                                                               const float* __restrict__ bias,
+                                                               const T* __restrict__ residual, T* __restrict__ y,
+                                                               ConvGeom g) {
+    __shared__ __align__(16) float As[CS_BK][CS_BM + 4];
+    __shared__ __align__(16) float Bs[CS_BK][CS_BN + 4];
+    const int tid = threadIdx.x;
+    const long long M = (long long)g.B * g.Ho * g.Wo;
+    const int K = g.KH * g.KW * g.Cin;
+    const long long m0 = (long long)blockIdx.x * CS_BM;
+    const int n0 = blockIdx.y * CS_BN;
+    // loader coordinates
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    const long long lm = m0 + lrow;
+    const bool m_ok = lm < M;
+    int lb = 0, loh = 0, low = 0;
+    if (m_ok) {
+        lb = (int)(lm / (g.Ho * g.Wo));
+        int rem = (int)(lm - (long long)lb * g.Ho * g.Wo);
+        loh = rem / g.Wo; low = rem - loh * g.Wo;
+    }
+    const int ln = n0 + lrow;
+    const bool n_ok = ln < g.Cout;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += CS_BK) {
+        float a[4], w[4];
+        gather_a4(x, g, m_ok, lb, loh, low, k0 + lk, K, a);
+        if (n_ok && k0 + lk < K) ld4(wp + (size_t)ln * K + k0 + lk, w);
+        else w[0] = w[1] = w[2] = w[3] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { As[lk + j][lrow] = a[j]; Bs[lk + j][lrow] = w[j]; }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CS_BK; ++kk) {
+            float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += aa[i] * bb[j];
+        }
+    }
+    const int n = n0 + tx * 4;
+    if (n < g.Cout) {
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias) { bv[0] = bias[n]; bv[1] = bias[n + 1]; bv[2] = bias[n + 2]; bv[3] = bias[n + 3]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            long long m = m0 + ty * 4 + i;
+            if (m >= M) continue;
+            float o[4] = {acc[i][0] + bv[0], acc[i][1] + bv[1], acc[i][2] + bv[2], acc[i][3] + bv[3]};
+            if (residual) {
+                float r[4];
+                ld4(residual + m * g.Cout + n, r);
+                o[0] += r[0]; o[1] += r[1]; o[2] += r[2]; o[3] += r[3];
+            }
+            st4(y + m * g.Cout + n, o);
+        }
+    }
+}
+
+// wgrad: dW[n][tap][c] += sum_m dy[m][n] * A(m, tap*Cin + c); written (atomicAdd) into the framework weight
+// layout through strides:  index = n*s_n + c*s_c + tap.   dbias[n] += sum_m dy[m][n].
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS) conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                     float* __restrict__ dw, float* __restrict__ dbias,
+                                                                     ConvGeom g, int c_real, long long s_n,
+                                                                     long long s_c, int m_per_split) {
+    __shared__ __align__(16) float Ds[CS_BK][CS_BN + 4];   // [mm][co]
+    __shared__ __align__(16) float As[CS_BK][CS_BM + 4];   // [mm][k]
+    const int tid = threadIdx.x;
+    const long long M = (long long)g.B * g.Ho * g.Wo;
+    const int K = g.KH * g.KW * g.Cin;
+    const int k0 = blockIdx.x * CS_BM;      // k tile (64 wide)
+    const int n0 = blockIdx.y * CS_BN;      // co tile
+    const long long m_begin = (long long)blockIdx.z * m_per_split;
+    long long m_end = m_begin + m_per_split;
+    if (m_end > M) m_end = M;
+    const int lmm = tid >> 4, lq = (tid & 15) * 4;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (long long mb = m_begin; mb < m_end; mb += CS_BK) {
+        long long m = mb + lmm;
+        bool m_ok = m < m_end;
+        int b = 0, oh = 0, ow = 0;
+        if (m_ok) {
+            b = (int)(m / (g.Ho * g.Wo));
+            int rem = (int)(m - (long long)b * g.Ho * g.Wo);
+            oh = rem / g.Wo; ow = rem - oh * g.Wo;
+        }
+        float a[4], d[4];
+        gather_a4(x, g, m_ok, b, oh, ow, k0 + lq, K, a);
+        if (m_ok && n0 + lq < g.Cout) ld4(dy + m * g.Cout + n0 + lq, d);
+        else d[0] = d[1] = d[2] = d[3] = 0.f;
+        __syncthreads();
+        *reinterpret_cast<float4*>(&As[lmm][lq]) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(&Ds[lmm][lq]) = make_float4(d[0], d[1], d[2], d[3]);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CS_BK; ++kk) {
+            float4 dv = *reinterpret_cast<const float4*>(&Ds[kk][ty * 4]);
+            float4 av = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+            float dd[4] = {dv.x, dv.y, dv.z, dv.w}, aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bacc[i] += dd[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += dd[i] * aa[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int n = n0 + ty * 4 + i;
+        if (n >= g.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + tx * 4 + j;
+            if (k >= K) continue;
+            int tap = k / g.Cin, c = k - tap * g.Cin;
+            if (c < c_real) atomicAdd(dw + (long long)n * s_n + (long long)c * s_c + tap, acc[i][j]);
+        }
+        if (dbias && blockIdx.x == 0 && tx == 0) atomicAdd(dbias + n, bacc[i]);
+    }
+}
+
+// ---- weight packing (framework fp32 layout -> Wp[n][tap*Cpad + c] in the activation dtype) ----------------
+struct PackEntry {
+    const float* src;
+    void* dst;
+    long long s_n, s_c;     // src index = n*s_n + c*s_c + tap_src
+    int N, C, Cpad, taps;
+    int flip, pad_;         // flip: tap_src = taps-1-tap (180-degree rotated kernel for stride-1 dgrad)
+};
+
+template <typename T>
+__global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
+    const PackEntry e = table[blockIdx.y];
+    const long long total = (long long)e.N * e.taps * e.Cpad;
+    T* dst = reinterpret_cast<T*>(e.dst);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % e.Cpad);
+        long long r = i / e.Cpad;
+        int tap = (int)(r % e.taps);
+        long long n = r / e.taps;
+        int ts = e.flip ? e.taps - 1 - tap : tap;
+        float v = (c < e.C) ? e.src[n * e.s_n + (long long)c * e.s_c + ts] : 0.f;
+        Act<T>::st(dst + i, v);
+    }
+}
+
+static int check_geom(const ConvGeom& g) {
+    PIDM_REQUIRE(g.Cin % 4 == 0 && g.Cout % 4 == 0, "conv: Cin and Cout must be multiples of 4 (Cin=%d Cout=%d)", g.Cin,
+                 g.Cout);
+    PIDM_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.Ho > 0 && g.Wo > 0 && g.stride >= 1, "conv: bad geometry");
+    return 0;
+}
+
+}  // namespace pidm
+using namespace pidm;
+
+extern "C" int pidm_conv2d_simt(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
+                                int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride,
+                                int pad, int transposed, int dtype, void* stream) {
+    ConvGeom g{B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed};
+    if (int e = check_geom(g)) return e;
+    long long M = (long long)B * Ho * Wo;
+    dim3 grid(ceil_div(M, CS_BM), ceil_div(Cout, CS_BN));
+    PIDM_DISPATCH_DTYPE(dtype, (conv_simt_kernel<T><<<grid, CS_THREADS, 0, (cudaStream_t)stream>>>(
+                                   (const T*)x, (const T*)w_packed, bias, (const T*)residual, (T*)y, g)));
+    PIDM_LAUNCH_CHECK("conv2d_simt");
+    return 0;
+}
+
+// dw / dbias are ACCUMULATED (atomicAdd).  (x, geometry) describe the A-operand gather exactly as in the
+// forward call whose weights are being differentiated; dy is [B,Ho,Wo,Cout].
+extern "C" int pidm_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, float* dbias, int B, int H, int W,
+                                      int Cin, int Cin_real, int Ho, int Wo, int Cout, int KH, int KW, int stride,
+                                      int pad, int transposed, long long w_stride_n, long long w_stride_c, int dtype,
+                                      void* stream) {
+    ConvGeom g{B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed};
+    if (int e = check_geom(g)) return e;
+    long long M = (long long)B * Ho * Wo;
+    int K = KH * KW * Cin;
+    int tiles = ceil_div(K, CS_BM) * ceil_div(Cout, CS_BN);
+    int splits = (148 * 4 + tiles - 1) / tiles;
+    long long max_splits = (M + 255) / 256;
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    int m_per_split = (int)(((M + splits - 1) / splits + CS_BK - 1) / CS_BK * CS_BK);
+    splits = (int)((M + m_per_split - 1) / m_per_split);
+    dim3 grid(ceil_div(K, CS_BM), ceil_div(Cout, CS_BN), splits);
+    PIDM_DISPATCH_DTYPE(dtype, (conv_wgrad_simt_kernel<T><<<grid, CS_THREADS, 0, (cudaStream_t)stream>>>(
+                                   (const T*)x, (const T*)dy, dw, dbias, g, Cin_real, w_stride_n, w_stride_c,
+                                   m_per_split)));
+    PIDM_LAUNCH_CHECK("conv2d_wgrad_simt");
+    return 0;
+}
+
+// table: device array of n_entries PackEntry records (see pidm.h for the layout).
+extern "C" int pidm_pack_weights(const void* table_dev, int n_entries, int dtype, void* stream) {
+    if (n_entries <= 0) return 0;
+    dim3 grid(64, n_entries);
+    PIDM_DISPATCH_DTYPE(dtype, (pack_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                   (const PackEntry*)table_dev)));
+    PIDM_LAUNCH_CHECK("pack_weights");
+    return 0;
+}
+
+extern "C" int pidm_pack_entry_size(void) { return (int)sizeof(PackEntry); }

@@ -1,0 +1,370 @@
+// Stride-1 KxK convolution ("same" padding) on NHWC bf16 activations as an implicit GEMM on the 5th-generation
+// tensor cores (tcgen05), operands staged by TMA, fp32 accumulators in tensor memory (TMEM).
+//
+//   y[b,h,w,n] = sum_{r,q,c} x[b, h+r-pad, w+q-pad, c] * Wp[n][(r*KW+q)*Cin + c] (+ bias[n]) (+ residual[b,h,w,n])
+//
+// This is the kernel behind every 3x3 / 1x1 layer of the U-Net (ResnetBlock convs, res_conv, to_qkv, to_out,
+// reference unet_model.py:227,253,275,279) and behind their dgrad (same kernel, 180-degree-rotated packed weights).
+//
+// Tiling.  GEMM M = 128 output pixels = a TN x TH x TW box of the image (TW = W), N = BN output channels,
+// K = taps * Cin walked in (tap, BK-channel) steps.  For one K step the A operand is ONE 4-D TMA box
+// {BK channels, TW, TH, TN} of the NHWC tensor at spatial offset (r-pad, q-pad): the im2col gather, the zero
+// padding (TMA out-of-bounds fill) and the 128B/64B shared-memory swizzle all happen in the copy engine.
+// The B operand is a 2-D TMA box {BK, BN} of the K-major packed weights.  Both land in the canonical K-major
+// swizzled layout that the UMMA shared-memory descriptors expect, so no thread ever touches the operands.
+//
+// Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane,
+// tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16), warp 2 = TMEM allocator, warps 4-7 = epilogue
+// (tcgen05.ld 32x32b.x32 -> +bias +residual -> bf16 -> 128-bit global stores).  smem full/empty mbarrier ring
+// between producer and MMA, tcgen05.commit releases stages and publishes the accumulator.
+#include "common.cuh"
+#include "pidm.h"
+#include <cuda.h>
+
+namespace pidm {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(tc_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            tc_smem_u32(dst)),
+        "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            tc_smem_u32(dst)),
+        "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major, swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major, 1), [32,46) SBO>>4 = 8 rows * swizzle span,
+//   [46,48) version = 1, [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2 : (SWIZZLE_BYTES == 64 ? 4 : 6);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * SWIZZLE_BYTES) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+struct TcParams {
+    int B, H, W, Cin, Cout;
+    int KH, KW, pad;
+    int TW, TH, TN;        // pixel box; TW*TH*TN == 128
+    int tiles_h;           // H / TH
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* y;
+};
+
+template <int BN, int BK>
+struct TcCfg {
+    static constexpr int SW = BK * 2;                                     // swizzle span in bytes (128 or 64)
+    static constexpr int A_BYTES = TC_BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                const __grid_constant__ CUtensorMap map_w, TcParams p) {
+    using Cfg = TcCfg<BN, BK>;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte aligned operand ring (required by the 128B swizzle atoms)
+    const uint32_t raw_addr = tc_smem_u32(smem_raw);
+    const uint32_t pad_bytes = (1024 - (raw_addr & 1023)) & 1023;
+    unsigned char* ring = smem_raw + pad_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
+    uint64_t* acc_full = bars + 2 * Cfg::STAGES; // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, n0 = blockIdx.y * BN;
+    const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
+    const int b0 = tb * p.TN, h0 = th_idx * p.TH;
+    const int kc_per_tap = p.Cin / BK;
+    const int n_iters = p.KH * p.KW * kc_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+        tc_mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // TMEM allocation: BN fp32 columns (power of two >= 32), whole warp executes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)),
+                     "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % Cfg::STAGES;
+                const uint32_t ph = (it / Cfg::STAGES) & 1;
+                tc_mbar_wait(&empty[s], ph ^ 1);
+                const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
+                const int r = tap / p.KW, q = tap - r * p.KW;
+                unsigned char* a_dst = ring + s * Cfg::STAGE_BYTES;
+                unsigned char* b_dst = a_dst + Cfg::A_BYTES;
+                tc_mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                tma_load_4d(a_dst, &map_x, &full[s], kc * BK, q - p.pad, h0 + r - p.pad, b0);
+                tma_load_2d(b_dst, &map_w, &full[s], tap * p.Cin + kc * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+        // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % Cfg::STAGES;
+            const uint32_t ph = (it / Cfg::STAGES) & 1;
+            tc_mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t a_addr = tc_smem_u32(ring + s * Cfg::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = umma_desc<Cfg::SW>(a_addr + k * 32);
+                    const uint64_t db = umma_desc<Cfg::SW>(b_addr + k * 32);
+                    const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
+                        "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                        : "memory");
+                }
+                // release the smem stage once the MMAs that read it have completed
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 tc_smem_u32(&empty[s]))
+                             : "memory");
+                if (it == n_iters - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     tc_smem_u32(acc_full))
+                                 : "memory");
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual) -> bf16 -> global =====
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = quarter * 32 + lane;            // accumulator row = pixel within the tile
+        const int tn = m / (p.TH * p.TW);
+        const int rem = m - tn * p.TH * p.TW;
+        const int th = rem / p.TW, tw = rem - th * p.TW;
+        const int b = b0 + tn, h = h0 + th;
+        const bool row_ok = (b < p.B) && (h < p.H);
+        const size_t row_off = (((size_t)b * p.H + h) * p.W + tw) * p.Cout + n0;
+        tc_mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row_ok) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
+                        f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                    }
+                }
+                if (p.residual) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float rv[8];
+                        ld8(p.residual + row_off + c + j, rv);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[j + k] += rv[k];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) st8(p.y + row_off + c + j, f + j);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+struct TcPlan {
+    int TW, TH, TN, BN, BK;
+};
+
+static bool tc_plan(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, TcPlan& pl) {
+    if (KH != KW || (KH & 1) == 0 || 2 * pad != KH - 1) return false;
+    if (W > 128 || (128 % W) != 0) return false;
+    if (Cin % 32 != 0 || Cout % 32 != 0) return false;
+    pl.TW = W;
+    int th = 128 / W;
+    if (th > H) th = H;
+    if (H % th != 0) return false;
+    pl.TH = th;
+    pl.TN = 128 / (pl.TW * pl.TH);
+    if (pl.TW * pl.TH * pl.TN != 128) return false;
+    pl.BK = (Cin % 64 == 0) ? 64 : 32;
+    const long long m_tiles = (long long)((B + pl.TN - 1) / pl.TN) * (H / pl.TH);
+    const int cands[4] = {256, 128, 64, 32};
+    pl.BN = 0;
+    for (int i = 0; i < 4; ++i) {
+        int bn = cands[i];
+        if (Cout % bn != 0) continue;
+        pl.BN = bn;
+        if (m_tiles * (Cout / bn) >= 148) break;    // widest tile that still fills the machine
+    }
+    return pl.BN != 0;
+}
+
+template <int BN, int BK>
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = TcCfg<BN, BK>;
+    static bool attr = false;
+    if (!attr) {
+        PIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    conv_tc_kernel<BN, BK><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+    PIDM_LAUNCH_CHECK("conv2d_tc");
+    return 0;
+}
+
+}  // namespace pidm
+using namespace pidm;
+
+extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad) {
+    TcPlan pl;
+    return tc_plan(B, H, W, Cin, Cout, KH, KW, pad, pl) ? 1 : 0;
+}
+
+extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
+                              int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
+    TcPlan pl;
+    PIDM_REQUIRE(tc_plan(B, H, W, Cin, Cout, KH, KW, pad, pl), "conv2d_tc: unsupported geometry");
+    EncodeTiledFn enc = get_encode();
+    PIDM_REQUIRE(enc != nullptr, "conv2d_tc: cuTensorMapEncodeTiled is not available from the driver");
+    PIDM_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "conv2d_tc: operands must be 16-byte aligned");
+    CUtensorMap mx, mw;
+    const CUtensorMapSwizzle sw = pl.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)pl.BK, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)pl.TN};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    }
+    {
+        const int K = KH * KW * Cin;
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)pl.BK, (cuuint32_t)pl.BN};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+    }
+    TcParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = H / pl.TH;
+    p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = (__nv_bfloat16*)y;
+    dim3 grid(((B + pl.TN - 1) / pl.TN) * p.tiles_h, Cout / pl.BN);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TC_CASE(bn, bk) if (pl.BN == bn && pl.BK == bk) return launch_tc<bn, bk>(mx, mw, p, grid, st)
+    TC_CASE(256, 64); TC_CASE(128, 64); TC_CASE(64, 64); TC_CASE(32, 64);
+    TC_CASE(256, 32); TC_CASE(128, 32); TC_CASE(64, 32); TC_CASE(32, 32);
+#undef TC_CASE
+    return set_error(2, "conv2d_tc: no kernel for BN=%d BK=%d", pl.BN, pl.BK);
+}

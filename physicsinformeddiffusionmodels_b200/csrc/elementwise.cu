@@ -1,0 +1,338 @@
+// HBM-bound element-wise pieces of the PIDM step: q_sample, ancestral posterior step, layout changes
+// (NCHW fp32 <-> NHWC activations), channel concat/split, residual add, and the tiny-N output head
+// (final 1x1 conv -> NCHW fp32, optional sigmoid on the last channel).  128-bit vectorised accesses.
+#include "common.cuh"
+#include "pidm.h"
+
+namespace pidm {
+
+// ---- q_sample: x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) eps   (denoising_utils.py:373-378, :633-638) -------
+__global__ void qsample_kernel(const float4* __restrict__ x0, const float4* __restrict__ eps,
+                               const long long* __restrict__ t, const float* __restrict__ sa,
+                               const float* __restrict__ sb, float4* __restrict__ xt, int per_sample4, long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        int b = (int)(i / per_sample4);
+        long long tb = t[b];
+        float a = sa[tb], s = sb[tb];
+        float4 x = x0[i], e = eps[i];
+        xt[i] = make_float4(a * x.x + s * e.x, a * x.y + s * e.y, a * x.z + s * e.z, a * x.w + s * e.w);
+    }
+}
+
+// ---- posterior step: x_{t-1} = c1 x0_pred + c2 x_t + sigma z     (denoising_utils.py:441-455) ------------
+__global__ void posterior_kernel(const float4* __restrict__ xt, const float4* __restrict__ x0p,
+                                 const float4* __restrict__ z, float4* __restrict__ out, float c1, float c2, float sig,
+                                 long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 a = xt[i], b = x0p[i], n = z[i];
+        out[i] = make_float4(c1 * b.x + c2 * a.x + sig * n.x, c1 * b.y + c2 * a.y + sig * n.y,
+                             c1 * b.z + c2 * a.z + sig * n.z, c1 * b.w + c2 * a.w + sig * n.w);
+    }
+}
+
+// ---- NCHW fp32 -> NHWC (channel-padded) activations -----------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int Cpad,
+                                    long long total) {  // total = B*HW*Cpad
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cpad);
+        long long pix = i / Cpad;
+        int hw = (int)(pix % HW);
+        long long b = pix / HW;
+        float v = (c < C) ? src[(b * C + c) * HW + hw] : 0.f;
+        Act<T>::st(dst + i, v);
+    }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW, int Cpad,
+                                    long long total) {  // total = B*C*HW
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int hw = (int)(i % HW);
+        long long bc = i / HW;
+        int c = (int)(bc % C);
+        long long b = bc / C;
+        dst[i] = Act<T>::ld(src + (b * HW + hw) * Cpad + c);
+    }
+}
+
+// ---- add, concat, split along channels (NHWC rows) ------------------------------------------------------
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n8) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+         i += (long long)gridDim.x * blockDim.x) {
+        float x[8], y[8];
+        ld8(a + i * 8, x);
+        ld8(b + i * 8, y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] += y[k];
+        st8(o + i * 8, x);
+    }
+}
+// out[m, 0:Ca] = a[m], out[m, Ca:Ca+Cb] = b[m]   (channels multiples of 8)
+template <typename T>
+__global__ void concat_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int Ca8, int Cb8,
+                              long long rows) {
+    const int Ct8 = Ca8 + Cb8;
+    const long long total = rows * Ct8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long m = i / Ct8;
+        int c = (int)(i % Ct8);
+        float v[8];
+        if (c < Ca8) ld8(a + (m * Ca8 + c) * 8, v);
+        else ld8(b + (m * Cb8 + (c - Ca8)) * 8, v);
+        st8(o + i * 8, v);
+    }
+}
+template <typename T>
+__global__ void split_kernel(const T* __restrict__ g, T* __restrict__ ga, T* __restrict__ gb, int Ca8, int Cb8,
+                             long long rows) {
+    const int Ct8 = Ca8 + Cb8;
+    const long long total = rows * Ct8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long m = i / Ct8;
+        int c = (int)(i % Ct8);
+        float v[8];
+        ld8(g + i * 8, v);
+        if (c < Ca8) st8(ga + (m * Ca8 + c) * 8, v);
+        else st8(gb + (m * Cb8 + (c - Ca8)) * 8, v);
+    }
+}
+
+// out = a_b x + b_b y + c_b z with per-sample coefficients (DDIM jump inside ddim_sample_x0, denoising_utils.py:771-785)
+__global__ void axpby_ps_kernel(const float* __restrict__ a, const float4* __restrict__ x, const float* __restrict__ b,
+                                const float4* __restrict__ y, const float* __restrict__ c, const float4* __restrict__ z,
+                                float4* __restrict__ out, int per4, long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        int s = (int)(i / per4);
+        float ca = a[s], cb = b[s], cc = c[s];
+        float4 xv = x[i], yv = y[i], zv = z[i];
+        out[i] = make_float4(ca * xv.x + cb * yv.x + cc * zv.x, ca * xv.y + cb * yv.y + cc * zv.y,
+                             ca * xv.z + cb * yv.z + cc * zv.z, ca * xv.w + cb * yv.w + cc * zv.w);
+    }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, const float* __restrict__ alpha, long long n) {
+    const float a = *alpha;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] *= a;
+}
+
+// ---- output head: y[b,o,hw] = sum_c x[b,hw,c] w[o,c] + bias[o]; sigmoid on last channel if asked --------
+//      (final_conv.1 of the reference, unet_model.py:517 and :619-621).  O <= 4, C multiple of 8.
+template <typename T, int O>
+__global__ void head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ y, int C, int HW, long long M, int sigmoid_last) {
+    extern __shared__ float sw[];  // [O][C]
+    for (int i = threadIdx.x; i < O * C; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        float acc[O];
+#pragma unroll
+        for (int o = 0; o < O; ++o) acc[o] = bias[o];
+        const T* xr = x + m * C;
+        for (int c = 0; c < C; c += 8) {
+            float v[8];
+            ld8(xr + c, v);
+#pragma unroll
+            for (int o = 0; o < O; ++o)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[o] += v[k] * sw[o * C + c + k];
+        }
+        long long b = m / HW;
+        int hw = (int)(m % HW);
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            float v = acc[o];
+            if (sigmoid_last && o == O - 1) v = 1.f / (1.f + __expf(-v));
+            y[(b * O + o) * HW + hw] = v;
+        }
+    }
+}
+
+// backward: dx[m,c] = sum_o dz[o,m] w[o,c];  dw[o,c] += sum_m dz[o,m] x[m,c];  db[o] += sum_m dz[o,m]
+// where dz = dy * (sigmoid' on the last channel).  One warp handles 32 pixels; per-CTA smem reduction then atomics.
+template <typename T, int O>
+__global__ void head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y,
+                                const float* __restrict__ dy, T* __restrict__ dx, float* __restrict__ dw,
+                                float* __restrict__ db, int C, int HW, long long M, int sigmoid_last) {
+    extern __shared__ float sm[];   // sw[O*C] | sdw[O*C] | sdb[O]
+    float* sw = sm;
+    float* sdw = sm + O * C;
+    float* sdb = sdw + O * C;
+    for (int i = threadIdx.x; i < O * C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+    if (threadIdx.x < O) sdb[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (long long m0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; m0 < M;
+         m0 += (long long)gridDim.x * blockDim.x) {
+        long long m = m0 + lane;
+        bool ok = m < M;
+        float dz[O];
+        long long b = ok ? m / HW : 0;
+        int hw = ok ? (int)(m % HW) : 0;
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            float g = ok ? dy[(b * O + o) * HW + hw] : 0.f;
+            if (sigmoid_last && o == O - 1 && ok) {
+                float s = y[(b * O + o) * HW + hw];
+                g *= s * (1.f - s);
+            }
+            dz[o] = g;
+        }
+        for (int c = 0; c < C; c += 8) {
+            float v[8], d[8];
+            if (ok) ld8(x + m * C + c, v);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float s = 0.f;
+#pragma unroll
+                for (int o = 0; o < O; ++o) s += dz[o] * sw[o * C + c + k];
+                d[k] = s;
+            }
+            if (ok) st8(dx + m * C + c, d);
+#pragma unroll
+            for (int o = 0; o < O; ++o)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float s = warp_sum(dz[o] * v[k]);
+                    if (lane == 0) atomicAdd(&sdw[o * C + c + k], s);
+                }
+        }
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            float s = warp_sum(dz[o]);
+            if (lane == 0) atomicAdd(&sdb[o], s);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < O * C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+    if (threadIdx.x < O) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
+}
+
+static inline int grid_for(long long n, int block, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace pidm
+using namespace pidm;
+
+extern "C" int pidm_qsample(const float* x0, const float* noise, const long long* t, const float* sqrt_ab,
+                            const float* sqrt_1mab, float* xt, int B, int per_sample, void* stream) {
+    PIDM_REQUIRE(per_sample % 4 == 0, "q_sample: per-sample size must be a multiple of 4");
+    long long total4 = (long long)B * per_sample / 4;
+    qsample_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x0, (const float4*)noise, t, sqrt_ab, sqrt_1mab, (float4*)xt, per_sample / 4, total4);
+    PIDM_LAUNCH_CHECK("qsample");
+    return 0;
+}
+
+extern "C" int pidm_posterior_step(const float* x_t, const float* x0_pred, const float* z, float* out, float coef1,
+                                   float coef2, float sigma, long long n, void* stream) {
+    PIDM_REQUIRE(n % 4 == 0, "posterior_step: size must be a multiple of 4");
+    posterior_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x_t, (const float4*)x0_pred, (const float4*)z, (float4*)out, coef1, coef2, sigma, n / 4);
+    PIDM_LAUNCH_CHECK("posterior_step");
+    return 0;
+}
+
+extern "C" int pidm_nchw_to_nhwc(const float* src, void* dst, int B, int C, int HW, int Cpad, int dtype, void* stream) {
+    long long total = (long long)B * HW * Cpad;
+    PIDM_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   src, (T*)dst, C, HW, Cpad, total)));
+    PIDM_LAUNCH_CHECK("nchw_to_nhwc");
+    return 0;
+}
+
+extern "C" int pidm_nhwc_to_nchw(const void* src, float* dst, int B, int C, int HW, int Cpad, int dtype, void* stream) {
+    long long total = (long long)B * HW * C;
+    PIDM_DISPATCH_DTYPE(dtype, (nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)src, dst, C, HW, Cpad, total)));
+    PIDM_LAUNCH_CHECK("nhwc_to_nchw");
+    return 0;
+}
+
+extern "C" int pidm_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
+    PIDM_REQUIRE(n % 8 == 0, "add: size must be a multiple of 8");
+    PIDM_DISPATCH_DTYPE(dtype, (add_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)a, (const T*)b, (T*)out, n / 8)));
+    PIDM_LAUNCH_CHECK("add");
+    return 0;
+}
+
+extern "C" int pidm_concat_channels(const void* a, const void* b, void* out, long long rows, int Ca, int Cb, int dtype,
+                                    void* stream) {
+    PIDM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat: channel counts must be multiples of 8");
+    long long total = rows * (Ca + Cb) / 8;
+    PIDM_DISPATCH_DTYPE(dtype, (concat_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)a, (const T*)b, (T*)out, Ca / 8, Cb / 8, rows)));
+    PIDM_LAUNCH_CHECK("concat");
+    return 0;
+}
+
+extern "C" int pidm_split_channels(const void* g, void* ga, void* gb, long long rows, int Ca, int Cb, int dtype,
+                                   void* stream) {
+    PIDM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "split: channel counts must be multiples of 8");
+    long long total = rows * (Ca + Cb) / 8;
+    PIDM_DISPATCH_DTYPE(dtype, (split_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)g, (T*)ga, (T*)gb, Ca / 8, Cb / 8, rows)));
+    PIDM_LAUNCH_CHECK("split");
+    return 0;
+}
+
+extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float* b, const float* y, const float* c,
+                                     const float* z, float* out, int B, int per_sample, void* stream) {
+    PIDM_REQUIRE(per_sample % 4 == 0, "axpby_per_sample: per-sample size must be a multiple of 4");
+    long long total4 = (long long)B * per_sample / 4;
+    axpby_ps_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        a, (const float4*)x, b, (const float4*)y, c, (const float4*)z, (float4*)out, per_sample / 4, total4);
+    PIDM_LAUNCH_CHECK("axpby_per_sample");
+    return 0;
+}
+
+extern "C" int pidm_scale_inplace(float* x, const float* alpha_dev, long long n, void* stream) {
+    scale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, alpha_dev, n);
+    PIDM_LAUNCH_CHECK("scale");
+    return 0;
+}
+
+extern "C" int pidm_head_fwd(const void* x, const float* w, const float* bias, float* y, int B, int HW, int C, int O,
+                             int sigmoid_last, int dtype, void* stream) {
+    PIDM_REQUIRE(C % 8 == 0 && O >= 1 && O <= 4, "head: C%%8==0 and 1<=O<=4 required (C=%d O=%d)", C, O);
+    long long M = (long long)B * HW;
+    size_t smem = (size_t)O * C * sizeof(float);
+#define HEAD_F(OO)                                                                                     \
+    PIDM_DISPATCH_DTYPE(dtype, (head_fwd_kernel<T, OO><<<grid_for(M, 256), 256, smem, (cudaStream_t)stream>>>( \
+                                   (const T*)x, w, bias, y, C, HW, M, sigmoid_last)))
+    switch (O) { case 1: HEAD_F(1); break; case 2: HEAD_F(2); break; case 3: HEAD_F(3); break; default: HEAD_F(4); }
+#undef HEAD_F
+    PIDM_LAUNCH_CHECK("head_fwd");
+    return 0;
+}
+
+extern "C" int pidm_head_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw,
+                             float* db, int B, int HW, int C, int O, int sigmoid_last, int dtype, void* stream) {
+    PIDM_REQUIRE(C % 8 == 0 && O >= 1 && O <= 4, "head: C%%8==0 and 1<=O<=4 required (C=%d O=%d)", C, O);
+    long long M = (long long)B * HW;
+    size_t smem = (size_t)(2 * O * C + O) * sizeof(float);
+#define HEAD_B(OO)                                                                                     \
+    PIDM_DISPATCH_DTYPE(dtype, (head_bwd_kernel<T, OO><<<grid_for(M, 256, 148 * 2), 256, smem, (cudaStream_t)stream>>>( \
+                                   (const T*)x, w, y, dy, (T*)dx, dw, db, C, HW, M, sigmoid_last)))
+    switch (O) { case 1: HEAD_B(1); break; case 2: HEAD_B(2); break; case 3: HEAD_B(3); break; default: HEAD_B(4); }
+#undef HEAD_B
+    PIDM_LAUNCH_CHECK("head_bwd");
+    return 0;
+}

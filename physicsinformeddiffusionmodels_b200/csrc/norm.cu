@@ -1,0 +1,396 @@
+// Normalisations of the U-Net on NHWC activations, all statistics in fp32:
+//   * GroupNorm(G) -> (scale+1, shift) FiLM -> SiLU      (Block.forward, reference unet_model.py:233-241)
+//   * channel LayerNorm (gain only, biased variance)     (LayerNorm.forward, unet_model.py:201-210)
+// Forward = one reduction kernel (sum, sum-of-squares per (sample, group), one atomic per CTA per group)
+// + one vectorised apply kernel.  Backward = reduction over pixels of (dz, dz*xhat) per (sample, channel),
+// a tiny per-sample kernel that turns those into parameter / FiLM gradients and group means, and an
+// element-wise dx kernel.  Nothing but the conv output x and the raw sums is saved for backward.
+#include "common.cuh"
+#include "pidm.h"
+
+namespace pidm {
+
+constexpr int NORM_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: sums[b][g][0] += sum x, sums[b][g][1] += sum x^2
+// thread = (row r, octet o); rows advance by rows_per_pass; grid = (chunks, B)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, int HW, int C, int G) {
+    extern __shared__ float sg[];  // [G][2]
+    const int oct = C / 8, cpg = C / G;
+    const int b = blockIdx.y;
+    const int o = threadIdx.x % oct, r0 = threadIdx.x / oct;
+    const int rows_per_pass = blockDim.x / oct;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sg[i] = 0.f;
+    __syncthreads();
+    float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};   // two half-octets (cpg may be 4)
+    const T* xb = x + (size_t)b * HW * C;
+    for (int p = blockIdx.x * rows_per_pass + r0; p < HW; p += gridDim.x * rows_per_pass) {
+        float v[8];
+        ld8(xb + (size_t)p * C + o * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k >> 2] += v[k]; ss[k >> 2] += v[k] * v[k]; }
+    }
+    if (cpg >= 8) {
+        int g = (o * 8) / cpg;
+        atomicAdd(&sg[2 * g], s[0] + s[1]);
+        atomicAdd(&sg[2 * g + 1], ss[0] + ss[1]);
+    } else {  // cpg == 4
+        int g = (o * 8) / cpg;
+        atomicAdd(&sg[2 * g], s[0]); atomicAdd(&sg[2 * g + 1], ss[0]);
+        atomicAdd(&sg[2 * g + 2], s[1]); atomicAdd(&sg[2 * g + 3], ss[1]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], sg[i]);
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const float* sums, int b, int g, int G, float inv_n, float eps, float& mean,
+                                             float& rstd) {
+    float s = sums[((size_t)b * G + g) * 2], ss = sums[((size_t)b * G + g) * 2 + 1];
+    mean = s * inv_n;
+    float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+    rstd = rsqrtf(var + eps);
+}
+
+// y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift )
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ ss /*[B,2C] or null*/,
+                                T* __restrict__ y, int HW, int C, int G, float eps, long long total8) {
+    const int oct = C / 8, cpg = C / G;
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+         i += (long long)gridDim.x * blockDim.x) {
+        int o = (int)(i % oct);
+        long long pix = i / oct;
+        int b = (int)(pix / HW);
+        float v[8];
+        ld8(x + i * 8, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int c0 = o * 8 + h * 4;
+            float mean, rstd;
+            gn_mean_rstd(sums, b, c0 / cpg, G, inv_n, eps, mean, rstd);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int c = c0 + k;
+                float a = (v[h * 4 + k] - mean) * rstd * gamma[c] + beta[c];
+                if (ss) a = a * (ss[(size_t)b * 2 * C + c] + 1.f) + ss[(size_t)b * 2 * C + C + c];
+                v[h * 4 + k] = silu_f(a);
+            }
+        }
+        st8(y + i * 8, v);
+    }
+}
+
+// backward pass 1: S[b][c][0] += sum_pix dz, S[b][c][1] += sum_pix dz*xhat, dz = dy * silu'(z)
+template <typename T>
+__global__ void gn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ ss, float* __restrict__ S, int HW, int C, int G,
+                                     float eps) {
+    extern __shared__ float sc[];  // [C][2]
+    const int oct = C / 8, cpg = C / G;
+    const int b = blockIdx.y;
+    const int o = threadIdx.x % oct, r0 = threadIdx.x / oct;
+    const int rows_per_pass = blockDim.x / oct;
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sc[i] = 0.f;
+    __syncthreads();
+    float mean[2], rstd[2], gm[8], bt[8], s1p[8], sh[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) gn_mean_rstd(sums, b, (o * 8 + h * 4) / cpg, G, inv_n, eps, mean[h], rstd[h]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int c = o * 8 + k;
+        gm[k] = gamma[c]; bt[k] = beta[c];
+        s1p[k] = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        sh[k] = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
+    }
+    float a1[8], a2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+    const size_t base = (size_t)b * HW * C;
+    for (int p = blockIdx.x * rows_per_pass + r0; p < HW; p += gridDim.x * rows_per_pass) {
+        float v[8], d[8];
+        ld8(x + base + (size_t)p * C + o * 8, v);
+        ld8(dy + base + (size_t)p * C + o * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xh = (v[k] - mean[k >> 2]) * rstd[k >> 2];
+            float z = (xh * gm[k] + bt[k]) * s1p[k] + sh[k];
+            float dz = d[k] * silu_grad_f(z);
+            a1[k] += dz; a2[k] += dz * xh;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&sc[(o * 8 + k) * 2], a1[k]); atomicAdd(&sc[(o * 8 + k) * 2 + 1], a2[k]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&S[(size_t)b * 2 * C + i], sc[i]);
+}
+
+// backward pass 2 (one CTA per sample): FiLM grads, parameter grads (atomics over the batch), group means.
+__global__ void gn_bwd_param_kernel(const float* __restrict__ S, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ ss,
+                                    float* __restrict__ dss /*[B,2C] or null*/, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, float* __restrict__ gmean /*[B][G][2]*/, int HW, int C,
+                                    int G) {
+    extern __shared__ float sgm[];  // [G][2]
+    const int b = blockIdx.x, cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sgm[i] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s1 = S[((size_t)b * C + c) * 2], s2 = S[((size_t)b * C + c) * 2 + 1];
+        float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        if (dss) {
+            dss[(size_t)b * 2 * C + c] = gamma[c] * s2 + beta[c] * s1;   // d scale
+            dss[(size_t)b * 2 * C + C + c] = s1;                          // d shift
+        }
+        atomicAdd(&dgamma[c], f * s2);
+        atomicAdd(&dbeta[c], f * s1);
+        atomicAdd(&sgm[(c / cpg) * 2], gamma[c] * f * s1);
+        atomicAdd(&sgm[(c / cpg) * 2 + 1], gamma[c] * f * s2);
+    }
+    __syncthreads();
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gmean[(size_t)b * 2 * G + i] = sgm[i] * inv_n;
+}
+
+// backward pass 3: dx = rstd * (gamma*(1+scale)*dz - m1 - xhat*m2)
+template <typename T>
+__global__ void gn_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ ss, const float* __restrict__ gmean, T* __restrict__ dx,
+                                 int HW, int C, int G, float eps, long long total8) {
+    const int oct = C / 8, cpg = C / G;
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+         i += (long long)gridDim.x * blockDim.x) {
+        int o = (int)(i % oct);
+        long long pix = i / oct;
+        int b = (int)(pix / HW);
+        float v[8], d[8];
+        ld8(x + i * 8, v);
+        ld8(dy + i * 8, d);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int c0 = o * 8 + h * 4, g = c0 / cpg;
+            float mean, rstd;
+            gn_mean_rstd(sums, b, g, G, inv_n, eps, mean, rstd);
+            float m1 = gmean[((size_t)b * G + g) * 2], m2 = gmean[((size_t)b * G + g) * 2 + 1];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int c = c0 + k;
+                float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+                float shv = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
+                float xh = (v[h * 4 + k] - mean) * rstd;
+                float z = (xh * gamma[c] + beta[c]) * f + shv;
+                float dz = d[h * 4 + k] * silu_grad_f(z);
+                v[h * 4 + k] = rstd * (gamma[c] * f * dz - m1 - xh * m2);
+            }
+        }
+        st8(dx + i * 8, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel LayerNorm: y[m,c] = (x[m,c]-mean_m)/sqrt(var_m+eps)*gamma[c]
+// a group of L = min(32, C/8) lanes owns one pixel; lane handles octets lane, lane+L, ...
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool BWD>
+__global__ void ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ gamma,
+                          T* __restrict__ out, float* __restrict__ dgamma, long long M, int C, float eps) {
+    extern __shared__ float sdg[];  // [C] (BWD only)
+    const int oct = C / 8;
+    int L = 1;
+    while (L < 32 && L < oct) L <<= 1;            // power of two
+    const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L, gpw = 32 / L;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    if (BWD) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) sdg[i] = 0.f;
+        __syncthreads();
+    }
+    float dg[4][8];   // up to 4 octets per lane (C <= 1024)
+    if (BWD) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dg[q][k] = 0.f;
+    }
+    const long long stride = (long long)gridDim.x * warps * gpw;
+    const long long first = ((long long)blockIdx.x * warps + warp) * gpw + grp;
+    const long long iters = (M + stride - 1) / stride;   // uniform trip count (shuffles need all lanes)
+    for (long long it = 0; it < iters; ++it) {
+        long long m = first + it * stride;
+        bool ok = m < M;
+        float s = 0.f, ss = 0.f;
+        if (ok)
+            for (int o = sub; o < oct; o += L) {
+                float v[8];
+                ld8(x + m * C + o * 8, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s += v[k]; ss += v[k] * v[k]; }
+            }
+        for (int off = L >> 1; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        }
+        float mean = s / C;
+        float rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+        if (!BWD) {
+            if (ok)
+                for (int o = sub; o < oct; o += L) {
+                    float v[8];
+                    ld8(x + m * C + o * 8, v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * gamma[o * 8 + k];
+                    st8(out + m * C + o * 8, v);
+                }
+        } else {
+            float a = 0.f, bsum = 0.f;   // sum dxhat, sum dxhat*xhat
+            if (ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int o = sub + q * L;
+                    if (o >= oct) break;
+                    float v[8], d[8];
+                    ld8(x + m * C + o * 8, v);
+                    ld8(dy + m * C + o * 8, d);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float xh = (v[k] - mean) * rstd;
+                        float dxh = d[k] * gamma[o * 8 + k];
+                        a += dxh; bsum += dxh * xh;
+                        dg[q][k] += d[k] * xh;
+                    }
+                }
+            }
+            for (int off = L >> 1; off > 0; off >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, off);
+                bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+            }
+            a /= C; bsum /= C;
+            if (ok)
+                for (int o = sub; o < oct; o += L) {
+                    float v[8], d[8];
+                    ld8(x + m * C + o * 8, v);
+                    ld8(dy + m * C + o * 8, d);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float xh = (v[k] - mean) * rstd;
+                        v[k] = rstd * (d[k] * gamma[o * 8 + k] - a - xh * bsum);
+                    }
+                    st8(out + m * C + o * 8, v);
+                }
+        }
+    }
+    if (BWD) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = sub + q * L;
+            if (o < oct) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(&sdg[o * 8 + k], dg[q][k]);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dgamma[i], sdg[i]);
+    }
+}
+
+static int gn_block(int C) {
+    int oct = C / 8;
+    int rows = NORM_THREADS / oct;
+    if (rows < 1) rows = 1;
+    return oct * rows;
+}
+
+}  // namespace pidm
+using namespace pidm;
+
+static int gn_check(int C, int G) {
+    PIDM_REQUIRE(C % 8 == 0 && C / 8 <= 1024 && G > 0 && C % G == 0, "groupnorm: bad C=%d G=%d", C, G);
+    int cpg = C / G;
+    PIDM_REQUIRE(cpg == 4 || cpg % 8 == 0, "groupnorm: channels per group must be 4 or a multiple of 8 (got %d)", cpg);
+    return 0;
+}
+
+// sums [B,G,2] is zeroed here, filled by the stats kernel and must be kept for backward.
+extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const float* beta, const float* scale_shift,
+                                       void* y, float* sums, int B, int HW, int C, int G, float eps, int dtype,
+                                       void* stream) {
+    if (int e = gn_check(C, G)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    PIDM_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), st));
+    const int block = gn_block(C), rows = block / (C / 8);
+    int chunks = ceil_div(HW, rows * 8);
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    long long total8 = (long long)B * HW * C / 8;
+    int g2 = ceil_div(total8, 256);
+    if (g2 > 148 * 16) g2 = 148 * 16;
+    PIDM_DISPATCH_DTYPE(dtype, {
+        gn_stats_kernel<T><<<dim3(chunks, B), block, 2 * G * sizeof(float), st>>>((const T*)x, sums, HW, C, G);
+        gn_apply_kernel<T><<<g2, 256, 0, st>>>((const T*)x, sums, gamma, beta, scale_shift, (T*)y, HW, C, G, eps, total8);
+    });
+    PIDM_LAUNCH_CHECK("groupnorm_silu_fwd");
+    return 0;
+}
+
+// workspace: float[B*C*2 + B*G*2].  dgamma/dbeta are ACCUMULATED (atomicAdd); d_scale_shift is overwritten.
+extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const float* sums, const float* gamma,
+                                       const float* beta, const float* scale_shift, void* dx, float* dgamma,
+                                       float* dbeta, float* d_scale_shift, float* workspace, int B, int HW, int C, int G,
+                                       float eps, int dtype, void* stream) {
+    if (int e = gn_check(C, G)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* S = workspace;
+    float* gmean = workspace + (size_t)B * C * 2;
+    PIDM_CUDA(cudaMemsetAsync(S, 0, (size_t)B * C * 2 * sizeof(float), st));
+    const int block = gn_block(C), rows = block / (C / 8);
+    int chunks = ceil_div(HW, rows * 8);
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    long long total8 = (long long)B * HW * C / 8;
+    int g2 = ceil_div(total8, 256);
+    if (g2 > 148 * 16) g2 = 148 * 16;
+    PIDM_DISPATCH_DTYPE(dtype, {
+        gn_bwd_reduce_kernel<T><<<dim3(chunks, B), block, 2 * C * sizeof(float), st>>>(
+            (const T*)x, (const T*)dy, sums, gamma, beta, scale_shift, S, HW, C, G, eps);
+        gn_bwd_param_kernel<<<B, 256, 2 * G * sizeof(float), st>>>(S, gamma, beta, scale_shift, d_scale_shift, dgamma,
+                                                                  dbeta, gmean, HW, C, G);
+        gn_bwd_dx_kernel<T><<<g2, 256, 0, st>>>((const T*)x, (const T*)dy, sums, gamma, beta, scale_shift, gmean, (T*)dx,
+                                                HW, C, G, eps, total8);
+    });
+    PIDM_LAUNCH_CHECK("groupnorm_silu_bwd");
+    return 0;
+}
+
+extern "C" int pidm_layernorm_c_fwd(const void* x, const float* gamma, void* y, long long M, int C, float eps, int dtype,
+                                    void* stream) {
+    PIDM_REQUIRE(C % 8 == 0 && C <= 1024, "layernorm: C must be a multiple of 8 and <= 1024 (got %d)", C);
+    int oct = C / 8, L = 1;
+    while (L < 32 && L < oct) L <<= 1;
+    long long groups = (M + (32 / L) * 8 - 1) / ((32 / L) * 8);
+    int grid = (int)(groups < 148 * 8 ? (groups < 1 ? 1 : groups) : 148 * 8);
+    PIDM_DISPATCH_DTYPE(dtype, (ln_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)x, nullptr, gamma, (T*)y, nullptr, M, C, eps)));
+    PIDM_LAUNCH_CHECK("layernorm_c_fwd");
+    return 0;
+}
+
+// dgamma is ACCUMULATED.
+extern "C" int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma,
+                                    long long M, int C, float eps, int dtype, void* stream) {
+    PIDM_REQUIRE(C % 8 == 0 && C <= 1024, "layernorm: C must be a multiple of 8 and <= 1024 (got %d)", C);
+    int oct = C / 8, L = 1;
+    while (L < 32 && L < oct) L <<= 1;
+    long long groups = (M + (32 / L) * 8 - 1) / ((32 / L) * 8);
+    int grid = (int)(groups < 148 * 4 ? (groups < 1 ? 1 : groups) : 148 * 4);
+    PIDM_DISPATCH_DTYPE(dtype, (ln_kernel<T, true><<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>(
+                                   (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, M, C, eps)));
+    PIDM_LAUNCH_CHECK("layernorm_c_bwd");
+    return 0;
+}

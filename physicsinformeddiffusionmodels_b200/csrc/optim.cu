@@ -1,0 +1,103 @@
+// Step glue on FLAT fp32 buffers (one launch each instead of ~1000 per-tensor launches of the reference loop):
+//   global-norm clip (torch.nn.utils.clip_grad_norm_(params, 1.0), main.py:165)
+//   Adam(lr, betas=(0.9,0.999), eps=1e-8)                          (main.py:143,166)
+//   EMA shadow update mu=0.99                                       (denoising_utils.py:174-177, main.py:178-179)
+// and the error plumbing shared by all translation units.
+#include "common.cuh"
+#include "pidm.h"
+#include <stdarg.h>
+
+namespace pidm {
+
+thread_local char g_last_error[512] = {0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+__global__ void sumsq_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ tail, int ntail,
+                             float* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) s += tail[threadIdx.x] * tail[threadIdx.x];
+    __shared__ float red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v);
+    }
+}
+
+__global__ void adam_ema_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float* __restrict__ ema, long long n, float lr, float b1, float b2,
+                                float eps, float bc1, float bc2, const int* __restrict__ step_dev,
+                                const float* __restrict__ gnorm_sq, float grad_scale, float max_norm, float ema_mu,
+                                int ema_on, int zero_grad) {
+    if (step_dev) {   // CUDA-graph friendly: the 1-based step count lives on the device
+        const float st = (float)(*step_dev);
+        bc1 = 1.f - powf(b1, st);
+        bc2 = 1.f - powf(b2, st);
+    }
+    float coef = grad_scale;
+    if (gnorm_sq && max_norm > 0.f) {
+        float total = sqrtf(*gnorm_sq) * grad_scale;
+        coef *= fminf(max_norm / (total + 1e-6f), 1.f);
+    }
+    const float step = lr / bc1, rs = rsqrtf(bc2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * coef;
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        float pi = p[i] - step * mi / (sqrtf(vi) * rs + eps);
+        m[i] = mi; v[i] = vi; p[i] = pi;
+        if (ema_on) ema[i] = ema_mu * ema[i] + (1.f - ema_mu) * pi;
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+
+__global__ void incr_kernel(int* c) { *c += 1; }
+
+}  // namespace pidm
+using namespace pidm;
+
+extern "C" const char* pidm_last_error(void) { return g_last_error; }
+
+extern "C" int pidm_version(void) { return 100; }
+
+// out[0] += sum x^2   (caller zeroes out)
+extern "C" int pidm_sumsq(const float* x, long long n, float* out, void* stream) {
+    PIDM_REQUIRE(((uintptr_t)x & 15) == 0, "sumsq: buffer must be 16-byte aligned");
+    long long n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, n4, x + n4 * 4, (int)(n - n4 * 4), out);
+    PIDM_LAUNCH_CHECK("sumsq");
+    return 0;
+}
+
+extern "C" int pidm_adam_ema_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* ema_shadow,
+                                  long long n, float lr, float beta1, float beta2, float eps, int step,
+                                  int* step_counter_dev, const float* grad_norm_sq_dev, float grad_scale, float max_norm, float ema_mu,
+                                  int ema_on, int zero_grad, void* stream) {
+    PIDM_REQUIRE(step >= 1 || step_counter_dev, "adam: step is 1-based");
+    if (step_counter_dev) incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev);   // counter holds steps done so far
+    float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    adam_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, ema_shadow, n, lr, beta1,
+                                                           beta2, eps, bc1, bc2, step_counter_dev, grad_norm_sq_dev, grad_scale,
+                                                           max_norm, ema_mu, ema_on, zero_grad);
+    PIDM_LAUNCH_CHECK("adam_ema_step");
+    return 0;
+}

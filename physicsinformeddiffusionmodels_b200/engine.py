@@ -1,0 +1,132 @@
+"""Training-step engine: the body of the reference's loop (main.py:157-183) as a B200-native step.
+
+    q_sample -> U-Net -> x0_hat -> Darcy residual + loss (fused) -> backward -> [NCCL all-reduce of ONE flat
+    fp32 gradient buffer] -> global-norm clip + Adam + EMA (one fused kernel over the flat buffers)
+
+* Flat buffers: parameters, gradients, Adam moments and the EMA shadow live in five flat fp32 buffers; every
+  nn.Parameter is a view, and every wgrad-type kernel accumulates straight into the flat gradient
+  (`_pidm_grad`, see ops._grad_buffer), so there are no per-tensor copies, no 3,303 `copy_` calls per step.
+* CUDA graph: the whole step (RNG draws included) is captured once and replayed; the Adam step count lives on
+  the device.  Tracked scalars stay on the device (no `.item()` syncs in the loop).
+* Data parallel: one process per GPU; rank r owns rows [r*B, (r+1)*B) of the global batch; a single
+  `all_reduce(SUM)` of the flat gradient per step, averaged inside the Adam kernel (grad_scale = 1/world).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import call, stream
+
+_ALIGN = 64     # elements: every parameter starts on a 256-byte boundary (float4 / TMA friendly)
+
+
+class FlatParams:
+    """Re-homes the trainable parameters of `model` into one flat fp32 buffer (plus grad / moment / EMA twins)."""
+
+    def __init__(self, model, with_optimizer_state=True):
+        params = [p for p in model.parameters() if p.requires_grad]
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = total
+        self.params, self.offsets = params, offs
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(params, offs):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p._pidm_grad = self.grad[o:o + p.numel()].view(p.shape)
+        if with_optimizer_state:
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+            self.ema = self.flat.clone()
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    def release(self):
+        for p in self.params:
+            if hasattr(p, '_pidm_grad'):
+                del p._pidm_grad
+
+
+def shard_rows(global_batch, rank, world):
+    """Rows [lo, hi) of the global batch owned by `rank` (equal shards; the loss is a mean over equal shards)."""
+    assert global_batch % world == 0, 'global batch must divide evenly over the ranks'
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_flat_grad(flat_grad, world):
+    """The single exchange step of the data-parallel path: sum of the flat gradient over all ranks."""
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return flat_grad
+
+
+class TrainEngine:
+    def __init__(self, model, diffusion, residuals, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, ema_mu=0.99,
+                 c_data=1.0, c_residual=1e-3, use_graph=True, world=1):
+        self.model, self.diffusion, self.residuals = model, diffusion, residuals
+        self.lr, self.betas, self.eps, self.max_norm, self.ema_mu = lr, betas, eps, max_norm, ema_mu
+        self.c_data, self.c_residual = c_data, c_residual
+        self.world = world
+        self.fp = FlatParams(model)
+        self.diffusion.sync_scalars = False
+        self.use_graph = use_graph
+        self._graph = None
+        self._static_x0 = None
+        self._static_out = None
+        self.steps_done = 0
+
+    # ---- one step, eager (also the body that gets captured) -------------------------------------------------
+    def _step_body(self, x0):
+        fp = self.fp
+        loss, data_l, rabs, _, _ = self.diffusion.model_estimation_loss(
+            x0, residual_func=self.residuals, c_data=self.c_data, c_residual=self.c_residual, c_ineq=0., lambda_opt=0.)
+        loss.backward()
+        allreduce_flat_grad(fp.grad, self.world)
+        fp.gnorm_sq.zero_()
+        call('pidm_sumsq', fp.grad, fp.total, fp.gnorm_sq, stream())
+        call('pidm_adam_ema_step', fp.flat, fp.grad, fp.exp_avg, fp.exp_avg_sq, fp.ema, fp.total, self.lr,
+             self.betas[0], self.betas[1], self.eps, 0, fp.step_dev, fp.gnorm_sq, 1.0 / self.world, self.max_norm,
+             self.ema_mu, 1, 1, stream())
+        return loss.detach(), data_l, rabs
+
+    def step(self, x0):
+        """x0: [B, 2, 64, 64] fp32 on the device.  Returns (loss, data_loss, mean|r|) as device tensors."""
+        if not self.use_graph:
+            out = self._step_body(x0)
+            self.steps_done += 1
+            return out
+        if self._graph is None:
+            self._capture(x0)
+        self._static_x0.copy_(x0, non_blocking=True)
+        self._graph.replay()
+        self.steps_done += 1
+        return self._static_out
+
+    def _capture(self, x0):
+        self._static_x0 = x0.clone()
+        # warm-up on a side stream (allocator, lazy module state, table uploads), as CUDA-graph capture requires
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step_body(self._static_x0)
+                self.steps_done += 1
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._step_body(self._static_x0)
+
+    def ema_state_dict(self):
+        """EMA weights keyed like model.state_dict() (what the reference checkpoints hold, main.py:314)."""
+        sd = {k: v.clone() for k, v in self.model.state_dict().items()}
+        name_of = {id(p): n for n, p in self.model.named_parameters()}
+        for p, o in zip(self.fp.params, self.fp.offsets):
+            sd[name_of[id(p)]] = self.fp.ema[o:o + p.numel()].view(p.shape).clone()
+        return sd

@@ -1,0 +1,472 @@
+"""torch.autograd.Function wrappers around the libpidm C ABI (include/pidm.h).
+
+Activations are NHWC tensors [B, H, W, C] in the activation dtype (bf16 by default, fp32 in the
+exact mode used for parity debugging).  Every forward AND backward below is a libpidm kernel launch;
+PyTorch only allocates the buffers and records the graph.
+
+Parameter gradients: every wgrad-type kernel ACCUMULATES into the buffer it is given.  In the default
+mode that buffer is a fresh zero tensor returned to autograd; when a parameter carries a
+`_pidm_grad` view (flat-buffer engine, engine.py) the kernel accumulates straight into it and autograd
+sees None, so one flat fp32 buffer is ready for the NCCL all-reduce / fused Adam with no per-tensor
+copies."""
+import os
+
+import torch
+
+from . import _lib
+from ._lib import call, stream
+
+_TC_HARD_OFF = os.environ.get('PIDM_DISABLE_TC') == '1'     # debugging aid: force the CUDA-core conv kernels
+_STATE = {'act_dtype': torch.bfloat16, 'use_tc': not _TC_HARD_OFF}
+
+
+def set_precision(name):
+    """'bf16' (default: bf16 activations / GEMM operands, fp32 accumulate) or 'fp32' (exact mode)."""
+    _STATE['act_dtype'] = {'bf16': torch.bfloat16, 'fp32': torch.float32}[name]
+
+
+def set_tensor_core_conv(flag):
+    _STATE['use_tc'] = bool(flag) and not _TC_HARD_OFF
+
+
+def act_dtype():
+    return _STATE['act_dtype']
+
+
+def _code(t):
+    return _lib.DTYPE_CODE[t.dtype]
+
+
+def _grad_buffer(p):
+    """(buffer to accumulate into, value to hand back to autograd)."""
+    g = getattr(p, '_pidm_grad', None)
+    if g is not None:
+        return g, None
+    z = torch.zeros_like(p)
+    return z, z
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('physicsinformeddiffusionmodels_b200 runs on CUDA (B200) only: got a CPU tensor. '
+                               'There is no CPU fallback on the product path.')
+
+
+# ----------------------------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, cpad, dtype=None):
+    """[B,C,H,W] fp32 -> [B,H,W,cpad] activations (zero-padded channels).  Input is data: no gradient."""
+    _need_cuda(x)
+    B, C, H, W = x.shape
+    dtype = dtype or act_dtype()
+    y = torch.empty(B, H, W, cpad, device=x.device, dtype=dtype)
+    call('pidm_nchw_to_nhwc', x.contiguous().float(), y, B, C, H * W, cpad, _lib.DTYPE_CODE[dtype], stream())
+    return y
+
+
+def nhwc_to_nchw(x, C=None):
+    B, H, W, Cp = x.shape
+    C = C or Cp
+    y = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
+    call('pidm_nhwc_to_nchw', x, y, B, C, H * W, Cp, _code(x), stream())
+    return y
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        o = torch.empty_like(a)
+        call('pidm_add', a, b, o, a.numel(), _code(a), stream())
+        return o
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a.contiguous(), b.contiguous())
+
+
+class _Concat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        B, H, W, Ca = a.shape
+        Cb = b.shape[-1]
+        o = torch.empty(B, H, W, Ca + Cb, device=a.device, dtype=a.dtype)
+        call('pidm_concat_channels', a, b, o, B * H * W, Ca, Cb, _code(a), stream())
+        ctx.shapes = (a.shape, b.shape)
+        return o
+
+    @staticmethod
+    def backward(ctx, g):
+        sa, sb = ctx.shapes
+        g = g.contiguous()
+        ga = torch.empty(sa, device=g.device, dtype=g.dtype)
+        gb = torch.empty(sb, device=g.device, dtype=g.dtype)
+        call('pidm_split_channels', g, ga, gb, sa[0] * sa[1] * sa[2], sa[3], sb[3], _code(g), stream())
+        return ga, gb
+
+
+def concat(a, b):
+    return _Concat.apply(a.contiguous(), b.contiguous())
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution (implicit GEMM).  `spec` is a ConvSpec created by the owning module (packing.py).
+# ----------------------------------------------------------------------------------------------
+def _conv_launch(x, wp, bias, residual, y, g, transposed):
+    """g = (B,H,W,Cin,Ho,Wo,Cout,KH,KW,stride,pad)."""
+    B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = g
+    if (_STATE['use_tc'] and x.dtype == torch.bfloat16 and stride == 1 and not transposed and Ho == H and Wo == W
+            and call('pidm_conv2d_tc_supported', B, H, W, Cin, Cout, KH, KW, pad)):
+        call('pidm_conv2d_tc', x, wp, bias, residual, y, B, H, W, Cin, Cout, KH, KW, pad, stream())
+    else:
+        call('pidm_conv2d_simt', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad,
+             1 if transposed else 0, _code(x), stream())
+
+
+class _Conv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, spec):
+        B, H, W, Cin = x.shape
+        Ho, Wo = spec.out_hw(H, W)
+        y = torch.empty(B, Ho, Wo, spec.cout, device=x.device, dtype=x.dtype)
+        g = (B, H, W, Cin, Ho, Wo, spec.cout, spec.kh, spec.kw, spec.stride, spec.pad)
+        _conv_launch(x, spec.wp_fwd, bias, residual, y, g, spec.transposed)
+        ctx.save_for_backward(x, weight, bias)
+        ctx.spec, ctx.g, ctx.has_res = spec, g, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        spec = ctx.spec
+        B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = ctx.g
+        dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            # dgrad: roles of input/output swap; regular conv -> transposed gather and vice versa.
+            # For stride 1 the transposed gather equals a regular conv with the flipped kernel, which the
+            # dgrad packing already encodes (pad' = K-1-pad), so the tensor-core kernel can take it.
+            if stride == 1 and not spec.transposed:
+                gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, 1, KH - 1 - pad)
+                _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, False)
+            else:
+                gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, stride, pad)
+                _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
+        gw_buf, gw_ret = _grad_buffer(weight)
+        gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
+        call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW, stride,
+             pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
+        return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None
+
+
+def conv2d(x, weight, bias, spec, residual=None):
+    return _Conv2d.apply(x.contiguous(), weight, bias, None if residual is None else residual.contiguous(), spec)
+
+
+# ----------------------------------------------------------------------------------------------
+# GroupNorm -> FiLM -> SiLU ; channel LayerNorm
+# ----------------------------------------------------------------------------------------------
+class _GroupNormSilu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps):
+        B, H, W, C = x.shape
+        y = torch.empty_like(x)
+        sums = torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
+        call('pidm_groupnorm_silu_fwd', x, gamma, beta, scale_shift, y, sums, B, H * W, C, groups, eps, _code(x), stream())
+        ctx.save_for_backward(x, gamma, beta, scale_shift, sums)
+        ctx.groups, ctx.eps = groups, eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, ss, sums = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        gg_buf, gg_ret = _grad_buffer(gamma)
+        gb_buf, gb_ret = _grad_buffer(beta)
+        dss = None if ss is None else torch.empty_like(ss)
+        ws = torch.empty(B * C * 2 + B * ctx.groups * 2, device=x.device, dtype=torch.float32)
+        call('pidm_groupnorm_silu_bwd', x, dy, sums, gamma, beta, ss, dx, gg_buf, gb_buf, dss, ws, B, H * W, C,
+             ctx.groups, ctx.eps, _code(x), stream())
+        return dx, gg_ret, gb_ret, dss, None, None
+
+
+def groupnorm_silu(x, gamma, beta, scale_shift, groups, eps=1e-5):
+    return _GroupNormSilu.apply(x.contiguous(), gamma, beta, scale_shift, groups, eps)
+
+
+class _LayerNormC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, eps):
+        C = x.shape[-1]
+        y = torch.empty_like(x)
+        call('pidm_layernorm_c_fwd', x, gamma, y, x.numel() // C, C, eps, _code(x), stream())
+        ctx.save_for_backward(x, gamma)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        C = x.shape[-1]
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        gg_buf, gg_ret = _grad_buffer(gamma)
+        call('pidm_layernorm_c_bwd', x, dy, gamma, dx, gg_buf, x.numel() // C, C, ctx.eps, _code(x), stream())
+        return dx, gg_ret, None
+
+
+def layernorm_c(x, gamma, eps=1e-5):
+    """gamma: the reference's [1,C,1,1,1] parameter (contiguous, so it is a flat [C] buffer)."""
+    return _LayerNormC.apply(x.contiguous(), gamma, eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention cores
+# ----------------------------------------------------------------------------------------------
+class _LinAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        B, H, W, C3 = qkv.shape
+        N = H * W
+        hid = heads * 32
+        assert C3 == 3 * hid
+        out = torch.empty(B, H, W, hid, device=qkv.device, dtype=qkv.dtype)
+        ctxm = torch.empty(B, heads, 32, 32, device=qkv.device, dtype=torch.float32)
+        kmax = torch.empty(B, heads, 32, device=qkv.device, dtype=torch.float32)
+        kzinv = torch.empty_like(kmax)
+        ws = torch.empty(call('pidm_linattn_workspace_floats', B, N, heads), device=qkv.device, dtype=torch.float32)
+        call('pidm_linattn_fwd', qkv, out, ctxm, kmax, kzinv, ws, B, N, heads, _code(qkv), stream())
+        ctx.save_for_backward(qkv, ctxm, kmax, kzinv)
+        ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, ctxm, kmax, kzinv = ctx.saved_tensors
+        B, H, W, _ = qkv.shape
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dctx = torch.empty_like(ctxm)
+        call('pidm_linattn_bwd', qkv, dout, ctxm, kmax, kzinv, dqkv, dctx, B, H * W, ctx.heads, _code(qkv), stream())
+        return dqkv, None
+
+
+def linear_attention(qkv, heads):
+    return _LinAttn.apply(qkv.contiguous(), heads)
+
+
+class _Attn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        B, H, W, C3 = qkv.shape
+        out = torch.empty(B, H, W, heads * 32, device=qkv.device, dtype=qkv.dtype)
+        call('pidm_attn_fwd', qkv, out, B, H * W, heads, _code(qkv), stream())
+        ctx.save_for_backward(qkv)
+        ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        B, H, W, _ = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        call('pidm_attn_bwd', qkv, dout.contiguous(), dqkv, B, H * W, ctx.heads, _code(qkv), stream())
+        return dqkv, None
+
+
+def softmax_attention(qkv, heads):
+    return _Attn.apply(qkv.contiguous(), heads)
+
+
+# ----------------------------------------------------------------------------------------------
+# time conditioning
+# ----------------------------------------------------------------------------------------------
+class _TimeEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, W1, b1, W2, b2):
+        B = t.shape[0]
+        td, dim = W1.shape
+        dev = W1.device
+        emb = torch.empty(B, dim, device=dev, dtype=torch.float32)
+        h1 = torch.empty(B, td, device=dev, dtype=torch.float32)
+        temb = torch.empty_like(h1)
+        silu_t = torch.empty_like(h1)
+        call('pidm_time_embed_fwd', t, W1, b1, W2, b2, emb, h1, temb, silu_t, B, dim, td, stream())
+        ctx.save_for_backward(emb, h1, temb, W1, b1, W2, b2)
+        ctx.mark_non_differentiable(temb)
+        return silu_t, temb
+
+    @staticmethod
+    def backward(ctx, d_silu, _unused):
+        emb, h1, temb, W1, b1, W2, b2 = ctx.saved_tensors
+        B, td = h1.shape
+        gW1, rW1 = _grad_buffer(W1)
+        gb1, rb1 = _grad_buffer(b1)
+        gW2, rW2 = _grad_buffer(W2)
+        gb2, rb2 = _grad_buffer(b2)
+        call('pidm_time_embed_bwd', d_silu.contiguous(), emb, h1, temb, W2, gW1, gb1, gW2, gb2, B, emb.shape[1], td,
+             stream())
+        return None, rW1, rb1, rW2, rb2
+
+
+def time_embed(t, W1, b1, W2, b2):
+    """Returns (SiLU(time_mlp(t)), time_mlp(t)); the second output is for inspection only."""
+    return _TimeEmbed.apply(t.to(torch.int64).contiguous(), W1, b1, W2, b2)
+
+
+class _BlockMlps(torch.autograd.Function):
+    """All ResnetBlock time-MLPs in one launch.  `table` is a MlpTable (packing.py); one output per block."""
+
+    @staticmethod
+    def forward(ctx, silu_t, table, *wb):
+        B, td = silu_t.shape
+        outs = [torch.empty(B, n, device=silu_t.device, dtype=torch.float32) for n in table.rows]
+        call('pidm_block_mlps_fwd', table.device_table(outs), table.n, table.max_rows, silu_t, B, td, stream())
+        ctx.save_for_backward(silu_t, *wb)
+        ctx.table = table
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *d_outs):
+        silu_t, *wb = ctx.saved_tensors
+        table = ctx.table
+        B, td = silu_t.shape
+        bufs, rets = [], []
+        for p in wb:
+            b_, r_ = _grad_buffer(p)
+            bufs.append(b_)
+            rets.append(r_)
+        d_outs = [d.contiguous() for d in d_outs]
+        d_silu = torch.empty_like(silu_t)
+        call('pidm_block_mlps_bwd', table.device_table(None, d_outs, bufs), table.n, table.max_rows, silu_t, d_silu, B, td,
+             stream())
+        return (d_silu, None, *rets)
+
+
+def block_mlps(silu_t, table):
+    """-> tuple of [B, 2*C_out] tensors (scale | shift), one per ResnetBlock with a time MLP."""
+    return _BlockMlps.apply(silu_t, table, *table.params)
+
+
+# ----------------------------------------------------------------------------------------------
+# output head (1x1 conv to NCHW fp32, optional sigmoid on the last channel)
+# ----------------------------------------------------------------------------------------------
+class _Head(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, sigmoid_last):
+        B, H, W, C = x.shape
+        O = w.shape[0]
+        y = torch.empty(B, O, H, W, device=x.device, dtype=torch.float32)
+        call('pidm_head_fwd', x, w, b, y, B, H * W, C, O, int(sigmoid_last), _code(x), stream())
+        ctx.save_for_backward(x, w, b, y)
+        ctx.sig = int(sigmoid_last)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, y = ctx.saved_tensors
+        B, H, W, C = x.shape
+        O = w.shape[0]
+        dx = torch.empty_like(x)
+        gw, rw = _grad_buffer(w)
+        gb, rb = _grad_buffer(b)
+        call('pidm_head_bwd', x, w, y, dy.contiguous().float(), dx, gw, gb, B, H * W, C, O, ctx.sig, _code(x), stream())
+        return dx, rw, rb, None
+
+
+def head(x, w, b, sigmoid_last=False):
+    return _Head.apply(x.contiguous(), w, b, sigmoid_last)
+
+
+# ----------------------------------------------------------------------------------------------
+# diffusion element-wise + Darcy residual / loss
+# ----------------------------------------------------------------------------------------------
+def q_sample(x0, noise, t, sqrt_ab, sqrt_1mab):
+    _need_cuda(x0, noise, t)
+    x0 = x0.contiguous().float()
+    xt = torch.empty_like(x0)
+    call('pidm_qsample', x0, noise.contiguous().float(), t.to(torch.int64).contiguous(), sqrt_ab, sqrt_1mab, xt,
+         x0.shape[0], x0[0].numel(), stream())
+    return xt
+
+
+def posterior_step(x_t, x0_pred, z, c1, c2, sigma):
+    out = torch.empty_like(x_t)
+    call('pidm_posterior_step', x_t.contiguous(), x0_pred.contiguous(), z.contiguous(), out, float(c1), float(c2),
+         float(sigma), x_t.numel(), stream())
+    return out
+
+
+class _DarcyResidual(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0hat, f_s, geom):
+        B, C, P, _ = x0hat.shape
+        r = torch.empty(B, P * P, 3, device=x0hat.device, dtype=torch.float32)
+        call('pidm_darcy_residual_fwd', x0hat, f_s, r, B, P, *geom, stream())
+        ctx.save_for_backward(x0hat, f_s)
+        ctx.geom = geom
+        return r
+
+    @staticmethod
+    def backward(ctx, gr):
+        x0hat, f_s = ctx.saved_tensors
+        B, C, P, _ = x0hat.shape
+        gx = torch.empty_like(x0hat)
+        call('pidm_darcy_residual_bwd', x0hat, f_s, gr.contiguous(), gx, B, P, *ctx.geom, stream())
+        return gx, None, None
+
+
+def darcy_residual(x0hat, f_s, domain_length=1.0, reverse_d1=True, pixels_at_boundary=True):
+    _need_cuda(x0hat)
+    assert x0hat.shape[1] == 2, 'Darcy fields are (p, K)'
+    return _DarcyResidual.apply(x0hat.contiguous().float(), f_s,
+                                (float(domain_length), int(reverse_d1), int(pixels_at_boundary)))
+
+
+class _DarcyPidmLoss(torch.autograd.Function):
+    """loss = c_data * mean_b(p2[t_b] mse_b) + mean(c_res * 0.5 r^2 / var_t); residual never materialised.
+    The gradient is produced in the forward pass (one kernel) and only scaled in backward.
+    model_out=None means "the data term uses x0hat itself" (x0_estimation: mean)."""
+
+    @staticmethod
+    def forward(ctx, x0hat, model_out, target, t, f_s, p2w, pvar, c_data, c_res, geom):
+        B, C, P, _ = x0hat.shape
+        same = model_out is None
+        sums = torch.empty(3, device=x0hat.device, dtype=torch.float32)
+        need = x0hat.requires_grad or (model_out is not None and model_out.requires_grad)
+        gx = torch.empty_like(x0hat) if need else None
+        gm = None if (same or not need) else torch.empty_like(model_out)
+        call('pidm_darcy_pidm_loss', x0hat, x0hat if same else model_out, target, f_s, t, p2w, pvar, float(c_data),
+             float(c_res), sums, gx, gm, B, P, *geom, stream())
+        ctx.save_for_backward(gx, gm)
+        ctx.mark_non_differentiable(sums)
+        return sums[0] + sums[1], sums
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        gx, gm = ctx.saved_tensors
+        g = g.contiguous().float()
+        call('pidm_scale_inplace', gx, g, gx.numel(), stream())
+        if gm is not None:
+            call('pidm_scale_inplace', gm, g, gm.numel(), stream())
+        return gx, gm, None, None, None, None, None, None, None, None
+
+
+def darcy_pidm_loss(x0hat, model_out, target, t, f_s, p2w, pvar, c_data, c_res, domain_length=1.0, reverse_d1=True,
+                    pixels_at_boundary=True):
+    """Returns (loss, sums) with sums = [data_loss, residual_loss, mean|r|] on the device."""
+    _need_cuda(x0hat, target)
+    geom = (float(domain_length), int(reverse_d1), int(pixels_at_boundary))
+    if model_out is not None and model_out is x0hat:
+        model_out = None
+    return _DarcyPidmLoss.apply(x0hat.contiguous(), None if model_out is None else model_out.contiguous(),
+                                target.contiguous().float(), t.to(torch.int64).contiguous(), f_s, p2w, pvar, c_data, c_res,
+                                geom)

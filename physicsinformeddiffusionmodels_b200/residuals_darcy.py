@@ -1,0 +1,92 @@
+"""`ResidualsDarcy` with the reference's constructor / method surface (reference src/residuals_darcy.py),
+backed by the fused Darcy kernels of libpidm (csrc/darcy.cu)."""
+import torch
+
+from . import ops
+from .grad_utils import GradientsHelper, generalized_b_xy_c_to_image, generalized_image_to_b_xy_c  # noqa: F401
+
+
+class ResidualsDarcy:
+    def __init__(self, model, fd_acc, pixels_per_dim, pixels_at_boundary, reverse_d1, device='cpu', bcs='none',
+                 domain_length=1., residual_grad_guidance=False, use_ddim_x0=False, ddim_steps=0):
+        self.gov_eqs = 'darcy'
+        self.model = model
+        self.pixels_at_boundary = pixels_at_boundary
+        self.periodic = bcs == 'periodic'
+        self.input_dim = 2
+        if self.periodic:
+            raise NotImplementedError("bcs='periodic' is not used by the reference drivers")
+        if residual_grad_guidance:
+            raise NotImplementedError('residual gradient guidance is outside the built hot path (SURVEY.md 8f.3)')
+        d0 = domain_length / (pixels_per_dim - 1) if pixels_at_boundary else domain_length / pixels_per_dim
+        d1 = -d0 if reverse_d1 else d0
+        self.reverse_d1 = reverse_d1
+        self.domain_length = domain_length
+        self.grads = GradientsHelper(d0=d0, d1=d1, fd_acc=fd_acc, periodic=False, device=device)
+        self.pixels_per_dim = pixels_per_dim
+        self.device = device
+        # stationary source field on the pixel-centre grid (reference :40-53,95-104)
+        w, r = 0.125, 10.0
+        ps = 1.0 / pixels_per_dim
+        c = torch.linspace(ps / 2, 1.0 - ps / 2, steps=pixels_per_dim)
+        X, Y = torch.meshgrid(c, c, indexing='ij')
+        f = torch.zeros_like(X)
+        f[torch.logical_and(torch.abs(X - 0.5 * w) <= 0.5 * w, torch.abs(Y - 0.5 * w) <= 0.5 * w)] = r
+        f[torch.logical_and(torch.abs(X - 1 + 0.5 * w) <= 0.5 * w, torch.abs(Y - 1 + 0.5 * w) <= 0.5 * w)] = -r
+        self.f_s = f.reshape(1, -1, 1).to(device)                 # [1, P*P, 1] like the reference
+        self.f_s_flat = self.f_s.reshape(-1).contiguous()
+        self.use_trapezoid = bool(pixels_at_boundary)
+        if self.use_trapezoid:
+            self.trapezoidal_weights = self.create_trapezoidal_weights()
+        self.residual_grad_guidance = residual_grad_guidance
+        self.use_ddim_x0 = use_ddim_x0
+        self.ddim_steps = ddim_steps
+        self.geometry = (float(domain_length), bool(reverse_d1), bool(pixels_at_boundary))
+
+    def create_trapezoidal_weights(self):
+        P = self.pixels_per_dim
+        w = torch.full((1, P, P), 4.)
+        w[..., 0, :] = 2.
+        w[..., -1, :] = 2.
+        w[..., :, 0] = 2.
+        w[..., :, -1] = 2.
+        for i in (0, -1):
+            for j in (0, -1):
+                w[..., i, j] = 1.
+        w *= (1. / P) ** 2 / 4.
+        return w.reshape(1, -1).to(self.device)
+
+    # (x0_pred, model_out) for the residual / loss kernels
+    def predict_x0(self, model_input, ddim_func=None):
+        noisy_in, time = model_input
+        if self.use_ddim_x0:
+            return ddim_func(noisy_in, time, self.model, noisy_in.shape, self.ddim_steps, 0.)
+        out = self.model(noisy_in, time)
+        return out, out
+
+    def compute_residual(self, input, reduce='none', return_model_out=False, return_optimizer=False,
+                         return_inequality=False, sample=False, ddim_func=None, pass_through=False):
+        if pass_through:
+            assert isinstance(input, torch.Tensor), 'Input is assumed to directly be given output.'
+            x0_pred = model_out = input
+        else:
+            assert len(input[0]) == 2 and isinstance(input[0], tuple), \
+                'Input[0] must be a tuple consisting of noisy signal and time.'
+            x0_pred, model_out = self.predict_x0(input[0], ddim_func)
+        assert len(x0_pred.shape) == 4, \
+            'Model output must be a tensor shaped as an image (with explicit axes for the spatial dimensions).'
+        residual = ops.darcy_residual(x0_pred, self.f_s_flat, *self.geometry)       # [B, P*P, 3]
+        output = {'residual': residual}
+        if return_model_out:
+            output['model_out'] = model_out
+        if reduce == 'full':
+            return {k: v.mean() for k, v in output.items()}
+        elif reduce == 'per-batch':
+            return {k: v.mean(dim=tuple(range(1, v.ndim))) if v.ndim > 1 and (k != 'model_out' and k != 'residual') else v
+                    for k, v in output.items()}
+        elif reduce == 'none':
+            return output
+        raise ValueError('Unknown reduction method.')
+
+    def residual_correction(self, x0_pred_in):
+        raise NotImplementedError('CoCoGen residual correction is outside the built hot path (SURVEY.md 8f.3)')

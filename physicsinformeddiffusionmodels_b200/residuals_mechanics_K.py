@@ -1,0 +1,181 @@
+"""`ResidualsMechanics` with the reference's constructor / method surface (reference
+src/residuals_mechanics_K.py), evaluated MATRIX-FREE by libpidm (csrc/mechanics.cu): the reference's dense
+B x 8450 x 8450 stiffness assembly (285.6 MB per sample) is never formed.
+
+Mesh convention (the authors' mesh files are an external download): the structured
+unit-square mesh with node id = row*65 + col, dof = 2*node + d and counter-clockwise Q4 elements
+n1=(er+1,ec), n2=(er+1,ec+1), n3=(er,ec+1), n4=(er,ec); with it the element->dof map is implicit and
+`no_BC_folder` is not read.  Element stiffness: closed-form plane-stress Q4, E = 1, nu = 0.3 (the reference
+overrides the material file with exactly these values, residuals_mechanics_K.py:30-33)."""
+import warnings
+
+import torch
+import torch.nn.functional as F  # noqa: F401  (re-exported name of the reference module)
+
+from ._lib import call, stream
+from .grad_utils import generalized_b_xy_c_to_image, generalized_image_to_b_xy_c  # noqa: F401
+
+
+def q4_plane_stress_stiffness(E=1.0, nu=0.3):
+    k = [1 / 2 - nu / 6, 1 / 8 + nu / 8, -1 / 4 - nu / 12, -1 / 8 + 3 * nu / 8,
+         -1 / 4 + nu / 12, -1 / 8 - nu / 8, nu / 6, 1 / 8 - 3 * nu / 8]
+    idx = [[0, 1, 2, 3, 4, 5, 6, 7], [1, 0, 7, 6, 5, 4, 3, 2], [2, 7, 0, 5, 6, 3, 4, 1], [3, 6, 5, 0, 7, 2, 1, 4],
+           [4, 5, 6, 7, 0, 1, 2, 3], [5, 4, 3, 2, 1, 0, 7, 6], [6, 3, 4, 1, 2, 7, 0, 5], [7, 2, 1, 4, 3, 6, 5, 0]]
+    return torch.tensor([[k[j] for j in row] for row in idx], dtype=torch.float64) * (E / (1 - nu ** 2))
+
+
+class _Resize(torch.autograd.Function):
+    """Bilinear resize of [B, C, S, S] fp32 planes, align_corners=False, antialias=False (reference :10-21)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        B, C, S, _ = x.shape
+        y = torch.empty(B, C, size, size, device=x.device, dtype=torch.float32)
+        call('pidm_bilinear_resize_fwd', x, y, B * C, S, size, stream())
+        ctx.dims = (B, C, S, size)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, S, size = ctx.dims
+        dx = torch.empty(B, C, S, S, device=dy.device, dtype=torch.float32)
+        call('pidm_bilinear_resize_bwd', dy.contiguous(), dx, B * C, S, size, stream())
+        return dx, None
+
+
+def resize_image(tensor, target_size):
+    assert len(tensor.shape) > 3, f'Expected image, got {tensor.shape}'
+    shp = tensor.shape
+    flat = tensor.reshape(shp[0], -1, shp[-2], shp[-1]).contiguous().float()
+    return _Resize.apply(flat, target_size).reshape(*shp[:-2], target_size, target_size)
+
+
+class _MechResidual(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, rho, bcs, KE):
+        B, _, nn_, _ = u.shape
+        nel = nn_ - 1
+        r = torch.empty(B, 2 * nn_ * nn_, device=u.device, dtype=torch.float32)
+        c = torch.empty(B, device=u.device, dtype=torch.float32)
+        call('pidm_mechanics_residual_fwd', u, rho, bcs, KE, r, c, B, nel, stream())
+        ctx.save_for_backward(u, rho, bcs, KE)
+        return r, c
+
+    @staticmethod
+    def backward(ctx, gr, gc):
+        u, rho, bcs, KE = ctx.saved_tensors
+        B, _, nn_, _ = u.shape
+        gu = torch.empty_like(u)
+        grho = torch.empty_like(rho)
+        ws = torch.empty(B * 2 * nn_ * nn_, device=u.device, dtype=torch.float32)
+        call('pidm_mechanics_residual_bwd', u, rho, bcs, KE, None if gr is None else gr.contiguous(),
+             None if gc is None else gc.contiguous(), gu, grho, ws, B, nn_ - 1, stream())
+        return gu, grho, None, None
+
+
+class ResidualsMechanics:
+    def __init__(self, model, pixels_per_dim, pixels_at_boundary, no_BC_folder, device='cpu', bcs='none', E=1.0,
+                 nu=0.3, topopt_eval=False, use_ddim_x0=False, ddim_steps=0):
+        self.gov_eqs = 'mechanics'
+        self.model = model
+        self.pixels_at_boundary = pixels_at_boundary
+        self.E, self.nu = E, nu
+        self.periodic = bcs == 'periodic'
+        if self.periodic:
+            raise NotImplementedError("bcs='periodic' is not used by the reference drivers")
+        self.device = device
+        self.pixels_per_dim = pixels_per_dim
+        self.KE = q4_plane_stress_stiffness(1.0, 0.3).float().to(device).contiguous()
+        self.topopt_eval = topopt_eval
+        self.use_ddim_x0 = use_ddim_x0
+        self.ddim_steps = ddim_steps
+        self._warned = False
+
+    def compute_residual(self, input_tuple, reduce='none', return_model_out=False, return_optimizer=False,
+                         return_inequality=False, sample=False, ddim_func=None, pass_through=False):
+        input, bcs, vf = input_tuple[0], input_tuple[1], input_tuple[2]
+        bcs = bcs.contiguous().float()
+        if pass_through:
+            assert isinstance(input, torch.Tensor), 'Input is assumed to directly be given output.'
+            x0_pred = model_out = input
+        else:
+            assert len(input) == 2 and isinstance(input, tuple), \
+                'Input must be a tuple consisting of noisy signal and time.'
+            noisy_in, time = input
+            noisy_in = generalized_b_xy_c_to_image(noisy_in)
+            net_in = torch.cat((resize_image(noisy_in, 64), resize_image(bcs, 64)), dim=1)
+            if self.use_ddim_x0:
+                x0_pred, model_out = ddim_func(net_in, time, self.model, noisy_in.shape, self.ddim_steps, 0.,
+                                               gov_eqs='mechanics')
+            else:
+                x0_pred = model_out = self.model(net_in, time)
+        assert len(x0_pred.shape) == 4, \
+            'Model output must be a tensor shaped as an image (with explicit axes for the spatial dimensions).'
+        P = x0_pred.shape[-1]
+        u = resize_image(x0_pred[:, :-1], P + 1)
+        rho = x0_pred[:, -1].contiguous().float()
+        residual, compliance = _MechResidual.apply(u, rho, bcs, self.KE)
+        output = {'residual': residual}
+        if return_model_out:
+            u_mo = u if model_out is x0_pred else resize_image(model_out[:, :-1], P + 1)
+            rho_pad = F.pad(model_out[:, -1], pad=(0, 1, 0, 1), mode='constant', value=0)
+            output['model_out'] = torch.cat((u_mo, rho_pad.unsqueeze(1)), dim=1)
+        if return_optimizer:
+            output['optimizer'] = compliance
+        if return_inequality:
+            output['inequality'] = rho.reshape(rho.shape[0], -1).mean(1) - vf
+        if self.topopt_eval and sample:
+            if not self._warned:
+                warnings.warn('topopt evaluation metrics (per-sample FEM solve, floating-material check; reference '
+                              ':276-354) are outside the built hot path and are reported as NaN')
+                self._warned = True
+            nan = torch.full((x0_pred.shape[0],), float('nan'), device=x0_pred.device)
+            output['rel_CE_error_full_batch'] = nan
+            output['vf_error_full_batch'] = nan.clone()
+            output['fm_error_full_batch'] = nan.clone()
+        if reduce == 'full':
+            return {k: v.mean() for k, v in output.items()}
+        elif reduce == 'per-batch':
+            return {k: v.mean(dim=tuple(range(1, v.ndim))) if v.ndim > 1 and (k != 'model_out' and k != 'residual') else v
+                    for k, v in output.items()}
+        elif reduce == 'none':
+            return output
+        raise ValueError('Unknown reduction method.')
+
+    # ---- hooks used by DenoisingDiffusion (mechanics branch of the reference's loss / sampler) ------------------
+    def training_loss(self, diffusion, input, t, c_data, c_residual, c_ineq, lambda_opt):
+        """model_estimation_loss for gov_eqs='mechanics' (reference denoising_utils.py:629-710)."""
+        from . import ops
+        from .denoising_utils import image_to_b_xy_c
+        dd = diffusion.diff_dict
+        conditioning, x_0, bcs = torch.tensor_split(input, (3, 6), dim=1)
+        x_0 = x_0.contiguous()
+        e = torch.randn_like(x_0)
+        x = ops.q_sample(x_0, e, t, dd['alphas_bar_sqrt'], dd['one_minus_alphas_bar_sqrt'])
+        x = torch.cat((x, conditioning), dim=1)
+        vf = conditioning[:, 0, 0, 0]
+        out = self.compute_residual(((image_to_b_xy_c(x), t), bcs, vf, x_0), reduce='per-batch', return_model_out=True,
+                                    return_optimizer=True, return_inequality=c_ineq > 0.,
+                                    ddim_func=diffusion.ddim_sample_x0)
+        residual, output = out['residual'], out['model_out']
+        B = x_0.shape[0]
+        mse = ((x_0 - output) ** 2).reshape(B, -1).mean(dim=1)
+        data_loss = c_data * (mse * dd['p2_loss_weight'][t]).mean()
+        var = dd['posterior_variance_clipped'][t]
+        loss = data_loss + (c_residual * 0.5 * residual ** 2 / var[:, None]).mean()
+        ineq_track = 0.
+        if c_ineq > 0.:
+            loss = loss + (c_ineq * 0.5 * out['inequality'] ** 2 / var).mean()
+            ineq_track = out['inequality'].mean().item()
+        loss = loss + (lambda_opt * out['optimizer']).mean()
+        return loss, data_loss.item(), residual.abs().mean().item(), ineq_track, out['optimizer'].mean().item()
+
+    def sampling_residual(self, diffusion, x, conditioning_input, t_vec, return_optimizer, return_inequality, sample):
+        from .denoising_utils import image_to_b_xy_c
+        conditioning, bcs, solution = conditioning_input
+        xin = torch.cat((x, conditioning), dim=1)
+        vf = conditioning[:, 0, 0, 0]
+        return self.compute_residual(((image_to_b_xy_c(xin), t_vec), bcs, vf, solution), reduce='per-batch',
+                                     return_model_out=True, return_optimizer=return_optimizer,
+                                     return_inequality=return_inequality, sample=sample,
+                                     ddim_func=diffusion.ddim_sample_x0)

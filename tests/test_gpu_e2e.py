@@ -1,0 +1,206 @@
+"""End-to-end parity of the B200 engine (U-Net, loss, gradients, sampler, training step) against the golden
+fixtures produced by the UNMODIFIED reference (tests/golden, oracle/make_golden.py) and against the CPU oracle.
+
+Two precision modes: 'fp32' activations (exact mode: only summation order differs from the reference -> tight
+tolerances) and 'bf16' (production mode: bf16 GEMM operands / activations, fp32 accumulate and statistics)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def env():
+    from oracle import pidm_oracle as O
+    from physicsinformeddiffusionmodels_b200 import ops
+    from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
+    from physicsinformeddiffusionmodels_b200.residuals_darcy import ResidualsDarcy
+    from physicsinformeddiffusionmodels_b200.unet_model import Unet3D
+    cfg = O.unet_config(dim=32, channels=2)
+    sd = O.make_test_state_dict(cfg, 0)
+
+    def build(n_steps=100, use_ddim_x0=False):
+        model = Unet3D(dim=32, channels=2).to(DEV)
+        model.load_state_dict(sd)
+        diff = DenoisingDiffusion(n_steps, DEV)
+        res = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True,
+                             device=DEV, bcs='none', domain_length=1., use_ddim_x0=use_ddim_x0, ddim_steps=0)
+        return model, diff, res
+    yield dict(O=O, ops=ops, build=build, cfg=cfg, sd=sd)
+    ops.set_precision('bf16')
+
+
+# fp32 mode: 1e-4 (accumulation order over K up to 4608 and ~60 layers); bf16 mode: 3e-2 (2^-9 per rounding)
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 3e-2)])
+def test_unet_forward_matches_reference(env, golden, mode, tol):
+    env['ops'].set_precision(mode)
+    gd = golden('unet_darcy_fwd.pt')
+    model, _, _ = env['build']()
+    with torch.no_grad():
+        y = model(gd['x'].to(DEV), gd['t'].to(DEV))
+        y2 = model(gd['x'].permute(0, 2, 3, 1).reshape(2, 4096, 2).to(DEV), gd['t'].to(DEV))
+    assert y.shape == (2, 2, 64, 64) and y.dtype == torch.float32
+    assert torch.equal(y, y2)
+    assert rel(y, gd['y']) < tol, rel(y, gd['y'])
+
+
+def test_unet_forward_tcgen05_vs_cuda_core_path(env, golden):
+    """Same bf16 operands through the tcgen05 kernels and through the CUDA-core implicit GEMM: both round the same
+    activations to bf16, so they agree to accumulation order + occasional 1-ulp flips (5e-3)."""
+    ops = env['ops']
+    ops.set_precision('bf16')
+    gd = golden('unet_darcy_fwd.pt')
+    model, _, _ = env['build']()
+    with torch.no_grad():
+        ops.set_tensor_core_conv(True)
+        y_tc = model(gd['x'].to(DEV), gd['t'].to(DEV))
+        ops.set_tensor_core_conv(False)
+        y_cc = model(gd['x'].to(DEV), gd['t'].to(DEV))
+        ops.set_tensor_core_conv(True)
+    assert rel(y_tc, y_cc) < 5e-3, rel(y_tc, y_cc)
+
+
+@pytest.mark.parametrize('mode,tol_loss,tol_grad', [('fp32', 5e-5, 1e-3), ('bf16', 3e-2, 8e-2)])
+def test_training_loss_and_gradients_match_reference(env, golden, mode, tol_loss, tol_grad):
+    env['ops'].set_precision(mode)
+    gd = golden('darcy_loss_mean.pt')
+    model, diff, res = env['build']()
+    loss, data_l, rabs, _, _ = diff.darcy_loss_from_draws(gd['x0'].to(DEV), gd['t'].to(DEV), gd['noise'].to(DEV), res,
+                                                          1.0, 1e-3)
+    assert abs(loss.item() / gd['loss'].item() - 1) < tol_loss
+    assert abs(data_l / gd['data_loss'].item() - 1) < tol_loss
+    assert abs(rabs / gd['residual_abs'].item() - 1) < tol_loss
+    loss.backward()
+    named = dict(model.named_parameters())
+    worst = {}
+    for k, v in gd.items():
+        if k.startswith('grad_') and k != 'grad_norm':
+            worst[k] = rel(named[k[5:]].grad, v)
+    assert max(worst.values()) < tol_grad, worst
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters() if p.grad is not None)).item()
+    assert abs(gn / gd['grad_norm'].item() - 1) < tol_grad
+    import os
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'params_without_grad.txt')) as f:
+        ref_dead = sorted(k for k in f.read().split() if not k.endswith('rotary_emb.freqs'))
+    dead = sorted(k for k, p in named.items() if p.requires_grad and p.grad is None)
+    assert dead == ref_dead
+
+
+def test_sample_mode_loss_matches_reference(env, golden):
+    env['ops'].set_precision('fp32')
+    gd = golden('darcy_loss_sample.pt')
+    model, diff, res = env['build'](use_ddim_x0=True)
+    loss, _, _, _, _ = diff.darcy_loss_from_draws(gd['x0'].to(DEV), gd['t'].to(DEV), gd['noise'].to(DEV), res, 1.0, 1e-3)
+    assert abs(loss.item() / gd['loss'].item() - 1) < 1e-4
+    loss.backward()
+    assert rel(model.final_conv[1].weight.grad, gd['grad_final_w']) < 2e-3
+    assert rel(model.init_conv.weight.grad, gd['grad_init_w']) < 2e-3
+
+
+def test_sampling_loop_matches_reference(env, golden, monkeypatch):
+    """p_sample_loop with the reference's own draws injected (x_T, then one z per step incl. t=0)."""
+    env['ops'].set_precision('fp32')
+    gd = golden('sample_loop_6.pt')
+    model, diff, res = env['build'](n_steps=6)
+    model.eval()
+    draws = [gd['x_T']] + list(gd['noises'])
+    it = iter(draws)
+    monkeypatch.setattr(torch, 'randn', lambda *a, **k: next(it).to(DEV))
+    monkeypatch.setattr(torch, 'randn_like', lambda *a, **k: next(it).to(DEV))
+    (x_seq, interm), aux = diff.p_sample_loop(None, (1, 2, 64, 64), save_output=True, surpress_noise=True,
+                                              residual_func=res, eval_residuals=True)
+    monkeypatch.undo()
+    assert len(x_seq) == 7 and len(interm) == 7 and not x_seq[-1].is_cuda
+    assert rel(x_seq[1], gd['x_after_first']) < 1e-4
+    assert rel(x_seq[-1], gd['x_final']) < 5e-4
+    assert rel(aux['residual'], gd['residual']) < 5e-3      # residual amplifies x0 differences by 1/h^2
+
+
+def test_engine_training_steps_match_oracle(env):
+    """3 optimizer steps of the flat-buffer engine (eager and CUDA-graph) vs the oracle's autograd + Adam + EMA."""
+    O, ops = env['O'], env['ops']
+    ops.set_precision('fp32')
+    from physicsinformeddiffusionmodels_b200.engine import TrainEngine
+    B = 2
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(B, 2, 64, 64, generator=g)
+    ts = [torch.tensor([3, 70]), torch.tensor([50, 9]), torch.tensor([99, 0])]
+    es = [torch.randn(B, 2, 64, 64, generator=g) for _ in ts]
+    tables = O.diffusion_tables(100)
+    sdr = {k: v.clone().requires_grad_('freqs' not in k) for k, v in env['sd'].items()}
+    train = [v for k, v in sdr.items() if v.requires_grad]
+    m = [torch.zeros_like(p) for p in train]
+    v = [torch.zeros_like(p) for p in train]
+    ema = [p.detach().clone() for p in train]
+    ref_losses = []
+    for step, (t, e) in enumerate(zip(ts, es), 1):
+        for p in train:
+            p.grad = None
+        loss, _ = O.darcy_training_loss(sdr, env['cfg'], x0, t, e, tables)
+        loss.backward()
+        ref_losses.append(loss.item())
+        with torch.no_grad():
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in train]
+            O.adam_ema_step(train, grads, m, v, ema, step)
+    model, diff, res = env['build']()
+    eng = TrainEngine(model, diff, res, use_graph=False)
+    losses = []
+    for t, e in zip(ts, es):
+        draws = iter([e])
+        orig_randint, orig_randn_like = torch.randint, torch.randn_like
+        torch.randint = lambda *a, **k: t.to(DEV)
+        torch.randn_like = lambda *a, **k: next(draws).to(DEV)
+        try:
+            loss, _, _ = eng.step(x0.to(DEV))
+        finally:
+            torch.randint, torch.randn_like = orig_randint, orig_randn_like
+        losses.append(loss.item())
+    for a, b in zip(losses, ref_losses):
+        assert abs(a / b - 1) < 2e-3, (losses, ref_losses)
+    named = dict(model.named_parameters())
+    for k in ('final_conv.1.weight', 'downs.0.0.block1.proj.weight', 'mid_spatial_attn.fn.fn.fn.to_qkv.weight'):
+        # Adam normalises every coordinate to |update| ~ lr, so parameters are compared by their UPDATE
+        upd = named[k].detach().cpu() - env['sd'][k]
+        upd_ref = sdr[k].detach() - env['sd'][k]
+        assert rel(upd, upd_ref) < 0.1, (k, rel(upd, upd_ref))
+    sd_ema = eng.ema_state_dict()
+    assert set(sd_ema.keys()) == set(env['sd'].keys())
+
+
+def test_engine_cuda_graph_replay_runs_and_learns(env):
+    env['ops'].set_precision('bf16')
+    from physicsinformeddiffusionmodels_b200.engine import TrainEngine
+    model, diff, res = env['build']()
+    eng = TrainEngine(model, diff, res, use_graph=True, lr=1e-3)
+    g = torch.Generator().manual_seed(22)
+    x0 = (0.5 * torch.randn(4, 2, 64, 64, generator=g)).to(DEV)
+    w0 = model.final_conv[1].weight.detach().clone()
+    first = None
+    for i in range(6):
+        loss, data_l, rabs = eng.step(x0)
+        if i == 0:
+            first = loss.item()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and first is not None
+    assert not torch.equal(model.final_conv[1].weight.detach(), w0)
+    assert int(eng.fp.step_dev.item()) == eng.steps_done
+
+
+def test_state_dict_roundtrip_and_cpu_rejection(env):
+    model, diff, res = env['build']()
+    sd = model.state_dict()
+    assert len(sd) == 317 and sum(v.numel() for v in sd.values()) == 10386514
+    assert list(sd.keys()) == list(env['sd'].keys())
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 2, 64, 64), torch.zeros(1, dtype=torch.long))     # CPU tensor: no fallback
+
+
+def test_smoke_entry_point():
+    import __graft_entry__
+    __graft_entry__.smoke()
