@@ -330,6 +330,13 @@ extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* 
                               int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
     TcPlan pl;
     PIDM_REQUIRE(tc_plan(B, H, W, Cin, Cout, KH, KW, pad, pl), "conv2d_tc: unsupported geometry");
+    // cuTensorMapEncodeTiled is a driver-API call: the calling thread (e.g. the autograd worker) may not have the
+    // primary context bound yet if no runtime call has run in it
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        PIDM_CUDA(cudaFree(0));
+        ctx_bound = true;
+    }
     EncodeTiledFn enc = get_encode();
     PIDM_REQUIRE(enc != nullptr, "conv2d_tc: cuTensorMapEncodeTiled is not available from the driver");
     PIDM_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "conv2d_tc: operands must be 16-byte aligned");

@@ -445,7 +445,7 @@ def test_adam_ema_step(pk):
              stream())
     assert abs(nsq.item() - (gr.double() ** 2).sum().item()) / nsq.item() < 1e-5
     assert torch.allclose(pd.cpu(), pr, rtol=1e-5, atol=1e-7) and torch.allclose(ed.cpu(), er, rtol=1e-5, atol=1e-7)
-    assert torch.allclose(md.cpu(), mr, rtol=1e-5, atol=1e-9) and torch.allclose(vd.cpu(), vr, rtol=1e-5, atol=1e-12)
+    assert torch.allclose(md.cpu(), mr, rtol=1e-4, atol=1e-9) and torch.allclose(vd.cpu(), vr, rtol=1e-4, atol=1e-12)
 
 
 def test_mechanics_residual_golden(pk, golden):
