@@ -83,10 +83,35 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference training iteration on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, batch=PER_GPU_BATCH):
+def log(msg):
+    print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
+
+
+def usable_cores():
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota (a shared GPU box reports
+    every host core in os.cpu_count(); spawning that many threads inside a small quota is pathologically slow)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def cpu_reference_steps(steps, warmup, batch=PER_GPU_BATCH, budget_s=150.0):
     from oracle import pidm_oracle as O
-    ncores = os.cpu_count() or 1
+    ncores = usable_cores()
     torch.set_num_threads(ncores)
+    log(f'cpu reference: {ncores} usable cores (os.cpu_count()={os.cpu_count()}), batch {batch}')
+    t_begin = time.perf_counter()
     cfg = O.unet_config(dim=32, channels=2)
     sd = O.make_test_state_dict(cfg, 0)
     sdr = {k: v.clone().requires_grad_('freqs' not in k) for k, v in sd.items()}
@@ -111,6 +136,10 @@ def cpu_reference_steps(steps, warmup, batch=PER_GPU_BATCH):
             O.adam_ema_step(train, grads, m, v, ema, it + 1)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
+        log(f'cpu reference: iteration {it} took {time.perf_counter() - t0:.2f} s')
+        if times and time.perf_counter() - t_begin > budget_s:
+            break                                  # bounded sample
+    steps = len(times)
     sec = sum(times) / len(times)
     return dict(value=batch / sec, unit='samples/s', cores=ncores, kind='port', ms_per_step=sec * 1e3,
                 sample=f'{steps} training iterations at batch {batch} after {warmup} warm-up, torch {torch.__version__} '
@@ -275,9 +304,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------------------------------
+    import faulthandler
+    faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)
+    log('warm-up (first call captures the CUDA graph)')
     for _ in range(args.warmup):
         eng.step(x0_dev)
     barrier()
+    log('timed region')
     launches0 = _lib.launch_count
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -290,6 +323,7 @@ def main():
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     last_loss = float(out[0].item())
+    log(f'device-resident: {ms / args.steps:.3f} ms/step')
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ------------------------------------
     for _ in range(3):
         x0_dev.copy_(x0_host, non_blocking=True)
@@ -312,6 +346,7 @@ def main():
 
     extra = {}
     if rank == 0:
+        log(f'e2e: {ms_e2e / args.steps:.3f} ms/step; per-kernel breakdown of one eager step')
         pk = peaks()
         c0 = _lib.launch_count
         agg = breakdown_one_step(eng, x0_dev)
@@ -332,6 +367,7 @@ def main():
             roof = {'bound': 'hbm', 'kernel': name, 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
                     'traffic': None, 'share_of_step_kernel_time': d['ms'] / total_ms}
         extra['roofline'] = roof
+        log('residual kernel sweep')
         extra['roofline_residual'] = residual_kernel_sweep(pk)
         extra['kernel_time_breakdown_ms'] = {k: {'ms': round(v['ms'], 4), 'calls': v['calls'],
                                                  'tflops': (v['flop'] / (v['ms'] * 1e-3) / 1e12) if v['flop'] else None}
@@ -345,6 +381,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
+        faulthandler.cancel_dump_traceback_later()
         sps = world * B * args.steps / (ms * 1e-3)
         sps_e2e = world * B * args.steps / (ms_e2e * 1e-3)
         tflops = 3 * FWD_GFLOP_PER_SAMPLE * 1e9 * sps / 1e12
