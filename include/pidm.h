@@ -90,6 +90,12 @@ int pidm_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, float* dbia
 int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
                    int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
+/* wgrad of the same layers on tcgen05: D[(tap,ci)][co] = sum over pixels with MN-major (pixel-strided) TMA operands,
+ * split over pixel ranges, red.global.add into dw (framework layout through strides); dbias by a column-sum kernel.
+ * x [B,H,W,Cin], dy [B,H,W,Cout] bf16; dw, dbias fp32 ACCUMULATED. */
+int pidm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, float* dbias, int B, int H, int W, int Cin, int Cout,
+                         int KH, int KW, int pad, long long w_stride_n, long long w_stride_c, void* stream);
+int pidm_conv2d_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
 
 /* ---- normalisations ------------------------------------------------------------------------------------ */
 /* Block.forward tail: GroupNorm(G) -> *(scale+1)+shift -> SiLU (src/unet_model.py:233-241).  scale_shift [B,2C] or NULL.

@@ -102,8 +102,9 @@ struct TcCfg {
     static constexpr int A_BYTES = TC_BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    // big tiles: fill shared memory (one CTA per SM); small tiles: a short ring so that 2-5 CTAs co-reside per SM
+    // and hide each other's TMA / MMA / epilogue latencies (the 64x64 layers are latency-, not throughput-bound)
+    static constexpr int STAGES = STAGE_BYTES >= 40 * 1024 ? 4 : (STAGE_BYTES > 24 * 1024 ? 3 : 4);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 

@@ -160,8 +160,14 @@ class _Conv2d(torch.autograd.Function):
                 _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
         gw_buf, gw_ret = _grad_buffer(weight)
         gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
-        call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW, stride,
-             pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
+        if (_STATE['use_tc'] and x.dtype == torch.bfloat16 and stride == 1 and not spec.transposed and Ho == H
+                and Wo == W and Cin == spec.cin_real
+                and call('pidm_conv2d_wgrad_tc_supported', B, H, W, Cin, Cout, KH, KW, pad)):
+            call('pidm_conv2d_wgrad_tc', x, dy, gw_buf, gb_buf, B, H, W, Cin, Cout, KH, KW, pad, spec.w_stride_n,
+                 spec.w_stride_c, stream())
+        else:
+            call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW,
+                 stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
         return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None
 
 

@@ -463,3 +463,45 @@ def test_mechanics_residual_golden(pk, golden):
     ((out['residual'] * gd['cotangent'].to(DEV)).sum() + 0.3 * out['optimizer'].sum()
      + 2.0 * out['inequality'].sum()).backward()
     assert rel(x.grad, gd['grad_x0_pred']) < 5e-5
+
+
+WG_CASES = [
+    # B, H, Cin, Cout, k
+    (2, 64, 32, 32, 3),       # 64x64 C=32: 4 taps per M' tile (64B swizzle atoms), 3 M' tiles, last one padded
+    (2, 32, 64, 64, 3),       # 128B atoms, 2 (tap,chunk) pairs per tile
+    (2, 32, 32, 64, 3),
+    (4, 16, 128, 128, 3),
+    (3, 8, 256, 256, 3),      # odd batch with TN = 2
+    (2, 64, 32, 768, 1),      # to_qkv
+    (2, 64, 256, 32, 1),      # to_out
+    (2, 16, 256, 64, 3),
+    (2, 8, 512, 128, 3),
+    (2, 16, 64, 96, 3),       # Cout % 64 != 0 -> N' = 32
+]
+
+
+@pytest.mark.parametrize('case', WG_CASES, ids=[f'B{c[0]}_H{c[1]}_C{c[2]}x{c[3]}_k{c[4]}' for c in WG_CASES])
+def test_wgrad_tcgen05_matches_reference(pk, case):
+    """tcgen05 wgrad (MN-major TMA operands, split over pixels, fp32 atomics) vs autograd of F.conv2d on
+    bf16-representable operands: fp32 accumulation both sides -> 2e-3 (summation order over up to 131072 pixels)."""
+    ops, packing = pk
+    from physicsinformeddiffusionmodels_b200._lib import call, stream
+    B, H, Cin, Cout, k = case
+    assert call('pidm_conv2d_wgrad_tc_supported', B, H, H, Cin, Cout, k, k, k // 2) == 1
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, Cin, H, H, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, 1, k, k, generator=g) / math.sqrt(Cin * k * k)).requires_grad_(True)
+    b = torch.zeros(Cout, requires_grad=True)
+    y = F.conv2d(x, w[:, :, 0], b, padding=k // 2)
+    cot = torch.randn(y.shape, generator=g).bfloat16().float()
+    (y * cot).sum().backward()
+    xd, dyd = nhwc(x, torch.bfloat16).to(DEV), nhwc(cot, torch.bfloat16).to(DEV)
+    dw = torch.zeros(Cout, Cin, 1, k, k, device=DEV)
+    db = torch.zeros(Cout, device=DEV)
+    call('pidm_conv2d_wgrad_tc', xd, dyd, dw, db, B, H, H, Cin, Cout, k, k, k // 2, Cin * k * k, k * k, stream())
+    torch.cuda.synchronize()
+    assert rel(dw, w.grad) < 2e-3, rel(dw, w.grad)
+    assert rel(db, b.grad) < 2e-3
+    # accumulate semantics: a second call doubles the buffers
+    call('pidm_conv2d_wgrad_tc', xd, dyd, dw, db, B, H, H, Cin, Cout, k, k, k // 2, Cin * k * k, k * k, stream())
+    assert rel(dw, 2 * w.grad) < 2e-3
