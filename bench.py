@@ -200,13 +200,17 @@ def breakdown_one_step(engine, x0):
         if name in ('pidm_conv2d_tc',):
             B, H, W, Cin, Cout, KH, KW = a[5], a[6], a[7], a[8], a[9], a[10], a[11]
             flop = 2.0 * B * H * W * Cout * KH * KW * Cin
+        elif name == 'pidm_conv2d_tc_general':
+            B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[5], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
+            taps = KH * KW / (stride * stride) if tr else KH * KW
+            flop = 2.0 * B * Ho * Wo * Cout * taps * Cin
         elif name == 'pidm_conv2d_simt':
             B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[5], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
             taps = KH * KW / (stride * stride) if tr else KH * KW       # useful taps of the transposed gather
             flop = 2.0 * B * Ho * Wo * Cout * taps * Cin
         elif name == 'pidm_conv2d_wgrad_tc':
-            B, H, W, Cin, Cout, KH, KW = a[4], a[5], a[6], a[7], a[8], a[9], a[10]
-            flop = 2.0 * B * H * W * Cout * KH * KW * Cin
+            B, CAr, GH, GW, CB, KH, KW = a[3], a[7], a[8], a[9], a[10], a[11], a[12]
+            flop = 2.0 * B * GH * GW * CB * KH * KW * CAr
         elif name == 'pidm_conv2d_wgrad_simt':
             B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[4], a[7], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
             taps = KH * KW / (stride * stride) if tr else KH * KW
@@ -357,7 +361,8 @@ def main():
         total_ms = sum(d['ms'] for d in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
         name, d = top[0]
-        tensor_names = ('pidm_conv2d_tc', 'pidm_conv2d_simt', 'pidm_conv2d_wgrad_simt', 'pidm_conv2d_wgrad_tc')
+        tensor_names = ('pidm_conv2d_tc', 'pidm_conv2d_tc_general', 'pidm_conv2d_simt', 'pidm_conv2d_wgrad_simt',
+                        'pidm_conv2d_wgrad_tc')
         if name in tensor_names and d['flop'] > 0:
             ach = d['flop'] / (d['ms'] * 1e-3) / 1e12
             peak = pk['bf16_sustained'] or pk['bf16_tflops']

@@ -90,12 +90,23 @@ int pidm_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, float* dbia
 int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
                    int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
-/* wgrad of the same layers on tcgen05: D[(tap,ci)][co] = sum over pixels with MN-major (pixel-strided) TMA operands,
- * split over pixel ranges, red.global.add into dw (framework layout through strides); dbias by a column-sum kernel.
- * x [B,H,W,Cin], dy [B,H,W,Cout] bf16; dw, dbias fp32 ACCUMULATED. */
-int pidm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, float* dbias, int B, int H, int W, int Cin, int Cout,
-                         int KH, int KW, int pad, long long w_stride_n, long long w_stride_c, void* stream);
-int pidm_conv2d_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
+/* General tensor-core path: stride-1/2 regular convolution (input sampled through TMA elementStrides) and the
+ * stride-2 transposed gather (ConvTranspose forward / dgrad of the stride-2 conv) as 4 output-parity classes. */
+int pidm_conv2d_tc_general(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B,
+                           int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
+                           int transposed, void* stream);
+int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride,
+                                     int pad, int transposed);
+/* wgrad on tcgen05: D[(tap,cA)][cB] = sum over grid pixels g of a[a_stride*g - pad + tap][cA] * b[g][cB], MN-major
+ * (pixel-strided) TMA operands, split over pixel ranges, red.global.add into dw[cA*s_row + cB*s_col + tap] (fp32,
+ * ACCUMULATED).  Regular conv: a = x, b = dy.  ConvTranspose: a = dy (a_stride 2), b = x.  Rows cA >= CA_real (channel
+ * padding) are dropped. */
+int pidm_conv2d_wgrad_tc(const void* a, const void* b, float* dw, int B, int HA, int WA, int CA, int CA_real, int GH,
+                         int GW, int CB, int KH, int KW, int a_stride, int pad, long long s_row, long long s_col,
+                         void* stream);
+int pidm_conv2d_wgrad_tc_supported(int B, int GH, int GW, int CA, int CB, int KH, int KW, int a_stride);
+/* out[c] += sum_m x[m][c]: bias gradients (column sums of an NHWC tensor) */
+int pidm_colsum(const void* x, float* out, long long M, int C, int dtype, void* stream);
 
 /* ---- normalisations ------------------------------------------------------------------------------------ */
 /* Block.forward tail: GroupNorm(G) -> *(scale+1)+shift -> SiLU (src/unet_model.py:233-241).  scale_shift [B,2C] or NULL.

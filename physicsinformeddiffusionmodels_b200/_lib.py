@@ -37,8 +37,11 @@ _SIGS = {
     'pidm_conv2d_wgrad_simt': [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, L, L, I, P],
     'pidm_conv2d_tc': [P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     'pidm_conv2d_tc_supported': [I, I, I, I, I, I, I, I],
-    'pidm_conv2d_wgrad_tc': [P, P, P, P, I, I, I, I, I, I, I, I, L, L, P],
+    'pidm_conv2d_tc_general': [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
+    'pidm_conv2d_tc_general_supported': [I, I, I, I, I, I, I, I, I, I, I, I],
+    'pidm_conv2d_wgrad_tc': [P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, L, L, P],
     'pidm_conv2d_wgrad_tc_supported': [I, I, I, I, I, I, I, I],
+    'pidm_colsum': [P, P, L, I, I, P],
     'pidm_groupnorm_silu_fwd': [P, P, P, P, P, P, I, I, I, I, F, I, P],
     'pidm_groupnorm_silu_bwd': [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     'pidm_layernorm_c_fwd': [P, P, P, L, I, F, I, P],
@@ -65,7 +68,7 @@ _SIGS = {
 }
 # functions whose int return value is a result, not an error code
 _VALUE_RETURN = {'pidm_pack_entry_size', 'pidm_mlp_entry_size', 'pidm_linattn_workspace_floats', 'pidm_version',
-                 'pidm_conv2d_tc_supported', 'pidm_conv2d_wgrad_tc_supported'}
+                 'pidm_conv2d_tc_supported', 'pidm_conv2d_wgrad_tc_supported', 'pidm_conv2d_tc_general_supported'}
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f'{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). '

@@ -86,14 +86,26 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return d;
 }
 
+struct TcClass {             // one output-parity class of a transposed (stride-2) gather: <= 16 taps
+    int n_taps, off_h, off_w;
+    signed char dh[16], dw[16];
+    short ktap[16];          // tap index into the packed weights (k offset = ktap * Cin)
+};
+
 struct TcParams {
-    int B, H, W, Cin, Cout;
+    int B, GH, GW;           // pixel grid that forms the GEMM M dimension (TW == GW)
+    int Cin, Cout;
+    int mode;                // 0: regular conv, taps by formula (KH, KW, pad), input sampled with in_stride
+                             // 1: transposed gather, per-class tap tables, output scattered with out_scale / offsets
     int KH, KW, pad;
-    int TW, TH, TN;        // pixel box; TW*TH*TN == 128
-    int tiles_h;           // H / TH
+    int in_stride, out_scale;
+    int Ho, Wo;              // spatial size of the output tensor
+    int TW, TH, TN;          // pixel box; TW*TH*TN == 128
+    int tiles_h;             // GH / TH
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* y;
+    TcClass cls[4];
 };
 
 template <int BN, int BK>
@@ -128,7 +140,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
     const int b0 = tb * p.TN, h0 = th_idx * p.TH;
     const int kc_per_tap = p.Cin / BK;
-    const int n_iters = p.KH * p.KW * kc_per_tap;
+    const TcClass& cl = p.cls[blockIdx.z];
+    const int n_taps = (p.mode == 0) ? p.KH * p.KW : cl.n_taps;
+    const int n_iters = n_taps * kc_per_tap;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -157,12 +171,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t ph = (it / Cfg::STAGES) & 1;
                 tc_mbar_wait(&empty[s], ph ^ 1);
                 const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
-                const int r = tap / p.KW, q = tap - r * p.KW;
+                int dh, dw, ktap;
+                if (p.mode == 0) {
+                    const int r = tap / p.KW, q = tap - r * p.KW;
+                    dh = r - p.pad; dw = q - p.pad; ktap = tap;
+                } else {
+                    dh = cl.dh[tap]; dw = cl.dw[tap]; ktap = cl.ktap[tap];
+                }
                 unsigned char* a_dst = ring + s * Cfg::STAGE_BYTES;
                 unsigned char* b_dst = a_dst + Cfg::A_BYTES;
                 tc_mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                tma_load_4d(a_dst, &map_x, &full[s], kc * BK, q - p.pad, h0 + r - p.pad, b0);
-                tma_load_2d(b_dst, &map_w, &full[s], tap * p.Cin + kc * BK, n0);
+                tma_load_4d(a_dst, &map_x, &full[s], kc * BK, dw, p.in_stride * h0 + dh, b0);
+                tma_load_2d(b_dst, &map_w, &full[s], ktap * p.Cin + kc * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -210,8 +230,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int rem = m - tn * p.TH * p.TW;
         const int th = rem / p.TW, tw = rem - th * p.TW;
         const int b = b0 + tn, h = h0 + th;
-        const bool row_ok = (b < p.B) && (h < p.H);
-        const size_t row_off = (((size_t)b * p.H + h) * p.W + tw) * p.Cout + n0;
+        const bool row_ok = (b < p.B) && (h < p.GH);
+        const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * tw + cl.off_w;
+        const size_t row_off = (((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0;
         tc_mbar_wait(acc_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -281,19 +302,20 @@ struct TcPlan {
     int TW, TH, TN, BN, BK;
 };
 
-static bool tc_plan(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, TcPlan& pl) {
-    if (KH != KW || (KH & 1) == 0 || 2 * pad != KH - 1) return false;
-    if (W > 128 || (128 % W) != 0) return false;
+// GH x GW = pixel grid of the GEMM (output grid for regular convs, input grid for the transposed gather)
+static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int in_stride, int classes, TcPlan& pl) {
+    if (GW > 128 || GW < 1 || (128 % GW) != 0) return false;
     if (Cin % 32 != 0 || Cout % 32 != 0) return false;
-    pl.TW = W;
-    int th = 128 / W;
-    if (th > H) th = H;
-    if (H % th != 0) return false;
+    pl.TW = GW;
+    int th = 128 / GW;
+    if (th > GH) th = GH;
+    if (GH % th != 0) return false;
     pl.TH = th;
     pl.TN = 128 / (pl.TW * pl.TH);
     if (pl.TW * pl.TH * pl.TN != 128) return false;
+    if (pl.TW * in_stride > 256 || pl.TH * in_stride > 256) return false;      // TMA box limit
     pl.BK = (Cin % 64 == 0) ? 64 : 32;
-    const long long m_tiles = (long long)((B + pl.TN - 1) / pl.TN) * (H / pl.TH);
+    const long long m_tiles = (long long)((B + pl.TN - 1) / pl.TN) * (GH / pl.TH) * classes;
     const int cands[4] = {256, 128, 64, 32};
     pl.BN = 0;
     for (int i = 0; i < 4; ++i) {
@@ -319,18 +341,49 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
     return 0;
 }
 
-}  // namespace pidm
-using namespace pidm;
-
-extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad) {
-    TcPlan pl;
-    return tc_plan(B, H, W, Cin, Cout, KH, KW, pad, pl) ? 1 : 0;
+// geometry of one call -> (pixel grid, classes).  Returns false when the tensor-core kernel does not cover it.
+static bool tc_geometry(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
+                        int transposed, TcParams& p, TcPlan& pl, int& classes) {
+    if (KH != KW) return false;
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad; p.Ho = Ho; p.Wo = Wo;
+    for (int c = 0; c < 4; ++c) { p.cls[c].n_taps = 0; p.cls[c].off_h = 0; p.cls[c].off_w = 0; }
+    if (!transposed) {
+        if (stride != 1 && stride != 2) return false;
+        if ((H + 2 * pad - KH) / stride + 1 != Ho || (W + 2 * pad - KW) / stride + 1 != Wo) return false;
+        p.mode = 0; p.GH = Ho; p.GW = Wo; p.in_stride = stride; p.out_scale = 1; classes = 1;
+    } else {
+        if (stride != 2 || (KH & 1) || Ho != 2 * H || Wo != 2 * W) return false;     // 4x4/s2/p1 style up-sampling
+        p.mode = 1; p.GH = H; p.GW = W; p.in_stride = 1; p.out_scale = 2; classes = 4;
+        for (int pa = 0; pa < 2; ++pa)
+            for (int pb = 0; pb < 2; ++pb) {
+                TcClass& c = p.cls[pa * 2 + pb];
+                c.off_h = pa; c.off_w = pb;
+                for (int r = 0; r < KH; ++r) {
+                    if ((pa + pad - r) & 1) continue;
+                    for (int q = 0; q < KW; ++q) {
+                        if ((pb + pad - q) & 1) continue;
+                        if (c.n_taps >= 16) return false;
+                        c.dh[c.n_taps] = (signed char)((pa + pad - r) / 2);
+                        c.dw[c.n_taps] = (signed char)((pb + pad - q) / 2);
+                        c.ktap[c.n_taps] = (short)(r * KW + q);
+                        ++c.n_taps;
+                    }
+                }
+            }
+    }
+    if (!tc_plan(B, p.GH, p.GW, Cin, Cout, p.in_stride, classes, pl)) return false;
+    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = p.GH / pl.TH;
+    return true;
 }
 
-extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
-                              int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
+static int tc_run(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
+                  int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int transposed,
+                  cudaStream_t st) {
+    TcParams p;
     TcPlan pl;
-    PIDM_REQUIRE(tc_plan(B, H, W, Cin, Cout, KH, KW, pad, pl), "conv2d_tc: unsupported geometry");
+    int classes = 1;
+    PIDM_REQUIRE(tc_geometry(B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed, p, pl, classes),
+                 "conv2d_tc: unsupported geometry");
     // cuTensorMapEncodeTiled is a driver-API call: the calling thread (e.g. the autograd worker) may not have the
     // primary context bound yet if no runtime call has run in it
     static thread_local bool ctx_bound = false;
@@ -344,10 +397,12 @@ extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* 
     CUtensorMap mx, mw;
     const CUtensorMapSwizzle sw = pl.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
+        const int s = p.in_stride;
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)pl.BK, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)pl.TN};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        // with elementStrides = s the box spans boxDim global elements and loads boxDim / s of them
+        cuuint32_t box[4] = {(cuuint32_t)pl.BK, (cuuint32_t)(pl.TW * s), (cuuint32_t)(pl.TH * s), (cuuint32_t)pl.TN};
+        cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
         CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -364,15 +419,37 @@ extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
     }
-    TcParams p;
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
-    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = H / pl.TH;
     p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = (__nv_bfloat16*)y;
-    dim3 grid(((B + pl.TN - 1) / pl.TN) * p.tiles_h, Cout / pl.BN);
-    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(((B + pl.TN - 1) / pl.TN) * p.tiles_h, Cout / pl.BN, classes);
 #define TC_CASE(bn, bk) if (pl.BN == bn && pl.BK == bk) return launch_tc<bn, bk>(mx, mw, p, grid, st)
     TC_CASE(256, 64); TC_CASE(128, 64); TC_CASE(64, 64); TC_CASE(32, 64);
     TC_CASE(256, 32); TC_CASE(128, 32); TC_CASE(64, 32); TC_CASE(32, 32);
 #undef TC_CASE
     return set_error(2, "conv2d_tc: no kernel for BN=%d BK=%d", pl.BN, pl.BK);
+}
+
+}  // namespace pidm
+using namespace pidm;
+
+extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad) {
+    TcParams p; TcPlan pl; int classes;
+    return (2 * pad == KH - 1 && tc_geometry(B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, p, pl, classes)) ? 1 : 0;
+}
+
+extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
+                              int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
+    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, (cudaStream_t)stream);
+}
+
+extern "C" int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
+                                                int stride, int pad, int transposed) {
+    TcParams p; TcPlan pl; int classes;
+    return tc_geometry(B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed, p, pl, classes) ? 1 : 0;
+}
+
+extern "C" int pidm_conv2d_tc_general(const void* x, const void* w_packed, const float* bias, const void* residual,
+                                      void* y, int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
+                                      int stride, int pad, int transposed, void* stream) {
+    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed,
+                  (cudaStream_t)stream);
 }

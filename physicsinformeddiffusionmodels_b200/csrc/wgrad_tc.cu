@@ -69,12 +69,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lb
 }
 
 struct WgParams {
-    int B, H, W, Cin, Cout;
-    int KH, KW, pad;
+    int B, Cin, Cout;            // Cin = channels of the A-side (gathered) tensor, Cout = channels of the B-side tensor
+    int c_real;                  // A-side channels >= c_real are padding (their rows are not written)
+    int KH, KW, pad, a_stride;   // A-side pixel = a_stride * g - pad + tap for grid pixel g
     int TW, TH, TN, tiles_h;
     int n_pix_tiles, tiles_per_split;
     float* dw;
-    long long s_n, s_c;          // dw index = co*s_n + ci*s_c + tap
+    long long s_row, s_col;      // dw index = cA*s_row + cB*s_col + tap
 };
 
 template <int NP, int ATOM_A, int ATOM_B>
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                         if (pr >= n_pairs) pr = n_pairs - 1;      // padding rows of the last M' tile (discarded later)
                         const int tap = pr / chunks, ch = pr - tap * chunks;
                         const int r = tap / p.KW, q = tap - r * p.KW;
-                        wg_tma_4d(a_dst + j * Cfg::A_TILE, &map_x, &full[s], ch * ATOM_A, q - p.pad, h0 + r - p.pad, b0);
+                        wg_tma_4d(a_dst + j * Cfg::A_TILE, &map_x, &full[s], ch * ATOM_A, q - p.pad, p.a_stride * h0 + r - p.pad, b0);
                     }
 #pragma unroll
                     for (int j = 0; j < Cfg::NB; ++j)
@@ -193,10 +194,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const int mrow = quarter * 32 + lane;             // accumulator row = (pair j, channel within atom)
             const int j = mrow / ATOM_A, cl = mrow - j * ATOM_A;
             const int pr = mt * Cfg::NA + j;
-            const bool row_ok = pr < n_pairs;
-            const int tap = row_ok ? pr / chunks : 0;
-            const int ci = row_ok ? (pr - tap * chunks) * ATOM_A + cl : 0;
-            float* dst = p.dw + (long long)ci * p.s_c + tap;
+            const int tap = (pr < n_pairs) ? pr / chunks : 0;
+            const int ci = (pr < n_pairs) ? (pr - tap * chunks) * ATOM_A + cl : 0;
+            const bool row_ok = (pr < n_pairs) && (ci < p.c_real);
+            float* dst = p.dw + (long long)ci * p.s_row + tap;
             wg_mbar_wait(acc_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 if (row_ok) {
 #pragma unroll
                     for (int n = 0; n < 32; ++n)
-                        atomicAdd(dst + (long long)(n0 + c + n) * p.s_n, __uint_as_float(v[n]));
+                        atomicAdd(dst + (long long)(n0 + c + n) * p.s_col, __uint_as_float(v[n]));
                 }
             }
         }
@@ -267,30 +268,33 @@ static WgEncodeFn wg_get_encode() {
 
 struct WgPlan { int TW, TH, TN, NP, AA, AB; };
 
-static bool wg_plan(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, WgPlan& pl) {
-    if (KH != KW || (KH & 1) == 0 || 2 * pad != KH - 1) return false;
-    if (W > 128 || (128 % W) != 0) return false;
-    if (Cin % 32 != 0 || Cout % 32 != 0) return false;
-    pl.TW = W;
-    int th = 128 / W;
-    if (th > H) th = H;
-    if (H % th != 0) return false;
+// GH x GW: pixel grid of the reduction (the B-side tensor's spatial size); the A side is sampled at a_stride*g-pad+tap
+static bool wg_plan(int B, int GH, int GW, int CA, int CB, int a_stride, WgPlan& pl) {
+    if (GW > 128 || GW < 1 || (128 % GW) != 0) return false;
+    if (CA % 32 != 0 || CB % 32 != 0) return false;
+    if (a_stride != 1 && a_stride != 2) return false;
+    pl.TW = GW;
+    int th = 128 / GW;
+    if (th > GH) th = GH;
+    if (GH % th != 0) return false;
     pl.TH = th;
     pl.TN = 128 / (pl.TW * pl.TH);
     if (pl.TW * pl.TH * pl.TN != 128) return false;
-    pl.AA = (Cin % 64 == 0) ? 64 : 32;
-    pl.AB = (Cout % 64 == 0) ? 64 : 32;
-    pl.NP = (Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32);
+    if (pl.TW * a_stride > 256 || pl.TH * a_stride > 256) return false;
+    pl.AA = (CA % 64 == 0) ? 64 : 32;
+    pl.AB = (CB % 64 == 0) ? 64 : 32;
+    pl.NP = (CB % 128 == 0) ? 128 : ((CB % 64 == 0) ? 64 : 32);
     return true;
 }
 
-static int wg_encode(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int atom, int TW, int TH, int TN) {
+static int wg_encode(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int atom, int TW, int TH, int TN,
+                     int es_) {
     WgEncodeFn enc = wg_get_encode();
     PIDM_REQUIRE(enc != nullptr, "wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)atom, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)atom, (cuuint32_t)(TW * es_), (cuuint32_t)(TH * es_), (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, (cuuint32_t)es_, (cuuint32_t)es_, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, atom == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -315,17 +319,19 @@ static int wg_launch(const CUtensorMap& mx, const CUtensorMap& my, const WgParam
 }  // namespace pidm
 using namespace pidm;
 
-extern "C" int pidm_conv2d_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad) {
+extern "C" int pidm_conv2d_wgrad_tc_supported(int B, int GH, int GW, int CA, int CB, int KH, int KW, int a_stride) {
     WgPlan pl;
-    return wg_plan(B, H, W, Cin, Cout, KH, KW, pad, pl) ? 1 : 0;
+    return (KH == KW && wg_plan(B, GH, GW, CA, CB, a_stride, pl)) ? 1 : 0;
 }
 
-// dw (fp32, framework layout through strides) and dbias are ACCUMULATED.  bf16 activations only.
-extern "C" int pidm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
-                                    int Cout, int KH, int KW, int pad, long long w_stride_n, long long w_stride_c,
-                                    void* stream) {
+// D[(tap, cA)][cB] = sum over grid pixels g of a[a_stride*g - pad + tap][cA] * b[g][cB], ACCUMULATED into
+// dw[cA*s_row + cB*s_col + tap] (fp32).  a: [B,HA,WA,CA] bf16 (CA may be channel-padded: rows >= CA_real are dropped),
+// b: [B,GH,GW,CB] bf16.
+extern "C" int pidm_conv2d_wgrad_tc(const void* a, const void* b, float* dw, int B, int HA, int WA, int CA, int CA_real,
+                                    int GH, int GW, int CB, int KH, int KW, int a_stride, int pad, long long s_row,
+                                    long long s_col, void* stream) {
     WgPlan pl;
-    PIDM_REQUIRE(wg_plan(B, H, W, Cin, Cout, KH, KW, pad, pl), "conv2d_wgrad_tc: unsupported geometry");
+    PIDM_REQUIRE(KH == KW && wg_plan(B, GH, GW, CA, CB, a_stride, pl), "conv2d_wgrad_tc: unsupported geometry");
     static thread_local bool ctx_bound = false;
     if (!ctx_bound) {
         PIDM_CUDA(cudaFree(0));
@@ -333,36 +339,40 @@ extern "C" int pidm_conv2d_wgrad_tc(const void* x, const void* dy, float* dw, fl
     }
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap mx, my;
-    if (int e = wg_encode(&mx, x, B, H, W, Cin, pl.AA, pl.TW, pl.TH, pl.TN)) return e;
-    if (int e = wg_encode(&my, dy, B, H, W, Cout, pl.AB, pl.TW, pl.TH, pl.TN)) return e;
+    if (int e = wg_encode(&mx, a, B, HA, WA, CA, pl.AA, pl.TW, pl.TH, pl.TN, a_stride)) return e;
+    if (int e = wg_encode(&my, b, B, GH, GW, CB, pl.AB, pl.TW, pl.TH, pl.TN, 1)) return e;
     WgParams p;
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
-    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = H / pl.TH;
+    p.B = B; p.Cin = CA; p.Cout = CB; p.c_real = CA_real; p.KH = KH; p.KW = KW; p.pad = pad; p.a_stride = a_stride;
+    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = GH / pl.TH;
     p.n_pix_tiles = ((B + pl.TN - 1) / pl.TN) * p.tiles_h;
-    p.dw = dw; p.s_n = w_stride_n; p.s_c = w_stride_c;
+    p.dw = dw; p.s_row = s_row; p.s_col = s_col;
     const int na = 128 / pl.AA;
-    const int n_pairs = KH * KW * (Cin / pl.AA);
+    const int n_pairs = KH * KW * (CA / pl.AA);
     const int m_tiles = (n_pairs + na - 1) / na;
-    const int n_tiles = Cout / pl.NP;
+    const int n_tiles = CB / pl.NP;
     int splits = (148 * 2 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
     if (splits > p.n_pix_tiles) splits = p.n_pix_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_split = (p.n_pix_tiles + splits - 1) / splits;
     splits = (p.n_pix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
     dim3 grid(m_tiles, n_tiles, splits);
-#define WG_CASE(np, aa, ab) if (pl.NP == np && pl.AA == aa && pl.AB == ab) { if (int e = wg_launch<np, aa, ab>(mx, my, p, grid, st)) return e; }
-    WG_CASE(128, 64, 64) else WG_CASE(128, 32, 64) else WG_CASE(64, 64, 64) else WG_CASE(64, 32, 64)
-    else WG_CASE(32, 64, 32) else WG_CASE(32, 32, 32)
-    else return set_error(2, "conv2d_wgrad_tc: no kernel for NP=%d AA=%d AB=%d", pl.NP, pl.AA, pl.AB);
+#define WG_CASE(np, aa, ab) if (pl.NP == np && pl.AA == aa && pl.AB == ab) return wg_launch<np, aa, ab>(mx, my, p, grid, st)
+    WG_CASE(128, 64, 64); WG_CASE(128, 32, 64); WG_CASE(64, 64, 64); WG_CASE(64, 32, 64);
+    WG_CASE(32, 64, 32); WG_CASE(32, 32, 32);
 #undef WG_CASE
-    if (dbias) {
-        long long M = (long long)B * H * W;
-        int oct = Cout / 8, rows = 256 / oct;
-        if (rows < 1) rows = 1;
-        int grid1 = (int)((M + rows * 8 - 1) / (rows * 8));
-        if (grid1 > 148 * 4) grid1 = 148 * 4;
-        colsum_kernel<__nv_bfloat16><<<grid1, oct * rows, Cout * sizeof(float), st>>>((const __nv_bfloat16*)dy, dbias, M, Cout);
-        PIDM_LAUNCH_CHECK("colsum");
-    }
+    return set_error(2, "conv2d_wgrad_tc: no kernel for NP=%d AA=%d AB=%d", pl.NP, pl.AA, pl.AB);
+}
+
+// out[c] += sum_m x[m][c]   (bias gradient: column sums of an NHWC tensor)
+extern "C" int pidm_colsum(const void* x, float* out, long long M, int C, int dtype, void* stream) {
+    PIDM_REQUIRE(C % 8 == 0 && C / 8 <= 1024, "colsum: C must be a multiple of 8");
+    int oct = C / 8, rows = 256 / oct;
+    if (rows < 1) rows = 1;
+    int grid1 = (int)((M + rows * 8 - 1) / (rows * 8));
+    if (grid1 > 148 * 4) grid1 = 148 * 4;
+    if (grid1 < 1) grid1 = 1;
+    PIDM_DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid1, oct * rows, C * sizeof(float), (cudaStream_t)stream>>>(
+                                   (const T*)x, out, M, C)));
+    PIDM_LAUNCH_CHECK("colsum");
     return 0;
 }

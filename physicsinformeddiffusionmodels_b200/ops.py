@@ -120,9 +120,11 @@ def concat(a, b):
 def _conv_launch(x, wp, bias, residual, y, g, transposed):
     """g = (B,H,W,Cin,Ho,Wo,Cout,KH,KW,stride,pad)."""
     B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = g
-    if (_STATE['use_tc'] and x.dtype == torch.bfloat16 and stride == 1 and not transposed and Ho == H and Wo == W
-            and call('pidm_conv2d_tc_supported', B, H, W, Cin, Cout, KH, KW, pad)):
-        call('pidm_conv2d_tc', x, wp, bias, residual, y, B, H, W, Cin, Cout, KH, KW, pad, stream())
+    tr = 1 if transposed else 0
+    if (_STATE['use_tc'] and x.dtype == torch.bfloat16
+            and call('pidm_conv2d_tc_general_supported', B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, tr)):
+        call('pidm_conv2d_tc_general', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, tr,
+             stream())
     else:
         call('pidm_conv2d_simt', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad,
              1 if transposed else 0, _code(x), stream())
@@ -160,11 +162,19 @@ class _Conv2d(torch.autograd.Function):
                 _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
         gw_buf, gw_ret = _grad_buffer(weight)
         gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
-        if (_STATE['use_tc'] and x.dtype == torch.bfloat16 and stride == 1 and not spec.transposed and Ho == H
-                and Wo == W and Cin == spec.cin_real
-                and call('pidm_conv2d_wgrad_tc_supported', B, H, W, Cin, Cout, KH, KW, pad)):
-            call('pidm_conv2d_wgrad_tc', x, dy, gw_buf, gb_buf, B, H, W, Cin, Cout, KH, KW, pad, spec.w_stride_n,
-                 spec.w_stride_c, stream())
+        use_tc = _STATE['use_tc'] and x.dtype == torch.bfloat16
+        if use_tc and not spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, Ho, Wo, Cin, Cout, KH, KW, stride):
+            # D[(tap, ci)][co]: gathered operand = x, reduction grid = output pixels
+            call('pidm_conv2d_wgrad_tc', x, dy, gw_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW, stride, pad,
+                 spec.w_stride_c, spec.w_stride_n, stream())
+            if gb_buf is not None:
+                call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
+        elif use_tc and spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, H, W, Cout, Cin, KH, KW, stride):
+            # ConvTranspose: D[(tap, co)][ci]: gathered operand = dy (sampled with the stride), grid = input pixels
+            call('pidm_conv2d_wgrad_tc', dy, x, gw_buf, B, Ho, Wo, Cout, Cout, H, W, Cin, KH, KW, stride, pad,
+                 spec.w_stride_n, spec.w_stride_c, stream())
+            if gb_buf is not None:
+                call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
         else:
             call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW,
                  stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())

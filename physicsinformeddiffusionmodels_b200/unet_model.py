@@ -212,7 +212,9 @@ class Unet3D(nn.Module):
     def _build_plan(self):
         pk = WeightPacker()
         self._packer = pk
-        self._cin_pad = _round_up(self.input_channels, 8)
+        # the 2-channel (10 for mechanics) input is zero-padded to 32 channels so that the 7x7 stem runs on the
+        # tensor-core kernels too (K step = 32 channels = one 64-byte swizzle span)
+        self._cin_pad = _round_up(self.input_channels, 32)
         k = self.init_kernel_size
         self._spec = {}
 

@@ -487,7 +487,7 @@ def test_wgrad_tcgen05_matches_reference(pk, case):
     ops, packing = pk
     from physicsinformeddiffusionmodels_b200._lib import call, stream
     B, H, Cin, Cout, k = case
-    assert call('pidm_conv2d_wgrad_tc_supported', B, H, H, Cin, Cout, k, k, k // 2) == 1
+    assert call('pidm_conv2d_wgrad_tc_supported', B, H, H, Cin, Cout, k, k, 1) == 1
     g = torch.Generator().manual_seed(31)
     x = torch.randn(B, Cin, H, H, generator=g).bfloat16().float()
     w = (torch.randn(Cout, Cin, 1, k, k, generator=g) / math.sqrt(Cin * k * k)).requires_grad_(True)
@@ -498,10 +498,66 @@ def test_wgrad_tcgen05_matches_reference(pk, case):
     xd, dyd = nhwc(x, torch.bfloat16).to(DEV), nhwc(cot, torch.bfloat16).to(DEV)
     dw = torch.zeros(Cout, Cin, 1, k, k, device=DEV)
     db = torch.zeros(Cout, device=DEV)
-    call('pidm_conv2d_wgrad_tc', xd, dyd, dw, db, B, H, H, Cin, Cout, k, k, k // 2, Cin * k * k, k * k, stream())
+    args = (xd, dyd, dw, B, H, H, Cin, Cin, H, H, Cout, k, k, 1, k // 2, k * k, Cin * k * k, stream())
+    call('pidm_conv2d_wgrad_tc', *args)
+    call('pidm_colsum', dyd, db, B * H * H, Cout, 1, stream())
     torch.cuda.synchronize()
     assert rel(dw, w.grad) < 2e-3, rel(dw, w.grad)
     assert rel(db, b.grad) < 2e-3
     # accumulate semantics: a second call doubles the buffers
-    call('pidm_conv2d_wgrad_tc', xd, dyd, dw, db, B, H, H, Cin, Cout, k, k, k // 2, Cin * k * k, k * k, stream())
+    call('pidm_conv2d_wgrad_tc', *args)
     assert rel(dw, 2 * w.grad) < 2e-3
+
+
+TC_GENERAL_CASES = [
+    # name, kind, Cin, Cout, k, stride, pad, H (input), B
+    ('stem7x7_pad32', 'conv', 2, 32, 7, 1, 3, 64, 2),
+    ('down4x4s2_c32', 'conv', 32, 32, 4, 2, 1, 64, 2),
+    ('down4x4s2_c64', 'conv', 64, 64, 4, 2, 1, 32, 2),
+    ('down4x4s2_c128', 'conv', 128, 128, 4, 2, 1, 16, 3),
+    ('up4x4s2T_c128', 'convT', 128, 128, 4, 2, 1, 8, 3),
+    ('up4x4s2T_c64', 'convT', 64, 64, 4, 2, 1, 16, 2),
+    ('up4x4s2T_c32', 'convT', 32, 32, 4, 2, 1, 32, 2),
+]
+
+
+@pytest.mark.parametrize('case', TC_GENERAL_CASES, ids=[c[0] for c in TC_GENERAL_CASES])
+def test_conv_tcgen05_strided_transposed_and_stem(pk, case):
+    """Stride-2 conv (TMA elementStrides), stride-2 transposed conv (4 output-parity classes) and the channel-padded
+    7x7 stem through the tcgen05 kernels: forward, dgrad and wgrad vs autograd of torch conv ops on bf16-representable
+    operands (1e-2: bf16 rounding of outputs)."""
+    ops, packing = pk
+    from physicsinformeddiffusionmodels_b200._lib import call
+    name, kind, Cin, Cout, k, stride, pad, H, B = case
+    ops.set_tensor_core_conv(True)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(B, Cin, H, H, generator=g).bfloat16().float()
+    wshape = (Cout, Cin, 1, k, k) if kind == 'conv' else (Cin, Cout, 1, k, k)
+    w = (torch.randn(wshape, generator=g) / math.sqrt(Cin * k * k)).bfloat16().float()
+    b = torch.randn(Cout, generator=g) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    if kind == 'conv':
+        yr = F.conv2d(xr, wr[:, :, 0], br, stride=stride, padding=pad)
+    else:
+        yr = F.conv_transpose2d(xr, wr[:, :, 0], br, stride=stride, padding=pad)
+    cot = torch.randn(yr.shape, generator=g).bfloat16().float()
+    (yr * cot).sum().backward()
+    cpad = (Cin + 31) // 32 * 32
+    Ho = yr.shape[-1]
+    assert call('pidm_conv2d_tc_general_supported', B, H, H, cpad, Ho, Ho, Cout, k, k, stride, pad,
+                1 if kind == 'convT' else 0) == 1
+    wd, bd = torch.nn.Parameter(w.to(DEV)), torch.nn.Parameter(b.to(DEV))
+    spec = packing.ConvSpec(wd, kind, k, k, stride, pad, cin_pad=cpad, need_dgrad=(cpad == Cin))
+    packer = packing.WeightPacker()
+    packer.add(spec)
+    packer.refresh(torch.bfloat16)
+    xin = torch.zeros(B, H, H, cpad)
+    xin[..., :Cin] = x.permute(0, 2, 3, 1)
+    xd = xin.to(DEV).bfloat16().requires_grad_(cpad == Cin)
+    y = ops.conv2d(xd, wd, bd, spec)
+    assert rel(nchw(y), yr) < 1e-2, f'{name} fwd {rel(nchw(y), yr)}'
+    y.backward(nhwc(cot, torch.bfloat16).to(DEV))
+    assert rel(wd.grad, wr.grad) < 1e-2, f'{name} wgrad {rel(wd.grad, wr.grad)}'
+    assert rel(bd.grad, br.grad) < 1e-2, f'{name} bgrad'
+    if cpad == Cin:
+        assert rel(nchw(xd.grad), xr.grad) < 1e-2, f'{name} dgrad {rel(nchw(xd.grad), xr.grad)}'
