@@ -194,8 +194,10 @@ def breakdown_one_step(engine, x0):
         for mo in mods:
             mo.call = orig
     agg = {}
+    detail = []
     for name, a, e0, e1 in records:
         ms = e0.elapsed_time(e1)
+        detail.append((round(ms * 1e3, 1), name, [x for x in a if isinstance(x, int) and not isinstance(x, bool) and x < (1 << 24)][:14]))
         flop = 0.0
         if name in ('pidm_conv2d_tc',):
             B, H, W, Cin, Cout, KH, KW = a[5], a[6], a[7], a[8], a[9], a[10], a[11]
@@ -219,6 +221,10 @@ def breakdown_one_step(engine, x0):
         d['ms'] += ms
         d['calls'] += 1
         d['flop'] += flop
+    if os.environ.get('PIDM_BENCH_DETAIL'):
+        with open(os.environ['PIDM_BENCH_DETAIL'], 'w') as f:
+            for us, name, ints in sorted(detail, key=lambda r: -r[0]):
+                f.write(f'{us:9.1f} us  {name:28s} {ints}\n')
     return agg
 
 
