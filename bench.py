@@ -187,10 +187,13 @@ def breakdown_one_step(engine, x0):
     mods = [ops, packing, denoising_utils, eng_mod]
     for mo in mods:
         mo.call = timed
+    world = engine.world
+    engine.world = 1          # rank-local diagnostic step: no collective (the other ranks are not in this code path)
     try:
         engine._step_body(x0)
         torch.cuda.synchronize()
     finally:
+        engine.world = world
         for mo in mods:
             mo.call = orig
     agg = {}

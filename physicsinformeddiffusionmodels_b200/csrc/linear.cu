@@ -137,20 +137,17 @@ __global__ void block_mlps_wgrad_kernel(const MlpEntry* __restrict__ table, cons
     }
 }
 
-// d_s[b,k] = sum_entries sum_j dout_e[b, j] W_e[j,k]     grid (B), block td
-__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, int n_entries, float* __restrict__ ds,
-                                        int td) {
+// d_s[b,k] += sum_j dout_e[b, j] W_e[j,k]     grid (B, entries), block td; ds zeroed by the caller
+__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, float* __restrict__ ds, int td) {
     extern __shared__ float sd[];   // [max_rows]
     const int b = blockIdx.x, k = threadIdx.x;
+    const MlpEntry e = table[blockIdx.y];
+    for (int j = threadIdx.x; j < e.n; j += blockDim.x) sd[j] = e.dout[(size_t)b * e.n + j];
+    __syncthreads();
     float acc = 0.f;
-    for (int i = 0; i < n_entries; ++i) {
-        const MlpEntry e = table[i];
-        __syncthreads();
-        for (int j = threadIdx.x; j < e.n; j += blockDim.x) sd[j] = e.dout[(size_t)b * e.n + j];
-        __syncthreads();
-        for (int j = 0; j < e.n; ++j) acc += sd[j] * e.W[(size_t)j * td + k];
-    }
-    ds[(size_t)b * td + k] = acc;
+#pragma unroll 4
+    for (int j = 0; j < e.n; ++j) acc += sd[j] * e.W[(size_t)j * td + k];
+    atomicAdd(&ds[(size_t)b * td + k], acc);
 }
 
 }  // namespace pidm
@@ -208,7 +205,8 @@ extern "C" int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max
     if (int e = mlp_smem_attr(smem)) return e;
     dim3 grid(n_entries, ceil_div(max_rows, 64));
     block_mlps_wgrad_kernel<<<grid, 256, smem, st>>>((const MlpEntry*)table_dev, silu_t, B, td);
-    block_mlps_dgrad_kernel<<<B, td, max_rows * sizeof(float), st>>>((const MlpEntry*)table_dev, n_entries, d_silu_t, td);
+    PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
+    block_mlps_dgrad_kernel<<<dim3(B, n_entries), td, max_rows * sizeof(float), st>>>((const MlpEntry*)table_dev, d_silu_t, td);
     PIDM_LAUNCH_CHECK("block_mlps_bwd");
     return 0;
 }
