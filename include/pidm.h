@@ -91,10 +91,12 @@ int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const
                    int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
 /* General tensor-core path: stride-1/2 regular convolution (input sampled through TMA elementStrides) and the
- * stride-2 transposed gather (ConvTranspose forward / dgrad of the stride-2 conv) as 4 output-parity classes. */
+ * stride-2 transposed gather (ConvTranspose forward / dgrad of the stride-2 conv) as 4 output-parity classes.
+ * gn_sums (optional, [B, gn_groups, 2], zeroed here): per-(sample, group) sum and sum of squares of the fp32 output,
+ * accumulated in the epilogue so that the following GroupNorm needs no statistics pass. */
 int pidm_conv2d_tc_general(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B,
                            int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
-                           int transposed, void* stream);
+                           int transposed, float* gn_sums, int gn_groups, void* stream);
 int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride,
                                      int pad, int transposed);
 /* wgrad on tcgen05: D[(tap,cA)][cB] = sum over grid pixels g of a[a_stride*g - pad + tap][cA] * b[g][cB], MN-major
@@ -112,11 +114,14 @@ int pidm_colsum(const void* x, float* out, long long M, int C, int dtype, void* 
 /* Block.forward tail: GroupNorm(G) -> *(scale+1)+shift -> SiLU (src/unet_model.py:233-241).  scale_shift [B,2C] or NULL.
  * sums [B,G,2] (sum, sum of squares) is written here and consumed by the backward. */
 int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const float* beta, const float* scale_shift, void* y,
-                            float* sums, int B, int HW, int C, int G, float eps, int dtype, void* stream);
-/* workspace: float[B*C*2 + B*G*2]; dgamma/dbeta ACCUMULATE; d_scale_shift [B,2C] overwritten (may be NULL). */
+                            float* sums, int stats_precomputed, int B, int HW, int C, int G, float eps, int dtype,
+                            void* stream);
+/* workspace: float[B*C*2]; dgamma/dbeta ACCUMULATE; d_scale_shift [B,2C] overwritten (may be NULL);
+ * dbias_of_producer (may be NULL): column sums of dx ACCUMULATED = bias gradient of the convolution that produced x. */
 int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const float* sums, const float* gamma, const float* beta,
                             const float* scale_shift, void* dx, float* dgamma, float* dbeta, float* d_scale_shift,
-                            float* workspace, int B, int HW, int C, int G, float eps, int dtype, void* stream);
+                            float* dbias_of_producer, float* workspace, int B, int HW, int C, int G, float eps,
+                            int dtype, void* stream);
 /* channel LayerNorm, gain only, biased variance (src/unet_model.py:201-210); dgamma ACCUMULATES */
 int pidm_layernorm_c_fwd(const void* x, const float* gamma, void* y, long long M, int C, float eps, int dtype, void* stream);
 int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma, long long M, int C,

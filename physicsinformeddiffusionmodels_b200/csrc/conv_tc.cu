@@ -105,8 +105,30 @@ struct TcParams {
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* y;
+    float* gn_sums;          // optional [B, G, 2]: GroupNorm sum / sum-of-squares of the output, fused into the epilogue
+    int gn_cpg, gn_groups;   // channels per group, groups
     TcClass cls[4];
 };
+
+// GroupNorm statistics of one 32-channel chunk held by a warp (one pixel row per lane): per group, reduce over the
+// group's channels in registers, over the 32 pixels by shuffles, one atomic pair per group per warp.
+template <int CPG>
+__device__ __forceinline__ void gn_stats_chunk(const float f[32], float* sums_b, int first_group, int lane) {
+    constexpr int NG = (CPG >= 32) ? 1 : 32 / CPG;
+    constexpr int W = (CPG >= 32) ? 32 : CPG;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < W; ++j) { float v = f[gi * W + j]; s += v; ss += v * v; }
+        s = warp_sum(s);
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            atomicAdd(sums_b + (first_group + gi) * 2, s);
+            atomicAdd(sums_b + (first_group + gi) * 2 + 1, ss);
+        }
+    }
+}
 
 template <int BN, int BK>
 struct TcCfg {
@@ -249,10 +271,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row_ok) {
-                float f[32];
+            float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
+            if (row_ok) {
                 if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -271,6 +293,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) st8(p.y + row_off + c + j, f + j);
+            }
+            if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
+                float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
+                const int fg = (n0 + c) / p.gn_cpg;
+                if (p.gn_cpg == 4) gn_stats_chunk<4>(f, sums_b, fg, lane);
+                else if (p.gn_cpg == 8) gn_stats_chunk<8>(f, sums_b, fg, lane);
+                else if (p.gn_cpg == 16) gn_stats_chunk<16>(f, sums_b, fg, lane);
+                else gn_stats_chunk<32>(f, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): chunk inside one group
             }
         }
     }
@@ -378,7 +408,7 @@ static bool tc_geometry(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, 
 
 static int tc_run(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
                   int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int transposed,
-                  cudaStream_t st) {
+                  float* gn_sums, int gn_groups, cudaStream_t st) {
     TcParams p;
     TcPlan pl;
     int classes = 1;
@@ -420,6 +450,14 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
     }
     p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = (__nv_bfloat16*)y;
+    p.gn_sums = gn_sums; p.gn_groups = gn_groups; p.gn_cpg = gn_groups > 0 ? Cout / gn_groups : 0;
+    if (gn_sums) {
+        PIDM_REQUIRE(gn_groups > 0 && Cout % gn_groups == 0, "conv2d_tc: bad GroupNorm group count %d", gn_groups);
+        const int cpg = p.gn_cpg;
+        PIDM_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16 || cpg % 32 == 0, "conv2d_tc: fused GroupNorm statistics need "
+                     "4, 8, 16 or a multiple of 32 channels per group (got %d)", cpg);
+        PIDM_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)B * gn_groups * 2 * sizeof(float), st));
+    }
     dim3 grid(((B + pl.TN - 1) / pl.TN) * p.tiles_h, Cout / pl.BN, classes);
 #define TC_CASE(bn, bk) if (pl.BN == bn && pl.BK == bk) return launch_tc<bn, bk>(mx, mw, p, grid, st)
     TC_CASE(256, 64); TC_CASE(128, 64); TC_CASE(64, 64); TC_CASE(32, 64);
@@ -438,7 +476,8 @@ extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, 
 
 extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
                               int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
-    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, (cudaStream_t)stream);
+    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, nullptr, 0,
+                  (cudaStream_t)stream);
 }
 
 extern "C" int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
@@ -449,7 +488,7 @@ extern "C" int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, in
 
 extern "C" int pidm_conv2d_tc_general(const void* x, const void* w_packed, const float* bias, const void* residual,
                                       void* y, int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
-                                      int stride, int pad, int transposed, void* stream) {
-    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed,
-                  (cudaStream_t)stream);
+                                      int stride, int pad, int transposed, float* gn_sums, int gn_groups, void* stream) {
+    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed, gn_sums,
+                  gn_groups, (cudaStream_t)stream);
 }

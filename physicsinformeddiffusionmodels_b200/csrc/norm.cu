@@ -131,67 +131,78 @@ __global__ void gn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&S[(size_t)b * 2 * C + i], sc[i]);
 }
 
-// backward pass 2 (one CTA per sample): FiLM grads, parameter grads (atomics over the batch), group means.
-__global__ void gn_bwd_param_kernel(const float* __restrict__ S, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, const float* __restrict__ ss,
-                                    float* __restrict__ dss /*[B,2C] or null*/, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, float* __restrict__ gmean /*[B][G][2]*/, int HW, int C,
-                                    int G) {
-    extern __shared__ float sgm[];  // [G][2]
-    const int b = blockIdx.x, cpg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sgm[i] = 0.f;
+// backward pass 2: dx = rstd * (gamma*(1+scale)*dz - m1 - xhat*m2), grid (chunks, B).
+// Every CTA first turns S[b] into the group means m1, m2 (C values: cheap); the chunk-0 CTA of each sample also
+// emits the FiLM gradients and the (atomic) parameter gradients.  Optionally accumulates the column sums of dx
+// (= bias gradient of the convolution that produced x) -- each thread owns a fixed channel octet.
+template <typename T>
+__global__ void gn_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ ss, const float* __restrict__ S, T* __restrict__ dx,
+                                 float* __restrict__ dss, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                 float* __restrict__ dbias, int HW, int C, int G, float eps) {
+    extern __shared__ float sm[];   // gm[G][2] | cs[C]
+    float* gm = sm;
+    float* cs = sm + 2 * G;
+    const int oct = C / 8, cpg = C / G;
+    const int b = blockIdx.y;
+    const int o = threadIdx.x % oct, r0 = threadIdx.x / oct;
+    const int rows_per_pass = blockDim.x / oct;
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    for (int i = threadIdx.x; i < 2 * G + C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s1 = S[((size_t)b * C + c) * 2], s2 = S[((size_t)b * C + c) * 2 + 1];
         float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
-        if (dss) {
-            dss[(size_t)b * 2 * C + c] = gamma[c] * s2 + beta[c] * s1;   // d scale
-            dss[(size_t)b * 2 * C + C + c] = s1;                          // d shift
+        atomicAdd(&gm[(c / cpg) * 2], gamma[c] * f * s1);
+        atomicAdd(&gm[(c / cpg) * 2 + 1], gamma[c] * f * s2);
+        if (blockIdx.x == 0) {
+            if (dss) {
+                dss[(size_t)b * 2 * C + c] = gamma[c] * s2 + beta[c] * s1;   // d scale
+                dss[(size_t)b * 2 * C + C + c] = s1;                          // d shift
+            }
+            atomicAdd(&dgamma[c], f * s2);
+            atomicAdd(&dbeta[c], f * s1);
         }
-        atomicAdd(&dgamma[c], f * s2);
-        atomicAdd(&dbeta[c], f * s1);
-        atomicAdd(&sgm[(c / cpg) * 2], gamma[c] * f * s1);
-        atomicAdd(&sgm[(c / cpg) * 2 + 1], gamma[c] * f * s2);
     }
     __syncthreads();
-    const float inv_n = 1.f / ((float)cpg * (float)HW);
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gmean[(size_t)b * 2 * G + i] = sgm[i] * inv_n;
-}
-
-// backward pass 3: dx = rstd * (gamma*(1+scale)*dz - m1 - xhat*m2)
-template <typename T>
-__global__ void gn_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 const float* __restrict__ ss, const float* __restrict__ gmean, T* __restrict__ dx,
-                                 int HW, int C, int G, float eps, long long total8) {
-    const int oct = C / 8, cpg = C / G;
-    const float inv_n = 1.f / ((float)cpg * (float)HW);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
-         i += (long long)gridDim.x * blockDim.x) {
-        int o = (int)(i % oct);
-        long long pix = i / oct;
-        int b = (int)(pix / HW);
+    float mean[2], rstd[2], m1[2], m2[2], gmv[8], bt[8], s1p[8], sh[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int g = (o * 8 + h * 4) / cpg;
+        gn_mean_rstd(sums, b, g, G, inv_n, eps, mean[h], rstd[h]);
+        m1[h] = gm[g * 2] * inv_n;
+        m2[h] = gm[g * 2 + 1] * inv_n;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int c = o * 8 + k;
+        gmv[k] = gamma[c]; bt[k] = beta[c];
+        s1p[k] = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        sh[k] = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
+    }
+    float colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t base = (size_t)b * HW * C;
+    for (int p = blockIdx.x * rows_per_pass + r0; p < HW; p += gridDim.x * rows_per_pass) {
         float v[8], d[8];
-        ld8(x + i * 8, v);
-        ld8(dy + i * 8, d);
+        ld8(x + base + (size_t)p * C + o * 8, v);
+        ld8(dy + base + (size_t)p * C + o * 8, d);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int c0 = o * 8 + h * 4, g = c0 / cpg;
-            float mean, rstd;
-            gn_mean_rstd(sums, b, g, G, inv_n, eps, mean, rstd);
-            float m1 = gmean[((size_t)b * G + g) * 2], m2 = gmean[((size_t)b * G + g) * 2 + 1];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int c = c0 + k;
-                float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
-                float shv = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
-                float xh = (v[h * 4 + k] - mean) * rstd;
-                float z = (xh * gamma[c] + beta[c]) * f + shv;
-                float dz = d[h * 4 + k] * silu_grad_f(z);
-                v[h * 4 + k] = rstd * (gamma[c] * f * dz - m1 - xh * m2);
-            }
+        for (int k = 0; k < 8; ++k) {
+            float xh = (v[k] - mean[k >> 2]) * rstd[k >> 2];
+            float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
+            float dz = d[k] * silu_grad_f(z);
+            float g = rstd[k >> 2] * (gmv[k] * s1p[k] * dz - m1[k >> 2] - xh * m2[k >> 2]);
+            v[k] = g;
+            colsum[k] += g;
         }
-        st8(dx + i * 8, v);
+        st8(dx + base + (size_t)p * C + o * 8, v);
+    }
+    if (dbias) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&cs[o * 8 + k], colsum[k]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], cs[i]);
     }
 }
 
@@ -317,52 +328,54 @@ static int gn_check(int C, int G) {
     return 0;
 }
 
-// sums [B,G,2] is zeroed here, filled by the stats kernel and must be kept for backward.
+static void gn_launch_dims(int HW, int C, int& block, int& chunks) {
+    block = gn_block(C);
+    const int rows = block / (C / 8);
+    chunks = ceil_div(HW, rows * 2);          // ~2 pixels per thread: enough CTAs to cover the machine at 64x64
+    if (chunks > 32) chunks = 32;
+    if (chunks < 1) chunks = 1;
+}
+
+// sums [B,G,2] holds (sum, sum of squares) per (sample, group): computed here unless stats_precomputed (then it was
+// filled by the producing convolution's epilogue); it must be kept for backward.
 extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const float* beta, const float* scale_shift,
-                                       void* y, float* sums, int B, int HW, int C, int G, float eps, int dtype,
-                                       void* stream) {
+                                       void* y, float* sums, int stats_precomputed, int B, int HW, int C, int G,
+                                       float eps, int dtype, void* stream) {
     if (int e = gn_check(C, G)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    PIDM_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), st));
-    const int block = gn_block(C), rows = block / (C / 8);
-    int chunks = ceil_div(HW, rows * 8);
-    if (chunks > 64) chunks = 64;
-    if (chunks < 1) chunks = 1;
+    int block, chunks;
+    gn_launch_dims(HW, C, block, chunks);
     long long total8 = (long long)B * HW * C / 8;
     int g2 = ceil_div(total8, 256);
     if (g2 > 148 * 16) g2 = 148 * 16;
+    if (!stats_precomputed) PIDM_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), st));
     PIDM_DISPATCH_DTYPE(dtype, {
-        gn_stats_kernel<T><<<dim3(chunks, B), block, 2 * G * sizeof(float), st>>>((const T*)x, sums, HW, C, G);
+        if (!stats_precomputed)
+            gn_stats_kernel<T><<<dim3(chunks, B), block, 2 * G * sizeof(float), st>>>((const T*)x, sums, HW, C, G);
         gn_apply_kernel<T><<<g2, 256, 0, st>>>((const T*)x, sums, gamma, beta, scale_shift, (T*)y, HW, C, G, eps, total8);
     });
     PIDM_LAUNCH_CHECK("groupnorm_silu_fwd");
     return 0;
 }
 
-// workspace: float[B*C*2 + B*G*2].  dgamma/dbeta are ACCUMULATED (atomicAdd); d_scale_shift is overwritten.
+// workspace: float[B*C*2].  dgamma/dbeta (and dbias_of_producer, if given) are ACCUMULATED (atomicAdd);
+// d_scale_shift is overwritten.
 extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const float* sums, const float* gamma,
                                        const float* beta, const float* scale_shift, void* dx, float* dgamma,
-                                       float* dbeta, float* d_scale_shift, float* workspace, int B, int HW, int C, int G,
-                                       float eps, int dtype, void* stream) {
+                                       float* dbeta, float* d_scale_shift, float* dbias_of_producer, float* workspace,
+                                       int B, int HW, int C, int G, float eps, int dtype, void* stream) {
     if (int e = gn_check(C, G)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     float* S = workspace;
-    float* gmean = workspace + (size_t)B * C * 2;
     PIDM_CUDA(cudaMemsetAsync(S, 0, (size_t)B * C * 2 * sizeof(float), st));
-    const int block = gn_block(C), rows = block / (C / 8);
-    int chunks = ceil_div(HW, rows * 8);
-    if (chunks > 64) chunks = 64;
-    if (chunks < 1) chunks = 1;
-    long long total8 = (long long)B * HW * C / 8;
-    int g2 = ceil_div(total8, 256);
-    if (g2 > 148 * 16) g2 = 148 * 16;
+    int block, chunks;
+    gn_launch_dims(HW, C, block, chunks);
     PIDM_DISPATCH_DTYPE(dtype, {
         gn_bwd_reduce_kernel<T><<<dim3(chunks, B), block, 2 * C * sizeof(float), st>>>(
             (const T*)x, (const T*)dy, sums, gamma, beta, scale_shift, S, HW, C, G, eps);
-        gn_bwd_param_kernel<<<B, 256, 2 * G * sizeof(float), st>>>(S, gamma, beta, scale_shift, d_scale_shift, dgamma,
-                                                                  dbeta, gmean, HW, C, G);
-        gn_bwd_dx_kernel<T><<<g2, 256, 0, st>>>((const T*)x, (const T*)dy, sums, gamma, beta, scale_shift, gmean, (T*)dx,
-                                                HW, C, G, eps, total8);
+        gn_bwd_dx_kernel<T><<<dim3(chunks, B), block, (2 * G + C) * sizeof(float), st>>>(
+            (const T*)x, (const T*)dy, sums, gamma, beta, scale_shift, S, (T*)dx, d_scale_shift, dgamma, dbeta,
+            dbias_of_producer, HW, C, G, eps);
     });
     PIDM_LAUNCH_CHECK("groupnorm_silu_bwd");
     return 0;

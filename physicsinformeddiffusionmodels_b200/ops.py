@@ -117,29 +117,42 @@ def concat(a, b):
 # ----------------------------------------------------------------------------------------------
 # convolution (implicit GEMM).  `spec` is a ConvSpec created by the owning module (packing.py).
 # ----------------------------------------------------------------------------------------------
-def _conv_launch(x, wp, bias, residual, y, g, transposed):
-    """g = (B,H,W,Cin,Ho,Wo,Cout,KH,KW,stride,pad)."""
+def _conv_launch(x, wp, bias, residual, y, g, transposed, gn_sums=None, gn_groups=0):
+    """g = (B,H,W,Cin,Ho,Wo,Cout,KH,KW,stride,pad).  Returns True if the fused GroupNorm statistics were produced."""
     B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = g
     tr = 1 if transposed else 0
     if (_STATE['use_tc'] and x.dtype == torch.bfloat16
             and call('pidm_conv2d_tc_general_supported', B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, tr)):
+        cpg = Cout // gn_groups if gn_groups else 0
+        fuse = gn_sums is not None and (cpg in (4, 8, 16) or (cpg > 0 and cpg % 32 == 0))
         call('pidm_conv2d_tc_general', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, tr,
-             stream())
+             gn_sums if fuse else None, gn_groups if fuse else 0, stream())
+        return fuse
     else:
         call('pidm_conv2d_simt', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad,
              1 if transposed else 0, _code(x), stream())
+        return False
 
 
 class _Conv2d(torch.autograd.Function):
+    """`link` (optional dict) couples this convolution to the GroupNorm that consumes its output: forward leaves the
+    fused statistics in link['sums']; the GroupNorm backward leaves this conv's bias gradient in link['dbias']."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, spec):
+    def forward(ctx, x, weight, bias, residual, spec, link):
         B, H, W, Cin = x.shape
         Ho, Wo = spec.out_hw(H, W)
         y = torch.empty(B, Ho, Wo, spec.cout, device=x.device, dtype=x.dtype)
         g = (B, H, W, Cin, Ho, Wo, spec.cout, spec.kh, spec.kw, spec.stride, spec.pad)
-        _conv_launch(x, spec.wp_fwd, bias, residual, y, g, spec.transposed)
+        sums = None
+        if link is not None:
+            sums = torch.empty(B, link['groups'], 2, device=x.device, dtype=torch.float32)
+        fused = _conv_launch(x, spec.wp_fwd, bias, residual, y, g, spec.transposed, sums, link['groups'] if link else 0)
+        if link is not None:
+            link['sums'] = sums if fused else None
+            link['bias'] = bias
         ctx.save_for_backward(x, weight, bias)
-        ctx.spec, ctx.g, ctx.has_res = spec, g, residual is not None
+        ctx.spec, ctx.g, ctx.has_res, ctx.link = spec, g, residual is not None, link
         return y
 
     @staticmethod
@@ -162,6 +175,9 @@ class _Conv2d(torch.autograd.Function):
                 _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
         gw_buf, gw_ret = _grad_buffer(weight)
         gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
+        if ctx.link is not None and 'dbias' in ctx.link:
+            # the consuming GroupNorm's backward already reduced dy over pixels (= this conv's bias gradient)
+            gb_buf, gb_ret = None, ctx.link.pop('dbias')
         use_tc = _STATE['use_tc'] and x.dtype == torch.bfloat16
         if use_tc and not spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, Ho, Wo, Cin, Cout, KH, KW, stride):
             # D[(tap, ci)][co]: gathered operand = x, reduction grid = output pixels
@@ -178,11 +194,12 @@ class _Conv2d(torch.autograd.Function):
         else:
             call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW,
                  stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
-        return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None
+        return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None, None
 
 
-def conv2d(x, weight, bias, spec, residual=None):
-    return _Conv2d.apply(x.contiguous(), weight, bias, None if residual is None else residual.contiguous(), spec)
+def conv2d(x, weight, bias, spec, residual=None, gn_link=None):
+    return _Conv2d.apply(x.contiguous(), weight, bias, None if residual is None else residual.contiguous(), spec,
+                         gn_link)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -190,13 +207,15 @@ def conv2d(x, weight, bias, spec, residual=None):
 # ----------------------------------------------------------------------------------------------
 class _GroupNormSilu(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale_shift, groups, eps):
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, link):
         B, H, W, C = x.shape
         y = torch.empty_like(x)
-        sums = torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
-        call('pidm_groupnorm_silu_fwd', x, gamma, beta, scale_shift, y, sums, B, H * W, C, groups, eps, _code(x), stream())
+        pre = link is not None and link.get('sums') is not None
+        sums = link['sums'] if pre else torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
+        call('pidm_groupnorm_silu_fwd', x, gamma, beta, scale_shift, y, sums, 1 if pre else 0, B, H * W, C, groups, eps,
+             _code(x), stream())
         ctx.save_for_backward(x, gamma, beta, scale_shift, sums)
-        ctx.groups, ctx.eps = groups, eps
+        ctx.groups, ctx.eps, ctx.link = groups, eps, link
         return y
 
     @staticmethod
@@ -208,14 +227,19 @@ class _GroupNormSilu(torch.autograd.Function):
         gg_buf, gg_ret = _grad_buffer(gamma)
         gb_buf, gb_ret = _grad_buffer(beta)
         dss = None if ss is None else torch.empty_like(ss)
-        ws = torch.empty(B * C * 2 + B * ctx.groups * 2, device=x.device, dtype=torch.float32)
-        call('pidm_groupnorm_silu_bwd', x, dy, sums, gamma, beta, ss, dx, gg_buf, gb_buf, dss, ws, B, H * W, C,
+        ws = torch.empty(B * C * 2, device=x.device, dtype=torch.float32)
+        dbias = None
+        link = ctx.link
+        if link is not None and link.get('bias') is not None:
+            dbias, dbias_ret = _grad_buffer(link['bias'])
+            link['dbias'] = dbias_ret             # picked up by the producing convolution's backward
+        call('pidm_groupnorm_silu_bwd', x, dy, sums, gamma, beta, ss, dx, gg_buf, gb_buf, dss, dbias, ws, B, H * W, C,
              ctx.groups, ctx.eps, _code(x), stream())
-        return dx, gg_ret, gb_ret, dss, None, None
+        return dx, gg_ret, gb_ret, dss, None, None, None
 
 
-def groupnorm_silu(x, gamma, beta, scale_shift, groups, eps=1e-5):
-    return _GroupNormSilu.apply(x.contiguous(), gamma, beta, scale_shift, groups, eps)
+def groupnorm_silu(x, gamma, beta, scale_shift, groups, eps=1e-5, gn_link=None):
+    return _GroupNormSilu.apply(x.contiguous(), gamma, beta, scale_shift, groups, eps, gn_link)
 
 
 class _LayerNormC(torch.autograd.Function):

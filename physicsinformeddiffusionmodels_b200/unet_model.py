@@ -254,15 +254,21 @@ class Unet3D(nn.Module):
         self._mlp_table = MlpTable(mlps)
 
     # ---- kernels ----------------------------------------------------------------------------------------
-    def _conv(self, mod, x, residual=None):
-        return ops.conv2d(x, mod.weight, getattr(mod, 'bias', None), self._spec[id(mod)], residual=residual)
+    def _conv(self, mod, x, residual=None, gn_link=None):
+        return ops.conv2d(x, mod.weight, getattr(mod, 'bias', None), self._spec[id(mod)], residual=residual,
+                          gn_link=gn_link)
 
     def _resblock(self, block, x, ss_list):
         ss = ss_list[block._mlp_index] if (block.mlp is not None and ss_list is not None) else None
-        h = self._conv(block.block1.proj, x)
-        h = ops.groupnorm_silu(h, block.block1.norm.weight, block.block1.norm.bias, ss, block.groups, block.block1.norm.eps)
-        h = self._conv(block.block2.proj, h)
-        h = ops.groupnorm_silu(h, block.block2.norm.weight, block.block2.norm.bias, None, block.groups, block.block2.norm.eps)
+        # conv -> GroupNorm pairs are linked: statistics come out of the conv epilogue, the conv's bias gradient
+        # out of the GroupNorm backward
+        l1, l2 = {'groups': block.groups}, {'groups': block.groups}
+        h = self._conv(block.block1.proj, x, gn_link=l1)
+        h = ops.groupnorm_silu(h, block.block1.norm.weight, block.block1.norm.bias, ss, block.groups,
+                               block.block1.norm.eps, gn_link=l1)
+        h = self._conv(block.block2.proj, h, gn_link=l2)
+        h = ops.groupnorm_silu(h, block.block2.norm.weight, block.block2.norm.bias, None, block.groups,
+                               block.block2.norm.eps, gn_link=l2)
         if isinstance(block.res_conv, nn.Identity):
             return ops.add(h, x)
         return self._conv(block.res_conv, x, residual=h)
