@@ -385,6 +385,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
     }
 }
 
+// tensor-core (mma.sync) versions for bf16 activations and 8 heads (attention_mma.cu)
+int la_mma_ctx(int mode, const void* qkv, const void* dout, const float* part, int n_stat_chunks, float* kmax,
+               float* kzinv, float* ctx, int B, int N, float scale, cudaStream_t st);
+int la_mma_out(const void* qkv, const float* ctx, void* out, int B, int N, float scale, cudaStream_t st);
+int la_mma_bwd(const void* qkv, const void* dout, const float* ctx, const float* dctx, const float* kmax,
+               const float* kzinv, void* dqkv, int B, int N, float scale, cudaStream_t st);
+
 static int la_chunks(int N) {
     int c = N / 128;
     if (c < 1) c = 1;
@@ -405,6 +412,13 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const int rpc = (N + chunks - 1) / chunks;
     const float scale = 0.17677669529663687f;   // 32^-0.5
     PIDM_CUDA(cudaMemsetAsync(ctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
+    if (dtype == PIDM_BF16 && heads == 8) {
+        la_kstats_kernel<__nv_bfloat16><<<dim3(chunks, B), HID, 0, st>>>((const __nv_bfloat16*)qkv, workspace, N, HID, rpc);
+        if (int e = la_mma_ctx(0, qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, B, N, scale, st)) return e;
+        if (int e = la_mma_out(qkv, ctx, out, B, N, scale, st)) return e;
+        PIDM_LAUNCH_CHECK("linattn_fwd");
+        return 0;
+    }
     const int cchunks = (N + 255) / 256 > 16 ? 16 : (N + 255) / 256;
     const int crpc = ((N + cchunks - 1) / cchunks + LA_TN - 1) / LA_TN * LA_TN;
     PIDM_DISPATCH_DTYPE(dtype, {
@@ -430,6 +444,10 @@ extern "C" int pidm_linattn_bwd(const void* qkv, const void* dout, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const float scale = 0.17677669529663687f;
     PIDM_CUDA(cudaMemsetAsync(dctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
+    if (dtype == PIDM_BF16 && heads == 8) {
+        if (int e = la_mma_ctx(1, qkv, dout, nullptr, 0, nullptr, nullptr, dctx, B, N, scale, st)) return e;
+        return la_mma_bwd(qkv, dout, ctx, dctx, kmax, kzinv, dqkv, B, N, scale, st);
+    }
     const int cchunks = (N + 255) / 256 > 16 ? 16 : (N + 255) / 256;
     const int crpc = ((N + cchunks - 1) / cchunks + LA_TN - 1) / LA_TN * LA_TN;
     PIDM_DISPATCH_DTYPE(dtype, {

@@ -95,6 +95,20 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Threads are laid out as (row = tid / oct, octet = tid % oct).  When oct is a power of two < 32, lanes that own
+// the same channel octet sit `oct` apart inside a warp: sum them by shuffles so that only the first `oct` lanes of
+// each warp touch shared-memory atomics (cuts same-address ATOMS traffic by 32/oct).  Returns true for the lanes
+// that must publish their (now warp-reduced) values.
+template <int NV>
+__device__ __forceinline__ bool reduce_same_octet(float (&v)[NV], int oct) {
+    if (oct >= 32 || (oct & (oct - 1)) != 0) return true;
+    for (int off = oct; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    }
+    return (threadIdx.x & 31) < oct;
+}
+
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
 __device__ __forceinline__ float silu_grad_f(float z) {
     float s = 1.f / (1.f + __expf(-z));

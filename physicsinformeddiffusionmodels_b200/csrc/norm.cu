@@ -33,14 +33,16 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, float* __restrict__ sum
 #pragma unroll
         for (int k = 0; k < 8; ++k) { s[k >> 2] += v[k]; ss[k >> 2] += v[k] * v[k]; }
     }
-    if (cpg >= 8) {
+    float red[4] = {s[0], s[1], ss[0], ss[1]};
+    if (reduce_same_octet(red, oct)) {
         int g = (o * 8) / cpg;
-        atomicAdd(&sg[2 * g], s[0] + s[1]);
-        atomicAdd(&sg[2 * g + 1], ss[0] + ss[1]);
-    } else {  // cpg == 4
-        int g = (o * 8) / cpg;
-        atomicAdd(&sg[2 * g], s[0]); atomicAdd(&sg[2 * g + 1], ss[0]);
-        atomicAdd(&sg[2 * g + 2], s[1]); atomicAdd(&sg[2 * g + 3], ss[1]);
+        if (cpg >= 8) {
+            atomicAdd(&sg[2 * g], red[0] + red[1]);
+            atomicAdd(&sg[2 * g + 1], red[2] + red[3]);
+        } else {  // cpg == 4
+            atomicAdd(&sg[2 * g], red[0]); atomicAdd(&sg[2 * g + 1], red[2]);
+            atomicAdd(&sg[2 * g + 2], red[1]); atomicAdd(&sg[2 * g + 3], red[3]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(size_t)b * 2 * G + i], sg[i]);
@@ -125,8 +127,12 @@ __global__ void gn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restric
             a1[k] += dz; a2[k] += dz * xh;
         }
     }
+    const bool pub1 = reduce_same_octet(a1, oct);
+    reduce_same_octet(a2, oct);
+    if (pub1) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&sc[(o * 8 + k) * 2], a1[k]); atomicAdd(&sc[(o * 8 + k) * 2 + 1], a2[k]); }
+        for (int k = 0; k < 8; ++k) { atomicAdd(&sc[(o * 8 + k) * 2], a1[k]); atomicAdd(&sc[(o * 8 + k) * 2 + 1], a2[k]); }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&S[(size_t)b * 2 * C + i], sc[i]);
 }
@@ -199,8 +205,10 @@ __global__ void gn_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ 
         st8(dx + base + (size_t)p * C + o * 8, v);
     }
     if (dbias) {
+        if (reduce_same_octet(colsum, oct)) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(&cs[o * 8 + k], colsum[k]);
+            for (int k = 0; k < 8; ++k) atomicAdd(&cs[o * 8 + k], colsum[k]);
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], cs[i]);
     }

@@ -245,8 +245,10 @@ __global__ void colsum_kernel(const T* __restrict__ dy, float* __restrict__ out,
 #pragma unroll
         for (int k = 0; k < 8; ++k) a[k] += v[k];
     }
+    if (reduce_same_octet(a, oct)) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&sacc[o * 8 + k], a[k]);
+        for (int k = 0; k < 8; ++k) atomicAdd(&sacc[o * 8 + k], a[k]);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], sacc[i]);
 }
