@@ -412,7 +412,7 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const int rpc = (N + chunks - 1) / chunks;
     const float scale = 0.17677669529663687f;   // 32^-0.5
     PIDM_CUDA(cudaMemsetAsync(ctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
-    if (dtype == PIDM_BF16 && heads == 8) {
+    if (dtype == PIDM_BF16 && heads == 8 && N % 64 == 0) {
         la_kstats_kernel<__nv_bfloat16><<<dim3(chunks, B), HID, 0, st>>>((const __nv_bfloat16*)qkv, workspace, N, HID, rpc);
         if (int e = la_mma_ctx(0, qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, B, N, scale, st)) return e;
         if (int e = la_mma_out(qkv, ctx, out, B, N, scale, st)) return e;
@@ -444,7 +444,7 @@ extern "C" int pidm_linattn_bwd(const void* qkv, const void* dout, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const float scale = 0.17677669529663687f;
     PIDM_CUDA(cudaMemsetAsync(dctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
-    if (dtype == PIDM_BF16 && heads == 8) {
+    if (dtype == PIDM_BF16 && heads == 8 && N % 64 == 0) {
         if (int e = la_mma_ctx(1, qkv, dout, nullptr, 0, nullptr, nullptr, dctx, B, N, scale, st)) return e;
         return la_mma_bwd(qkv, dout, ctx, dctx, kmax, kzinv, dqkv, B, N, scale, st);
     }

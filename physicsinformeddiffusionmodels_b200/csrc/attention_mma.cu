@@ -101,7 +101,53 @@ __device__ __forceinline__ void load_rows(const __nv_bfloat16* __restrict__ src,
     }
 }
 
-// ---- context / dcontext ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lm_smem(dst)), "l"(src) : "memory");
+}
+// asynchronously copy `rows` pixel rows (256 channels each) of a [., row_stride] tensor into smem [rows][LM_PITCH]
+__device__ __forceinline__ void issue_rows(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, size_t row_stride, int rows) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < rows * 32; idx += blockDim.x) {
+        const int row = idx >> 5;
+        cp_async16(dst + (size_t)row * LM_PITCH + lane * 8, src + (size_t)row * row_stride + lane * 8);
+    }
+}
+// in-place transform of landed rows: XF 1: exp(x - M[c]);  XF 2: exp(x - M[c]) * Zi[c];  XF 3: softmax_d * mul
+template <int XF>
+__device__ __forceinline__ void transform_rows(__nv_bfloat16* buf, int rows, const float* sM, const float* sZi, float mul) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < rows * 32; idx += blockDim.x) {
+        __nv_bfloat16* p = buf + (size_t)(idx >> 5) * LM_PITCH + lane * 8;
+        float v[8];
+        ld8(p, v);
+        if (XF == 1 || XF == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float e = __expf(v[k] - sM[lane * 8 + k]);
+                v[k] = (XF == 2) ? e * sZi[lane * 8 + k] : e;
+            }
+        } else {
+            float mx = v[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) mx = fmaxf(mx, v[k]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[k] = __expf(v[k] - mx); sum += v[k]; }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = mul / sum;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] *= inv;
+        }
+        st8_smem(p, v);
+    }
+}
+
+// ---- context / dcontext: 2-deep cp.async ring of 64-pixel (W | V) tiles ------------------------------------------
+constexpr int LC_ROWS = 64;
+constexpr int LC_TILE_ELEMS = 2 * LC_ROWS * LM_PITCH;
 template <int MODE>
 __global__ void __launch_bounds__(256) la_ctx_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                          const __nv_bfloat16* __restrict__ dout,
@@ -109,11 +155,25 @@ __global__ void __launch_bounds__(256) la_ctx_mma_kernel(const __nv_bfloat16* __
                                                          float* __restrict__ kmax, float* __restrict__ kzinv,
                                                          float* __restrict__ ctx, int N, float scale) {
     extern __shared__ __align__(16) unsigned char raw[];
-    __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(raw);
-    __nv_bfloat16* Vs = Ws + 64 * LM_PITCH;
-    float* sM = reinterpret_cast<float*>(Vs + 64 * LM_PITCH);
+    __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw);               // [2][W | V][64][LM_PITCH]
+    float* sM = reinterpret_cast<float*>(ring + 2 * LC_TILE_ELEMS);
     float* sZi = sM + LM_HID;
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+    const int n_begin = chunk * LM_CHUNK, n_end = min(N, n_begin + LM_CHUNK);
+    const int n_tiles = (n_end - n_begin) / LC_ROWS;
+    auto issue = [&](int it) {
+        __nv_bfloat16* buf = ring + (size_t)(it & 1) * LC_TILE_ELEMS;
+        const size_t pix = (size_t)b * N + n_begin + (size_t)it * LC_ROWS;
+        if (MODE == 0) {
+            issue_rows(buf, qkv + pix * 3 * LM_HID + LM_HID, 3 * LM_HID, LC_ROWS);
+            issue_rows(buf + LC_ROWS * LM_PITCH, qkv + pix * 3 * LM_HID + 2 * LM_HID, 3 * LM_HID, LC_ROWS);
+        } else {
+            issue_rows(buf, qkv + pix * 3 * LM_HID, 3 * LM_HID, LC_ROWS);
+            issue_rows(buf + LC_ROWS * LM_PITCH, dout + pix * LM_HID, LM_HID, LC_ROWS);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n_tiles > 0) issue(0);
     if (MODE == 0) {
         float M = -INFINITY;
         for (int i = 0; i < n_stat_chunks; ++i) M = fmaxf(M, part[(((size_t)b * n_stat_chunks + i) * LM_HID + tid) * 2]);
@@ -125,7 +185,6 @@ __global__ void __launch_bounds__(256) la_ctx_mma_kernel(const __nv_bfloat16* __
         sM[tid] = M;
         sZi[tid] = 1.f / Z;
         if (chunk == 0) { kmax[(size_t)b * LM_HID + tid] = M; kzinv[(size_t)b * LM_HID + tid] = 1.f / Z; }
-        __syncthreads();
     }
     float acc[2][4][4];
 #pragma unroll
@@ -134,18 +193,14 @@ __global__ void __launch_bounds__(256) la_ctx_mma_kernel(const __nv_bfloat16* __
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-    const int n_begin = chunk * LM_CHUNK;
-    const int n_end = min(N, n_begin + LM_CHUNK);
-    for (int t0 = n_begin; t0 < n_end; t0 += 64) {
-        const int valid = min(64, n_end - t0);
-        const __nv_bfloat16* rowp = qkv + ((size_t)b * N + t0) * 3 * LM_HID;
-        if (MODE == 0) {
-            load_rows<1>(rowp + LM_HID, 3 * LM_HID, valid, 64, Ws, sM, sZi, 1.f);
-            load_rows<0>(rowp + 2 * LM_HID, 3 * LM_HID, valid, 64, Vs, nullptr, nullptr, 1.f);
-        } else {
-            load_rows<3>(rowp, 3 * LM_HID, valid, 64, Ws, nullptr, nullptr, scale);
-            load_rows<0>(dout + ((size_t)b * N + t0) * LM_HID, LM_HID, valid, 64, Vs, nullptr, nullptr, 1.f);
-        }
+    for (int it = 0; it < n_tiles; ++it) {
+        __nv_bfloat16* Ws = ring + (size_t)(it & 1) * LC_TILE_ELEMS;
+        __nv_bfloat16* Vs = Ws + LC_ROWS * LM_PITCH;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                       // tile `it` landed for everyone; the other slot is no longer being read
+        if (it + 1 < n_tiles) issue(it + 1);
+        if (MODE == 0) transform_rows<1>(Ws, LC_ROWS, sM, sZi, 1.f);
+        else transform_rows<3>(Ws, LC_ROWS, nullptr, nullptr, scale);
         __syncthreads();
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -159,7 +214,6 @@ __global__ void __launch_bounds__(256) la_ctx_mma_kernel(const __nv_bfloat16* __
             mma_bf16(acc[1][0], a1, b01[0], b01[1]); mma_bf16(acc[1][1], a1, b01[2], b01[3]);
             mma_bf16(acc[1][2], a1, b23[0], b23[1]); mma_bf16(acc[1][3], a1, b23[2], b23[3]);
         }
-        __syncthreads();
     }
     const int g = lane >> 2, t = lane & 3;
     float* cb = ctx + ((size_t)b * LM_HEADS + h) * LM_D * LM_D;
@@ -185,15 +239,26 @@ __device__ __forceinline__ void stage_ctx_bf16(const float* __restrict__ src, __
     }
 }
 
-// ---- out = q~ ctx -------------------------------------------------------------------------------------------------
+// ---- out = q~ ctx: 3-deep cp.async ring of 64-pixel q tiles ----------------------------------------------------------
+constexpr int LO_ROWS = 64, LO_STAGES = 3;
 __global__ void __launch_bounds__(256) la_out_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                          const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out,
                                                          int N, float scale) {
     extern __shared__ __align__(16) unsigned char raw[];
     __nv_bfloat16* Cs = reinterpret_cast<__nv_bfloat16*>(raw);                 // [8*32][LM_CPITCH]
-    __nv_bfloat16* Qs = Cs + LM_HEADS * LM_D * LM_CPITCH;                      // [64][LM_PITCH]
-    __nv_bfloat16* Os = Qs + 64 * LM_PITCH;                                    // [64][LM_PITCH]
+    __nv_bfloat16* ring = Cs + LM_HEADS * LM_D * LM_CPITCH;                    // [3][64][LM_PITCH]
+    __nv_bfloat16* Os = ring + LO_STAGES * LO_ROWS * LM_PITCH;                 // [64][LM_PITCH]
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+    const int n_begin = chunk * LM_CHUNK, n_end = min(N, n_begin + LM_CHUNK);
+    const int n_tiles = (n_end - n_begin) / LO_ROWS;
+    const size_t pix_base = (size_t)b * N + n_begin;
+    auto issue = [&](int it) {
+        issue_rows(ring + (size_t)(it % LO_STAGES) * LO_ROWS * LM_PITCH, qkv + (pix_base + (size_t)it * LO_ROWS) * 3 * LM_HID,
+                   3 * LM_HID, LO_ROWS);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n_tiles > 0) issue(0);
+    if (n_tiles > 1) issue(1);
     stage_ctx_bf16(ctx + (size_t)b * LM_HEADS * LM_D * LM_D, Cs);
     __syncthreads();
     // B[k = d][n = e] = ctx[d][e]: rows of Cs are the K index
@@ -203,10 +268,13 @@ __global__ void __launch_bounds__(256) la_out_mma_kernel(const __nv_bfloat16* __
 #pragma unroll
         for (int np = 0; np < 2; ++np) frag_b_krows(bf[ks][np], Cs + (size_t)h * LM_D * LM_CPITCH, LM_CPITCH, ks * 16, np * 16, lane);
     const int g = lane >> 2, t = lane & 3;
-    const int n_begin = chunk * LM_CHUNK, n_end = min(N, n_begin + LM_CHUNK);
-    for (int t0 = n_begin; t0 < n_end; t0 += 64) {
-        const int valid = min(64, n_end - t0);
-        load_rows<3>(qkv + ((size_t)b * N + t0) * 3 * LM_HID, 3 * LM_HID, valid, 64, Qs, nullptr, nullptr, scale);
+    for (int it = 0; it < n_tiles; ++it) {
+        __nv_bfloat16* Qs = ring + (size_t)(it % LO_STAGES) * LO_ROWS * LM_PITCH;
+        if (it + 1 < n_tiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                       // tile landed; previous Os copy-out and previous q tile reads are done
+        if (it + 2 < n_tiles) issue(it + 2);
+        transform_rows<3>(Qs, LO_ROWS, nullptr, nullptr, scale);
         __syncthreads();
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
@@ -230,18 +298,68 @@ __global__ void __launch_bounds__(256) la_out_mma_kernel(const __nv_bfloat16* __
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < valid * 32; idx += 256) {
+        for (int idx = tid; idx < LO_ROWS * 32; idx += 256) {
             const int row = idx >> 5, oc = idx & 31;
-            *reinterpret_cast<uint4*>(out + ((size_t)b * N + t0 + row) * LM_HID + oc * 8) =
+            *reinterpret_cast<uint4*>(out + (pix_base + (size_t)it * LO_ROWS + row) * LM_HID + oc * 8) =
                 *reinterpret_cast<const uint4*>(Os + (size_t)row * LM_PITCH + oc * 8);
         }
-        __syncthreads();
     }
 }
 
 // ---- backward per pixel ---------------------------------------------------------------------------------------------
+// Streaming kernel: a 3-deep cp.async ring of raw 16-pixel tiles (dout | q | k | v rows, 32 KiB per tile) keeps two
+// tiles in flight per SM while the current one is transformed in place (q -> softmax, k -> k~), multiplied on the
+// tensor cores and written back through a staging tile with 16-byte coalesced stores.
 constexpr int LB_ROWS = 16;
 constexpr int LB_OPITCH = 3 * LM_HID + 8;
+constexpr int LB_STAGES = 3;
+constexpr int LB_TILE_ELEMS = 4 * LB_ROWS * LM_PITCH;        // dout, q, k, v
+
+__device__ __forceinline__ void lb_issue_tile(__nv_bfloat16* buf, const __nv_bfloat16* __restrict__ qkv,
+                                              const __nv_bfloat16* __restrict__ dout, size_t pix0) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < LB_ROWS * 32; idx += blockDim.x) {
+        const int row = idx >> 5;
+        const __nv_bfloat16* qrow = qkv + (pix0 + row) * 3 * LM_HID + lane * 8;
+        __nv_bfloat16* d = buf + (size_t)row * LM_PITCH + lane * 8;
+        cp_async16(d, dout + (pix0 + row) * LM_HID + lane * 8);
+        cp_async16(d + LB_ROWS * LM_PITCH, qrow);
+        cp_async16(d + 2 * LB_ROWS * LM_PITCH, qrow + LM_HID);
+        cp_async16(d + 3 * LB_ROWS * LM_PITCH, qrow + 2 * LM_HID);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// in-place transforms of a landed tile: q rows -> softmax_d (unscaled p), k rows -> exp(k - M) * Zinv
+__device__ __forceinline__ void lb_transform_tile(__nv_bfloat16* buf, const float* sM, const float* sZi) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < LB_ROWS * 32; idx += blockDim.x) {
+        const int row = idx >> 5;
+        __nv_bfloat16* q = buf + (size_t)(LB_ROWS + row) * LM_PITCH + lane * 8;
+        __nv_bfloat16* k = buf + (size_t)(2 * LB_ROWS + row) * LM_PITCH + lane * 8;
+        float v[8];
+        ld8(q, v);
+        float mx = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= inv;
+        st8_smem(q, v);
+        ld8(k, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __expf(v[i] - sM[lane * 8 + i]) * sZi[lane * 8 + i];
+        st8_smem(k, v);
+    }
+}
+
 __global__ void __launch_bounds__(256) la_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                          const __nv_bfloat16* __restrict__ dout,
                                                          const float* __restrict__ ctx, const float* __restrict__ dctx,
@@ -250,15 +368,18 @@ __global__ void __launch_bounds__(256) la_bwd_mma_kernel(const __nv_bfloat16* __
     extern __shared__ __align__(16) unsigned char raw[];
     __nv_bfloat16* Cs = reinterpret_cast<__nv_bfloat16*>(raw);                 // ctx  [8*32][LM_CPITCH]
     __nv_bfloat16* Ds = Cs + LM_HEADS * LM_D * LM_CPITCH;                      // dctx [8*32][LM_CPITCH]
-    __nv_bfloat16* T0 = Ds + LM_HEADS * LM_D * LM_CPITCH;                      // dout tile
-    __nv_bfloat16* T1 = T0 + LB_ROWS * LM_PITCH;                               // p = softmax_d(q)
-    __nv_bfloat16* T2 = T1 + LB_ROWS * LM_PITCH;                               // k~
-    __nv_bfloat16* T3 = T2 + LB_ROWS * LM_PITCH;                               // v
-    __nv_bfloat16* Os = T3 + LB_ROWS * LM_PITCH;                               // [16][LB_OPITCH]: dq | dk | dv
+    __nv_bfloat16* ring = Ds + LM_HEADS * LM_D * LM_CPITCH;                    // [LB_STAGES][4][16][LM_PITCH]
+    __nv_bfloat16* Os = ring + LB_STAGES * LB_TILE_ELEMS;                      // [16][LB_OPITCH]: dq | dk | dv
     float* sM = reinterpret_cast<float*>(Os + LB_ROWS * LB_OPITCH);
     float* sZi = sM + LM_HID;
     float* scd = sZi + LM_HID;
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+    const int n_begin = chunk * LM_CHUNK, n_end = min(N, n_begin + LM_CHUNK);
+    const int n_tiles = (n_end - n_begin) / LB_ROWS;
+    const size_t pix_base = (size_t)b * N + n_begin;
+    // start the pipeline before the (global-memory) prologue so that both overlap
+    if (n_tiles > 0) lb_issue_tile(ring, qkv, dout, pix_base);
+    if (n_tiles > 1) lb_issue_tile(ring + LB_TILE_ELEMS, qkv, dout, pix_base + LB_ROWS);
     const float* cg = ctx + (size_t)b * LM_HEADS * LM_D * LM_D;
     const float* dg = dctx + (size_t)b * LM_HEADS * LM_D * LM_D;
     stage_ctx_bf16(cg, Cs);
@@ -285,15 +406,19 @@ __global__ void __launch_bounds__(256) la_bwd_mma_kernel(const __nv_bfloat16* __
         }
     const int g = lane >> 2, t = lane & 3;
     const float invN = 1.f / (float)N;
-    const int n_begin = chunk * LM_CHUNK, n_end = min(N, n_begin + LM_CHUNK);
-    for (int t0 = n_begin; t0 < n_end; t0 += LB_ROWS) {
-        const int valid = min(LB_ROWS, n_end - t0);
-        const __nv_bfloat16* rowp = qkv + ((size_t)b * N + t0) * 3 * LM_HID;
-        load_rows<0>(dout + ((size_t)b * N + t0) * LM_HID, LM_HID, valid, LB_ROWS, T0, nullptr, nullptr, 1.f);
-        load_rows<3>(rowp, 3 * LM_HID, valid, LB_ROWS, T1, nullptr, nullptr, 1.f);
-        load_rows<2>(rowp + LM_HID, 3 * LM_HID, valid, LB_ROWS, T2, sM, sZi, 1.f);
-        load_rows<0>(rowp + 2 * LM_HID, 3 * LM_HID, valid, LB_ROWS, T3, nullptr, nullptr, 1.f);
+    for (int it = 0; it < n_tiles; ++it) {
+        __nv_bfloat16* buf = ring + (size_t)(it % LB_STAGES) * LB_TILE_ELEMS;
+        if (it + 1 < n_tiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // tile `it` visible to all; Os of tile it-1 fully copied out
+        if (it + 2 < n_tiles)                              // ring slot (it+2)%3 held tile it-1: free since the sync above
+            lb_issue_tile(ring + (size_t)((it + 2) % LB_STAGES) * LB_TILE_ELEMS, qkv, dout, pix_base + (size_t)(it + 2) * LB_ROWS);
+        lb_transform_tile(buf, sM, sZi);
         __syncthreads();
+        const __nv_bfloat16* T0 = buf;                         // dout
+        const __nv_bfloat16* T1 = buf + LB_ROWS * LM_PITCH;    // p
+        const __nv_bfloat16* T2 = buf + 2 * LB_ROWS * LM_PITCH;  // k~
+        const __nv_bfloat16* T3 = buf + 3 * LB_ROWS * LM_PITCH;  // v
         float cq[4][4], ck[4][4], cv[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -339,18 +464,17 @@ __global__ void __launch_bounds__(256) la_bwd_mma_kernel(const __nv_bfloat16* __
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < valid * 96; idx += 256) {
+        for (int idx = tid; idx < LB_ROWS * 96; idx += 256) {
             const int row = idx / 96, oc = idx - row * 96;
-            *reinterpret_cast<uint4*>(dqkv + ((size_t)b * N + t0 + row) * 3 * LM_HID + oc * 8) =
+            *reinterpret_cast<uint4*>(dqkv + (pix_base + (size_t)it * LB_ROWS + row) * 3 * LM_HID + oc * 8) =
                 *reinterpret_cast<const uint4*>(Os + (size_t)row * LB_OPITCH + oc * 8);
         }
-        __syncthreads();
     }
 }
 
-constexpr size_t LA_CTX_SMEM = (size_t)2 * 64 * LM_PITCH * 2 + 2 * LM_HID * 4;
-constexpr size_t LA_OUT_SMEM = (size_t)LM_HEADS * LM_D * LM_CPITCH * 2 + (size_t)2 * 64 * LM_PITCH * 2;
-constexpr size_t LA_BWD_SMEM = (size_t)2 * LM_HEADS * LM_D * LM_CPITCH * 2 + (size_t)4 * LB_ROWS * LM_PITCH * 2 +
+constexpr size_t LA_CTX_SMEM = (size_t)2 * LC_TILE_ELEMS * 2 + 2 * LM_HID * 4;
+constexpr size_t LA_OUT_SMEM = (size_t)LM_HEADS * LM_D * LM_CPITCH * 2 + (size_t)(LO_STAGES + 1) * LO_ROWS * LM_PITCH * 2;
+constexpr size_t LA_BWD_SMEM = (size_t)2 * LM_HEADS * LM_D * LM_CPITCH * 2 + (size_t)LB_STAGES * LB_TILE_ELEMS * 2 +
                                (size_t)LB_ROWS * LB_OPITCH * 2 + 3 * LM_HID * 4;
 
 static int la_mma_attrs() {
