@@ -102,6 +102,7 @@ struct TcParams {
     int Ho, Wo;              // spatial size of the output tensor
     int TW, TH, TN;          // pixel box; TW*TH*TN == 128
     int tiles_h;             // GH / TH
+    int m_tiles, n_tiles, n_classes;   // persistent tile walk: tile = (cls * n_tiles + nt) * m_tiles + mt
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* y;
@@ -136,12 +137,21 @@ struct TcCfg {
     static constexpr int A_BYTES = TC_BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // big tiles: fill shared memory (one CTA per SM); small tiles: a short ring so that 2-5 CTAs co-reside per SM
-    // and hide each other's TMA / MMA / epilogue latencies (the 64x64 layers are latency-, not throughput-bound)
-    static constexpr int STAGES = STAGE_BYTES >= 40 * 1024 ? 4 : (STAGE_BYTES > 24 * 1024 ? 3 : 4);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // persistent kernel, one CTA per SM: the operand ring takes (almost) all shared memory so that the TMA producer
+    // runs many K-steps (and tiles) ahead of the tensor pipe; latency is hidden by the ring, not by co-resident CTAs
+    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
+    static constexpr int ACC_STAGES = 2;                                  // TMEM accumulators: epilogue(i) || mainloop(i+1)
+    static constexpr int TMEM_COLS = ACC_STAGES * BN;                     // 64 .. 512, power of two
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
+// Persistent, warp-specialised implicit-GEMM convolution.  Tiles (m_tile, n_tile, class) are walked with a static
+// stride of gridDim.x by all three roles in lock step:
+//   warp 0   TMA producer : keeps the smem ring full across tile boundaries
+//   warp 1   MMA issuer   : tcgen05.mma into TMEM accumulator (tile & 1); commits free ring slots / publish the tile
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue    : drain accumulator (tile & 1) while the tensor pipe already works on the next tile
 template <int BN, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                 const __grid_constant__ CUtensorMap map_w, TcParams p) {
@@ -152,19 +162,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t pad_bytes = (1024 - (raw_addr & 1023)) & 1023;
     unsigned char* ring = smem_raw + pad_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                       // [STAGES]
-    uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
-    uint64_t* acc_full = bars + 2 * Cfg::STAGES; // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+    uint64_t* full = bars;                                   // [STAGES]
+    uint64_t* empty = bars + Cfg::STAGES;                    // [STAGES]
+    uint64_t* acc_full = bars + 2 * Cfg::STAGES;             // [ACC_STAGES]
+    uint64_t* acc_empty = acc_full + Cfg::ACC_STAGES;        // [ACC_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x, n0 = blockIdx.y * BN;
-    const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
-    const int b0 = tb * p.TN, h0 = th_idx * p.TH;
     const int kc_per_tap = p.Cin / BK;
-    const TcClass& cl = p.cls[blockIdx.z];
-    const int n_taps = (p.mode == 0) ? p.KH * p.KW : cl.n_taps;
-    const int n_iters = n_taps * kc_per_tap;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.n_classes;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -172,12 +178,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
-        tc_mbar_init(acc_full, 1);
+        for (int s = 0; s < Cfg::ACC_STAGES; ++s) { tc_mbar_init(&acc_full[s], 1); tc_mbar_init(&acc_empty[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {   // TMEM allocation: BN fp32 columns (power of two >= 32), whole warp executes
+    if (warp == 2) {   // TMEM allocation (power of two >= 32 columns), whole warp executes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)),
-                     "r"(BN));
+                     "r"(Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -188,23 +194,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            for (int it = 0; it < n_iters; ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (it / Cfg::STAGES) & 1;
-                tc_mbar_wait(&empty[s], ph ^ 1);
-                const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
-                int dh, dw, ktap;
-                if (p.mode == 0) {
-                    const int r = tap / p.KW, q = tap - r * p.KW;
-                    dh = r - p.pad; dw = q - p.pad; ktap = tap;
-                } else {
-                    dh = cl.dh[tap]; dw = cl.dw[tap]; ktap = cl.ktap[tap];
+            uint32_t git = 0;                                  // global K-step counter (ring position)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tile_m = tile % p.m_tiles;
+                const int rest = tile / p.m_tiles;
+                const int n0 = (rest % p.n_tiles) * BN;
+                const TcClass& cl = p.cls[rest / p.n_tiles];
+                const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
+                const int b0 = tb * p.TN, h0 = th_idx * p.TH;
+                const int n_taps = (p.mode == 0) ? p.KH * p.KW : cl.n_taps;
+                for (int tap = 0; tap < n_taps; ++tap) {
+                    int dh, dw, ktap;
+                    if (p.mode == 0) {
+                        const int r = tap / p.KW, q = tap - r * p.KW;
+                        dh = r - p.pad; dw = q - p.pad; ktap = tap;
+                    } else {
+                        dh = cl.dh[tap]; dw = cl.dw[tap]; ktap = cl.ktap[tap];
+                    }
+                    for (int kc = 0; kc < kc_per_tap; ++kc, ++git) {
+                        const int s = git % Cfg::STAGES;
+                        const uint32_t ph = (git / Cfg::STAGES) & 1;
+                        tc_mbar_wait(&empty[s], ph ^ 1);
+                        unsigned char* a_dst = ring + s * Cfg::STAGE_BYTES;
+                        unsigned char* b_dst = a_dst + Cfg::A_BYTES;
+                        tc_mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                        tma_load_4d(a_dst, &map_x, &full[s], kc * BK, dw, p.in_stride * h0 + dh, b0);
+                        tma_load_2d(b_dst, &map_w, &full[s], ktap * p.Cin + kc * BK, n0);
+                    }
                 }
-                unsigned char* a_dst = ring + s * Cfg::STAGE_BYTES;
-                unsigned char* b_dst = a_dst + Cfg::A_BYTES;
-                tc_mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                tma_load_4d(a_dst, &map_x, &full[s], kc * BK, dw, p.in_stride * h0 + dh, b0);
-                tma_load_2d(b_dst, &map_w, &full[s], ktap * p.Cin + kc * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -213,36 +230,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
-        for (int it = 0; it < n_iters; ++it) {
-            const int s = it % Cfg::STAGES;
-            const uint32_t ph = (it / Cfg::STAGES) & 1;
-            tc_mbar_wait(&full[s], ph);
+        uint32_t git = 0;
+        int lt = 0;                                            // local tile counter
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int rest = tile / p.m_tiles;
+            const TcClass& cl = p.cls[rest / p.n_tiles];
+            const int n_iters = ((p.mode == 0) ? p.KH * p.KW : cl.n_taps) * kc_per_tap;
+            const int as = lt & 1;
+            tc_mbar_wait(&acc_empty[as], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint32_t a_addr = tc_smem_u32(ring + s * Cfg::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+            for (int it = 0; it < n_iters; ++it, ++git) {
+                const int s = git % Cfg::STAGES;
+                const uint32_t ph = (git / Cfg::STAGES) & 1;
+                tc_mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t a_addr = tc_smem_u32(ring + s * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t da = umma_desc<Cfg::SW>(a_addr + k * 32);
-                    const uint64_t db = umma_desc<Cfg::SW>(b_addr + k * 32);
-                    const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\t"
-                        "setp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
-                        "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                        : "memory");
-                }
-                // release the smem stage once the MMAs that read it have completed
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                 tc_smem_u32(&empty[s]))
-                             : "memory");
-                if (it == n_iters - 1)
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = umma_desc<Cfg::SW>(a_addr + k * 32);
+                        const uint64_t db = umma_desc<Cfg::SW>(b_addr + k * 32);
+                        const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_acc),
+                            "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                            : "memory");
+                    }
+                    // release the smem stage once the MMAs that read it have completed
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     tc_smem_u32(acc_full))
+                                     tc_smem_u32(&empty[s]))
                                  : "memory");
+                    if (it == n_iters - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                         tc_smem_u32(&acc_full[as]))
+                                     : "memory");
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (+bias, +residual) -> bf16 -> global =====
@@ -251,63 +279,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int tn = m / (p.TH * p.TW);
         const int rem = m - tn * p.TH * p.TW;
         const int th = rem / p.TW, tw = rem - th * p.TW;
-        const int b = b0 + tn, h = h0 + th;
-        const bool row_ok = (b < p.B) && (h < p.GH);
-        const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * tw + cl.off_w;
-        const size_t row_off = (((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0;
-        tc_mbar_wait(acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int tile_m = tile % p.m_tiles;
+            const int rest = tile / p.m_tiles;
+            const int n0 = (rest % p.n_tiles) * BN;
+            const TcClass& cl = p.cls[rest / p.n_tiles];
+            const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
+            const int b = tb * p.TN + tn, h = th_idx * p.TH + th;
+            const bool row_ok = (b < p.B) && (h < p.GH);
+            const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * tw + cl.off_w;
+            const size_t row_off = (((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0;
+            const int as = lt & 1;
+            tc_mbar_wait(&acc_full[as], (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
-            if (row_ok) {
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
-                        f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-                    }
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 32 >= BN) {
+                    // the last chunk of this accumulator is in registers: hand the TMEM stage back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&acc_empty[as])) : "memory");
                 }
-                if (p.residual) {
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float rv[8];
-                        ld8(p.residual + row_off + c + j, rv);
+                for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
+                if (row_ok) {
+                    if (p.bias) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) f[j + k] += rv[k];
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
+                            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                        }
                     }
-                }
+                    if (p.residual) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) st8(p.y + row_off + c + j, f + j);
-            }
-            if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
-                float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
-                const int fg = (n0 + c) / p.gn_cpg;
-                if (p.gn_cpg == 4) gn_stats_chunk<4>(f, sums_b, fg, lane);
-                else if (p.gn_cpg == 8) gn_stats_chunk<8>(f, sums_b, fg, lane);
-                else if (p.gn_cpg == 16) gn_stats_chunk<16>(f, sums_b, fg, lane);
-                else gn_stats_chunk<32>(f, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): chunk inside one group
+                        for (int j = 0; j < 32; j += 8) {
+                            float rv[8];
+                            ld8(p.residual + row_off + c + j, rv);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[j + k] += rv[k];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) st8(p.y + row_off + c + j, f + j);
+                }
+                if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
+                    float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
+                    const int fg = (n0 + c) / p.gn_cpg;
+                    if (p.gn_cpg == 4) gn_stats_chunk<4>(f, sums_b, fg, lane);
+                    else if (p.gn_cpg == 8) gn_stats_chunk<8>(f, sums_b, fg, lane);
+                    else if (p.gn_cpg == 16) gn_stats_chunk<16>(f, sums_b, fg, lane);
+                    else gn_stats_chunk<32>(f, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): chunk inside one group
+                }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS));
     }
 }
 
@@ -458,7 +501,17 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
                      "4, 8, 16 or a multiple of 32 channels per group (got %d)", cpg);
         PIDM_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)B * gn_groups * 2 * sizeof(float), st));
     }
-    dim3 grid(((B + pl.TN - 1) / pl.TN) * p.tiles_h, Cout / pl.BN, classes);
+    p.m_tiles = ((B + pl.TN - 1) / pl.TN) * p.tiles_h;
+    p.n_tiles = Cout / pl.BN;
+    p.n_classes = classes;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        PIDM_CUDA(cudaGetDevice(&dev));
+        PIDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int total_tiles = p.m_tiles * p.n_tiles * p.n_classes;
+    dim3 grid(total_tiles < sm_count ? total_tiles : sm_count);
 #define TC_CASE(bn, bk) if (pl.BN == bn && pl.BK == bk) return launch_tc<bn, bk>(mx, mw, p, grid, st)
     TC_CASE(256, 64); TC_CASE(128, 64); TC_CASE(64, 64); TC_CASE(32, 64);
     TC_CASE(256, 32); TC_CASE(128, 32); TC_CASE(64, 32); TC_CASE(32, 32);
