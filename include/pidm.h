@@ -90,6 +90,8 @@ int pidm_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, float* dbia
 int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
                    int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
+/* debugging aid: device buffer (>= 4096 int64) receiving a clock64 timeline of CTA 0 of every tensor-core conv launch */
+int pidm_debug_set_trace(void* buf);
 /* General tensor-core path: stride-1/2 regular convolution (input sampled through TMA elementStrides) and the
  * stride-2 transposed gather (ConvTranspose forward / dgrad of the stride-2 conv) as 4 output-parity classes.
  * gn_sums (optional, [B, gn_groups, 2], zeroed here): per-(sample, group) sum and sum of squares of the fp32 output,

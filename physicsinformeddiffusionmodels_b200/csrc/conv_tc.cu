@@ -106,29 +106,64 @@ struct TcParams {
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* y;
+    long long* trace;        // optional debug timeline of CTA 0 (pidm_debug_set_trace): [role][event] = clock64
     float* gn_sums;          // optional [B, G, 2]: GroupNorm sum / sum-of-squares of the output, fused into the epilogue
     int gn_cpg, gn_groups;   // channels per group, groups
     TcClass cls[4];
 };
 
-// GroupNorm statistics of one 32-channel chunk held by a warp (one pixel row per lane): per group, reduce over the
-// group's channels in registers, over the 32 pixels by shuffles, one atomic pair per group per warp.
+// GroupNorm statistics of one 32-channel chunk held by a warp (one pixel row per lane).  Per group the channels
+// are summed in registers; the 2*NG partial sums of the 32 lanes are then reduced with a butterfly that halves the
+// number of live values at every step (NV + log2-many shuffles instead of 5 per value), leaving value i on lanes
+// {i*32/NV ...}; those lanes issue one atomic each.
+template <int NV>
+__device__ __forceinline__ float butterfly_reduce(float (&v)[NV], int lane) {
+    // after the step with offset `off`, a lane keeps the half of its values selected by bit `off` of its lane id
+    int n = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            const int half = n >> 1;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < half) {
+                    const float keep = upper ? v[i + half] : v[i];
+                    const float send = upper ? v[i] : v[i + half];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            n = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+    return v[0];
+}
+
 template <int CPG>
 __device__ __forceinline__ void gn_stats_chunk(const float f[32], float* sums_b, int first_group, int lane) {
     constexpr int NG = (CPG >= 32) ? 1 : 32 / CPG;
     constexpr int W = (CPG >= 32) ? 32 : CPG;
+    constexpr int NV = 2 * NG;                      // (sum, sumsq) per group: 2, 4, 8 or 16 values
+    float v[NV];
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
         float s = 0.f, ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < W; ++j) { float v = f[gi * W + j]; s += v; ss += v * v; }
-        s = warp_sum(s);
-        ss = warp_sum(ss);
-        if (lane == 0) {
-            atomicAdd(sums_b + (first_group + gi) * 2, s);
-            atomicAdd(sums_b + (first_group + gi) * 2 + 1, ss);
-        }
+        for (int j = 0; j < W; ++j) { float x = f[gi * W + j]; s += x; ss += x * x; }
+        v[2 * gi] = s; v[2 * gi + 1] = ss;
     }
+    const float total = butterfly_reduce<NV>(v, lane);
+    // value index held by this lane: built from the lane bits consumed while n > 1 (bit 16 first = most significant)
+    int idx = 0, n = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) { n >>= 1; if (lane & off) idx += n; }
+    }
+    // lanes that differ only in the bits consumed after n reached 1 hold the same total: the lowest one publishes
+    constexpr int DUP = 32 / NV;
+    if ((lane & (DUP - 1)) == 0) atomicAdd(sums_b + first_group * 2 + idx, total);
 }
 
 template <int BN, int BK>
@@ -191,8 +226,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===== TMA producer =====
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ===== TMA producers: three warps, one elected lane each, K-step `git` belongs to producer git % 3 ===========
+        // (a single thread can only issue a K-step every ~600 cycles -- wait + expect_tx + 2 TMA -- which starved the
+        //  tensor pipe on the small-channel layers; the three issue streams are independent)
+        const uint32_t pidx = (warp == 0) ? 0u : (uint32_t)(warp - 1);
         if (elect_one()) {
             uint32_t git = 0;                                  // global K-step counter (ring position)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -203,6 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
                 const int b0 = tb * p.TN, h0 = th_idx * p.TH;
                 const int n_taps = (p.mode == 0) ? p.KH * p.KW : cl.n_taps;
+                if (p.trace && blockIdx.x == 0 && pidx == 0 && git < 2000) p.trace[git / kc_per_tap / (n_taps > 0 ? n_taps : 1) * 2] = clock64();
                 for (int tap = 0; tap < n_taps; ++tap) {
                     int dh, dw, ktap;
                     if (p.mode == 0) {
@@ -212,6 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         dh = cl.dh[tap]; dw = cl.dw[tap]; ktap = cl.ktap[tap];
                     }
                     for (int kc = 0; kc < kc_per_tap; ++kc, ++git) {
+                        if (git % 3u != pidx) continue;
                         const int s = git % Cfg::STAGES;
                         const uint32_t ph = (git / Cfg::STAGES) & 1;
                         tc_mbar_wait(&empty[s], ph ^ 1);
@@ -237,8 +277,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const TcClass& cl = p.cls[rest / p.n_tiles];
             const int n_iters = ((p.mode == 0) ? p.KH * p.KW : cl.n_taps) * kc_per_tap;
             const int as = lt & 1;
+            if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64) p.trace[1024 + lt * 4] = clock64();
             tc_mbar_wait(&acc_empty[as], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64) p.trace[1024 + lt * 4 + 1] = clock64();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
             for (int it = 0; it < n_iters; ++it, ++git) {
                 const int s = git % Cfg::STAGES;
@@ -270,7 +312,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                      : "memory");
                 }
                 __syncwarp();
+                if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64 && it == 0) p.trace[1024 + lt * 4 + 2] = clock64();
             }
+            if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64) p.trace[1024 + lt * 4 + 3] = clock64();
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (+bias, +residual) -> bf16 -> global =====
@@ -291,8 +335,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * tw + cl.off_w;
             const size_t row_off = (((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0;
             const int as = lt & 1;
+            if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64) p.trace[2048 + lt * 4] = clock64();
             tc_mbar_wait(&acc_full[as], (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64) p.trace[2048 + lt * 4 + 1] = clock64();
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
@@ -308,6 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                       "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64 && c == 0) p.trace[3072 + lt * 4] = clock64();
                 if (c + 32 >= BN) {
                     // the last chunk of this accumulator is in registers: hand the TMEM stage back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -336,6 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) st8(p.y + row_off + c + j, f + j);
                 }
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 1] = clock64();
                 if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
                     float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
                     const int fg = (n0 + c) / p.gn_cpg;
@@ -344,7 +392,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     else if (p.gn_cpg == 16) gn_stats_chunk<16>(f, sums_b, fg, lane);
                     else gn_stats_chunk<32>(f, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): chunk inside one group
                 }
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 2] = clock64();
             }
+            if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64) p.trace[2048 + lt * 4 + 2] = clock64();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -415,6 +465,8 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
 }
 
 // geometry of one call -> (pixel grid, classes).  Returns false when the tensor-core kernel does not cover it.
+static long long* g_tc_trace = nullptr;
+
 static bool tc_geometry(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
                         int transposed, TcParams& p, TcPlan& pl, int& classes) {
     if (KH != KW) return false;
@@ -493,6 +545,7 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
     }
     p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = (__nv_bfloat16*)y;
+    p.trace = g_tc_trace;
     p.gn_sums = gn_sums; p.gn_groups = gn_groups; p.gn_cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     if (gn_sums) {
         PIDM_REQUIRE(gn_groups > 0 && Cout % gn_groups == 0, "conv2d_tc: bad GroupNorm group count %d", gn_groups);
@@ -521,6 +574,12 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
 
 }  // namespace pidm
 using namespace pidm;
+
+// debugging aid: device buffer of >= 4096 int64 that receives a clock64 timeline of CTA 0 of every conv_tc launch
+extern "C" int pidm_debug_set_trace(void* buf) {
+    g_tc_trace = (long long*)buf;
+    return 0;
+}
 
 extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad) {
     TcParams p; TcPlan pl; int classes;
