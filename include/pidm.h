@@ -94,11 +94,12 @@ int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int
 int pidm_debug_set_trace(void* buf);
 /* General tensor-core path: stride-1/2 regular convolution (input sampled through TMA elementStrides) and the
  * stride-2 transposed gather (ConvTranspose forward / dgrad of the stride-2 conv) as 4 output-parity classes.
- * gn_sums (optional, [B, gn_groups, 2], zeroed here): per-(sample, group) sum and sum of squares of the fp32 output,
- * accumulated in the epilogue so that the following GroupNorm needs no statistics pass. */
+ * gn_sums (optional, [B, gn_groups, 2]): per-(sample, group) sum and sum of squares of the fp32 output, accumulated in
+ * the epilogue so that the following GroupNorm needs no statistics pass.  It is zeroed here (one memset node) unless
+ * gn_sums_zeroed != 0, i.e. the caller hands in a slice of a buffer it has already cleared. */
 int pidm_conv2d_tc_general(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B,
                            int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad,
-                           int transposed, float* gn_sums, int gn_groups, void* stream);
+                           int transposed, float* gn_sums, int gn_groups, int gn_sums_zeroed, void* stream);
 int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride,
                                      int pad, int transposed);
 /* wgrad on tcgen05: D[(tap,cA)][cB] = sum over grid pixels g of a[a_stride*g - pad + tap][cA] * b[g][cB], MN-major

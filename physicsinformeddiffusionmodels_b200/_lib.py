@@ -38,7 +38,7 @@ _SIGS = {
     'pidm_conv2d_tc': [P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     'pidm_conv2d_tc_supported': [I, I, I, I, I, I, I, I],
     'pidm_debug_set_trace': [P],
-    'pidm_conv2d_tc_general': [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, P],
+    'pidm_conv2d_tc_general': [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, I, I, P],
     'pidm_conv2d_tc_general_supported': [I, I, I, I, I, I, I, I, I, I, I, I],
     'pidm_conv2d_wgrad_tc': [P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, L, L, P],
     'pidm_conv2d_wgrad_tc_supported': [I, I, I, I, I, I, I, I],

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "pidm.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace pidm {
 
@@ -101,7 +102,15 @@ struct TcParams {
     int in_stride, out_scale;
     int Ho, Wo;              // spatial size of the output tensor
     int TW, TH, TN;          // pixel box; TW*TH*TN == 128
-    int tiles_h;             // GH / TH
+    int tiles_h, tiles_w;    // GH / TH, GW / TW
+    // operand staging plan (see tc_plan):
+    //   rg = 1  "row-group" mode for stride-1 KxK convs on 16x8 (rows x cols) pixel tiles: one A box of
+    //           (TH + KH - 1) x TW pixels per kernel COLUMN q serves the KH vertical taps as row-shifted views of the
+    //           same shared-memory tile (a shift of r rows = r * TW * row_bytes, a whole swizzle period), so the
+    //           L2 -> SM operand traffic drops from KH*KW to KW * (TH + KH - 1) / TH tiles per output tile
+    //   nb      B (weight) tiles consumed per K-step (KH in row-group mode, else 1)
+    //   resident = 1: all weights of the CTA's (single) n-tile are loaded once into shared memory
+    int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes;
     int m_tiles, n_tiles, n_classes;   // persistent tile walk: tile = (cls * n_tiles + nt) * m_tiles + mt
     const float* bias;
     const __nv_bfloat16* residual;
@@ -142,7 +151,7 @@ __device__ __forceinline__ float butterfly_reduce(float (&v)[NV], int lane) {
 }
 
 template <int CPG>
-__device__ __forceinline__ void gn_stats_chunk(const float f[32], float* sums_b, int first_group, int lane) {
+__device__ __forceinline__ void gn_stats_chunk(const float* f, float* sums_b, int first_group, int lane) {
     constexpr int NG = (CPG >= 32) ? 1 : 32 / CPG;
     constexpr int W = (CPG >= 32) ? 32 : CPG;
     constexpr int NV = 2 * NG;                      // (sum, sumsq) per group: 2, 4, 8 or 16 values
@@ -169,17 +178,15 @@ __device__ __forceinline__ void gn_stats_chunk(const float f[32], float* sums_b,
 template <int BN, int BK>
 struct TcCfg {
     static constexpr int SW = BK * 2;                                     // swizzle span in bytes (128 or 64)
-    static constexpr int A_BYTES = TC_BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // persistent kernel, one CTA per SM: the operand ring takes (almost) all shared memory so that the TMA producer
-    // runs many K-steps (and tiles) ahead of the tensor pipe; latency is hidden by the ring, not by co-resident CTAs
-    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
     static constexpr int ACC_STAGES = 2;                                  // TMEM accumulators: epilogue(i) || mainloop(i+1)
     static constexpr int TMEM_COLS = ACC_STAGES * BN;                     // 64 .. 512, power of two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
+// persistent kernel, one CTA per SM: the operand ring takes (almost) all shared memory so that the TMA producers
+// run many K-steps (and tiles) ahead of the tensor pipe; latency is hidden by the ring, not by co-resident CTAs
+constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_OPERAND_BYTES = 200 * 1024;                              // resident weights + ring
+constexpr int TC_SMEM_BYTES = TC_OPERAND_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
 
 // Persistent, warp-specialised implicit-GEMM convolution.  Tiles (m_tile, n_tile, class) are walked with a static
 // stride of gridDim.x by all three roles in lock step:
@@ -195,13 +202,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // 1024-byte aligned operand ring (required by the 128B swizzle atoms)
     const uint32_t raw_addr = tc_smem_u32(smem_raw);
     const uint32_t pad_bytes = (1024 - (raw_addr & 1023)) & 1023;
-    unsigned char* ring = smem_raw + pad_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full = bars;                                   // [STAGES]
-    uint64_t* empty = bars + Cfg::STAGES;                    // [STAGES]
-    uint64_t* acc_full = bars + 2 * Cfg::STAGES;             // [ACC_STAGES]
+    unsigned char* wres = smem_raw + pad_bytes;              // resident weights (res_bytes, may be 0)
+    unsigned char* ring = wres + p.res_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pad_bytes + TC_OPERAND_BYTES);
+    uint64_t* full = bars;                                   // [TC_MAX_STAGES]
+    uint64_t* empty = bars + TC_MAX_STAGES;                  // [TC_MAX_STAGES]
+    uint64_t* acc_full = bars + 2 * TC_MAX_STAGES;           // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + Cfg::ACC_STAGES;        // [ACC_STAGES]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::ACC_STAGES);
+    uint64_t* wfull = acc_empty + Cfg::ACC_STAGES;           // resident weights have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    unsigned char* stage_base = smem_raw + pad_bytes + TC_OPERAND_BYTES + 512;   // 4 warps x 4 KB epilogue staging
+    const int n_stages = p.stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kc_per_tap = p.Cin / BK;
@@ -212,8 +223,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < n_stages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
         for (int s = 0; s < Cfg::ACC_STAGES; ++s) { tc_mbar_init(&acc_full[s], 1); tc_mbar_init(&acc_empty[s], 128); }
+        tc_mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {   // TMEM allocation (power of two >= 32 columns), whole warp executes
@@ -232,36 +244,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         //  tensor pipe on the small-channel layers; the three issue streams are independent)
         const uint32_t pidx = (warp == 0) ? 0u : (uint32_t)(warp - 1);
         if (elect_one()) {
-            uint32_t git = 0;                                  // global K-step counter (ring position)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int tile_m = tile % p.m_tiles;
-                const int rest = tile / p.m_tiles;
+            if (p.resident && pidx == 0) {
+                // all K tiles of the (single) n-tile: [tap][kc] boxes of BN x BK
+                const int n_k = p.KH * p.KW * kc_per_tap;
+                tc_mbar_expect_tx(wfull, (uint32_t)(n_k * Cfg::B_BYTES));
+                for (int i = 0; i < n_k; ++i) tma_load_2d(wres + (size_t)i * Cfg::B_BYTES, &map_w, wfull, i * BK, 0);
+            }
+            // ring position (stage, phase, whose turn) is carried incrementally: no integer divisions in the loop
+            uint32_t st = 0, ph = 0, turn = 0, git = 0;
+            unsigned char* a_dst = ring;
+            const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+            const int groups_m0 = p.rg ? p.KW : p.KH * p.KW;
+            int tile_m = blockIdx.x % p.m_tiles, rest = blockIdx.x / p.m_tiles;      // tile = rest * m_tiles + tile_m
+            const int step_m = gridDim.x % p.m_tiles, step_r = gridDim.x / p.m_tiles;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
                 const int n0 = (rest % p.n_tiles) * BN;
                 const TcClass& cl = p.cls[rest / p.n_tiles];
-                const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
-                const int b0 = tb * p.TN, h0 = th_idx * p.TH;
-                const int n_taps = (p.mode == 0) ? p.KH * p.KW : cl.n_taps;
-                if (p.trace && blockIdx.x == 0 && pidx == 0 && git < 2000) p.trace[git / kc_per_tap / (n_taps > 0 ? n_taps : 1) * 2] = clock64();
-                for (int tap = 0; tap < n_taps; ++tap) {
+                const int tw_idx = tile_m % p.tiles_w;
+                const int t2 = tile_m / p.tiles_w;
+                const int tb = t2 / p.tiles_h, th_idx = t2 - tb * p.tiles_h;
+                const int b0 = tb * p.TN, hh0 = p.in_stride * th_idx * p.TH, ww0 = p.in_stride * tw_idx * p.TW;
+                const int n_groups = (p.mode == 0) ? groups_m0 : cl.n_taps;
+                if (tracing && pidx == 0 && lt < 500) p.trace[lt * 2] = clock64();
+                int r = 0, q = 0;                              // mode 0, plain: tap (r, q) walked incrementally
+                for (int g = 0; g < n_groups; ++g) {
                     int dh, dw, ktap;
                     if (p.mode == 0) {
-                        const int r = tap / p.KW, q = tap - r * p.KW;
-                        dh = r - p.pad; dw = q - p.pad; ktap = tap;
+                        if (p.rg) { dh = -p.pad; dw = g - p.pad; }
+                        else { dh = r - p.pad; dw = q - p.pad; if (++q == p.KW) { q = 0; ++r; } }
+                        ktap = g;
                     } else {
-                        dh = cl.dh[tap]; dw = cl.dw[tap]; ktap = cl.ktap[tap];
+                        dh = cl.dh[g]; dw = cl.dw[g]; ktap = cl.ktap[g];
                     }
-                    for (int kc = 0; kc < kc_per_tap; ++kc, ++git) {
-                        if (git % 3u != pidx) continue;
-                        const int s = git % Cfg::STAGES;
-                        const uint32_t ph = (git / Cfg::STAGES) & 1;
-                        tc_mbar_wait(&empty[s], ph ^ 1);
-                        unsigned char* a_dst = ring + s * Cfg::STAGE_BYTES;
-                        unsigned char* b_dst = a_dst + Cfg::A_BYTES;
-                        tc_mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                        tma_load_4d(a_dst, &map_x, &full[s], kc * BK, dw, p.in_stride * h0 + dh, b0);
-                        tma_load_2d(b_dst, &map_w, &full[s], ktap * p.Cin + kc * BK, n0);
+                    int kcol = ktap * p.Cin;
+                    for (int kc = 0; kc < kc_per_tap; ++kc, kcol += BK) {
+                        if (turn == pidx) {
+                            tc_mbar_wait(&empty[st], ph ^ 1);
+                            if (tracing && git < 1000) p.trace[6144 + git] = clock64();
+                            tc_mbar_expect_tx(&full[st], (uint32_t)p.stage_bytes);
+                            tma_load_4d(a_dst, &map_x, &full[st], kc * BK, ww0 + dw, hh0 + dh, b0);
+                            if (!p.resident) {
+                                unsigned char* b_dst = a_dst + p.a_bytes;
+                                int kj = kcol;
+                                for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
+                                    tma_load_2d(b_dst, &map_w, &full[st], kj, n0);   // row-group mode: tap (r = j, q = g)
+                            }
+                        }
+                        ++git;
+                        if (++turn == 3u) turn = 0;
+                        if (++st == (uint32_t)n_stages) { st = 0; ph ^= 1; a_dst = ring; } else a_dst += p.stage_bytes;
                     }
                 }
+                tile_m += step_m; rest += step_r;
+                if (tile_m >= p.m_tiles) { tile_m -= p.m_tiles; ++rest; }
             }
         }
     } else if (warp == 1) {
@@ -270,131 +306,209 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
-        uint32_t git = 0;
-        int lt = 0;                                            // local tile counter
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-            const int rest = tile / p.m_tiles;
-            const TcClass& cl = p.cls[rest / p.n_tiles];
-            const int n_iters = ((p.mode == 0) ? p.KH * p.KW : cl.n_taps) * kc_per_tap;
-            const int as = lt & 1;
-            if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64) p.trace[1024 + lt * 4] = clock64();
-            tc_mbar_wait(&acc_empty[as], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64) p.trace[1024 + lt * 4 + 1] = clock64();
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
-            for (int it = 0; it < n_iters; ++it, ++git) {
-                const int s = git % Cfg::STAGES;
-                const uint32_t ph = (git / Cfg::STAGES) & 1;
-                tc_mbar_wait(&full[s], ph);
+        // One elected thread runs the whole loop.  The loop body is kept free of integer divisions and descriptor
+        // re-encoding: a clock64 trace showed ~500 cycles of scalar overhead per K-step in the naive form, more than
+        // the MMAs themselves on the narrow (N = 32) tiles.
+        if (elect_one()) {
+            const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+            // descriptor = hi(constant: SBO, version, swizzle) : lo(start >> 4 | LBO = 1 << 16)
+            const uint32_t desc_hi = (uint32_t)(umma_desc<Cfg::SW>(0) >> 32);
+            const uint32_t ring_lo = ((tc_smem_u32(ring) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t wres_lo = ((tc_smem_u32(wres) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4;
+            const uint32_t a_shift_lo = (uint32_t)(p.TW * BK * 2) >> 4;      // one tile row of pixels
+            const uint32_t b_off_lo = (uint32_t)p.a_bytes >> 4;
+            constexpr uint32_t b_tile_lo = (uint32_t)Cfg::B_BYTES >> 4;
+            const uint32_t res_j_lo = (uint32_t)(p.KW * kc_per_tap) * b_tile_lo;   // resident: next kernel row
+            const int groups_m0 = p.rg ? p.KW : p.KH * p.KW;
+            const int nb = p.nb;
+            const bool resident = p.resident != 0;
+            uint32_t st = 0, ph = 0, a_lo = ring_lo, git = 0;
+            int rest = blockIdx.x / p.m_tiles, tile_m = blockIdx.x % p.m_tiles;
+            const int step_m = gridDim.x % p.m_tiles, step_r = gridDim.x / p.m_tiles;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const int n_iters = ((p.mode == 0) ? groups_m0 : p.cls[rest / p.n_tiles].n_taps) * kc_per_tap;
+                const int as = lt & 1;
+                if (tracing && lt < 64) p.trace[1024 + lt * 4] = clock64();
+                if (lt == 0 && resident) tc_mbar_wait(wfull, 0);
+                tc_mbar_wait(&acc_empty[as], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t a_addr = tc_smem_u32(ring + s * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                if (tracing && lt < 64) p.trace[1024 + lt * 4 + 1] = clock64();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                uint32_t accum = 0;
+                uint32_t res_lo = wres_lo;                           // resident weights: tile (it) of kernel row 0
+                for (int it = 0; it < n_iters; ++it, res_lo += b_tile_lo) {
+                    tc_mbar_wait(&full[st], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (tracing && git < 1000) p.trace[4096 + git * 2] = clock64();
+                    uint32_t aj = a_lo;
+                    uint32_t bj = resident ? res_lo : a_lo + b_off_lo;
+                    const uint32_t bj_step = resident ? res_j_lo : b_tile_lo;
+                    for (int j = 0; j < nb; ++j, aj += a_shift_lo, bj += bj_step) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = umma_desc<Cfg::SW>(a_addr + k * 32);
-                        const uint64_t db = umma_desc<Cfg::SW>(b_addr + k * 32);
-                        const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_acc),
-                            "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                            : "memory");
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(aj + 2 * k);
+                            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(bj + 2 * k);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_acc),
+                                "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                                : "memory");
+                            accum = 1;
+                        }
                     }
                     // release the smem stage once the MMAs that read it have completed
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     tc_smem_u32(&empty[s]))
+                                     tc_smem_u32(&empty[st]))
                                  : "memory");
-                    if (it == n_iters - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                         tc_smem_u32(&acc_full[as]))
-                                     : "memory");
+                    if (tracing && git < 1000) p.trace[4096 + git * 2 + 1] = clock64();
+                    ++git;
+                    if (++st == (uint32_t)n_stages) { st = 0; ph ^= 1; a_lo = ring_lo; } else a_lo += stage_lo;
                 }
-                __syncwarp();
-                if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64 && it == 0) p.trace[1024 + lt * 4 + 2] = clock64();
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 tc_smem_u32(&acc_full[as]))
+                             : "memory");
+                if (tracing && lt < 64) p.trace[1024 + lt * 4 + 3] = clock64();
+                tile_m += step_m; rest += step_r;
+                if (tile_m >= p.m_tiles) { tile_m -= p.m_tiles; ++rest; }
             }
-            if (p.trace && blockIdx.x == 0 && lane == 0 && lt < 64) p.trace[1024 + lt * 4 + 3] = clock64();
         }
+        __syncwarp();
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> (+bias, +residual) -> bf16 -> global =====
+        // ===== epilogue: TMEM -> registers (+bias, +residual, GroupNorm statistics) -> bf16 -> smem transpose -> global
+        // A lane owns one accumulator row (pixel).  Writing its row straight to global memory would make every store
+        // instruction touch 32 different lines (16 bytes each): the LSU, not HBM, bounds the wide-N layers that way.
+        // Instead each warp stages its 32 rows x CH columns in a private, XOR-swizzled shared-memory tile and writes it
+        // back with LPR lanes per row, i.e. whole 64/128-byte row segments per quarter-warp.  The residual is read the
+        // same way (coalesced -> staged -> own row) so that it is still added in fp32 before the single rounding.
+        constexpr int CH = BN >= 64 ? 64 : 32;        // columns per pass
+        constexpr int LPR = CH / 8;                   // 16-byte units per staged row = lanes per row when storing
+        constexpr int RPI = 32 / LPR;                 // rows per store instruction
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        uint4* stage = reinterpret_cast<uint4*>(stage_base) + quarter * (32 * 8);
         const int m = quarter * 32 + lane;            // accumulator row = pixel within the tile
         const int tn = m / (p.TH * p.TW);
         const int rem = m - tn * p.TH * p.TW;
         const int th = rem / p.TW, tw = rem - th * p.TW;
+        const int my_sw = (LPR == 8) ? (lane & 7) : ((lane >> 1) & 3);
+        const int sr = lane / LPR, su = lane % LPR;   // store phase: row within the group of RPI rows, 16-byte unit
+        const bool tracing = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
+        int tile_m = blockIdx.x % p.m_tiles, rest = blockIdx.x / p.m_tiles;
+        const int step_m = gridDim.x % p.m_tiles, step_r = gridDim.x / p.m_tiles;
         int lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-            const int tile_m = tile % p.m_tiles;
-            const int rest = tile / p.m_tiles;
             const int n0 = (rest % p.n_tiles) * BN;
             const TcClass& cl = p.cls[rest / p.n_tiles];
-            const int tb = tile_m / p.tiles_h, th_idx = tile_m - tb * p.tiles_h;
-            const int b = tb * p.TN + tn, h = th_idx * p.TH + th;
+            const int tw_idx = tile_m % p.tiles_w;
+            const int t2 = tile_m / p.tiles_w;
+            const int tb = t2 / p.tiles_h, th_idx = t2 - tb * p.tiles_h;
+            const int b = tb * p.TN + tn, h = th_idx * p.TH + th, w = tw_idx * p.TW + tw;
             const bool row_ok = (b < p.B) && (h < p.GH);
-            const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * tw + cl.off_w;
-            const size_t row_off = (((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0;
+            const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * w + cl.off_w;
+            const long long row_off = row_ok ? (long long)((((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0) : -1ll;
+            // offsets of the rows this lane stores (row it * RPI + sr), -1 = masked
+            long long st_off[LPR];
+#pragma unroll
+            for (int it = 0; it < LPR; ++it) st_off[it] = __shfl_sync(0xffffffffu, row_off, it * RPI + sr);
             const int as = lt & 1;
-            if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64) p.trace[2048 + lt * 4] = clock64();
+            if (tracing && lt < 64) p.trace[2048 + lt * 4] = clock64();
             tc_mbar_wait(&acc_full[as], (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64) p.trace[2048 + lt * 4 + 1] = clock64();
+            if (tracing && lt < 64) p.trace[2048 + lt * 4 + 1] = clock64();
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64 && c == 0) p.trace[3072 + lt * 4] = clock64();
-                if (c + 32 >= BN) {
-                    // the last chunk of this accumulator is in registers: hand the TMEM stage back to the MMA warp
+            for (int c = 0; c < BN; c += CH) {
+                float f[CH];
+#pragma unroll
+                for (int hh = 0; hh < CH / 32; ++hh) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c + hh * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[hh * 32 + j] = row_ok ? __uint_as_float(v[j]) : 0.f;
+                }
+                if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4] = clock64();
+                if (c + CH >= BN) {
+                    // the last columns of this accumulator are in registers: hand the TMEM stage back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&acc_empty[as])) : "memory");
                 }
-                float f[32];
+                if (p.bias && row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
-                if (row_ok) {
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c + j);
-                            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-                        }
+                    for (int j = 0; j < CH; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+                        f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
                     }
-                    if (p.residual) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float rv[8];
-                            ld8(p.residual + row_off + c + j, rv);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) f[j + k] += rv[k];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) st8(p.y + row_off + c + j, f + j);
                 }
-                if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 1] = clock64();
+                if (p.residual) {
+#pragma unroll
+                    for (int it = 0; it < LPR; ++it) {
+                        const int r = it * RPI + sr;
+                        const int sw = (LPR == 8) ? (r & 7) : ((r >> 1) & 3);
+                        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                        if (st_off[it] >= 0) rv = *reinterpret_cast<const uint4*>(p.residual + st_off[it] + c + su * 8);
+                        stage[r * LPR + (su ^ sw)] = rv;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < LPR; ++u) {
+                        const uint4 rv = stage[lane * LPR + (u ^ my_sw)];
+                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            f[u * 8 + 2 * k] += __low2float(hp[k]);
+                            f[u * 8 + 2 * k + 1] += __high2float(hp[k]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                // bf16 rows -> swizzled staging tile
+#pragma unroll
+                for (int u = 0; u < LPR; ++u) {
+                    uint4 pk;
+                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hp[k] = __floats2bfloat162_rn(f[u * 8 + 2 * k], f[u * 8 + 2 * k + 1]);
+                    stage[lane * LPR + (u ^ my_sw)] = pk;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < LPR; ++it) {
+                    const int r = it * RPI + sr;
+                    const int sw = (LPR == 8) ? (r & 7) : ((r >> 1) & 3);
+                    if (st_off[it] >= 0)
+                        *reinterpret_cast<uint4*>(p.y + st_off[it] + c + su * 8) = stage[r * LPR + (su ^ sw)];
+                }
+                if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 1] = clock64();
                 if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
                     float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
-                    const int fg = (n0 + c) / p.gn_cpg;
-                    if (p.gn_cpg == 4) gn_stats_chunk<4>(f, sums_b, fg, lane);
-                    else if (p.gn_cpg == 8) gn_stats_chunk<8>(f, sums_b, fg, lane);
-                    else if (p.gn_cpg == 16) gn_stats_chunk<16>(f, sums_b, fg, lane);
-                    else gn_stats_chunk<32>(f, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): chunk inside one group
+#pragma unroll
+                    for (int hh = 0; hh < CH / 32; ++hh) {
+                        const int fg = (n0 + c + hh * 32) / p.gn_cpg;
+                        const float* fh = f + hh * 32;
+                        if (p.gn_cpg == 4) gn_stats_chunk<4>(fh, sums_b, fg, lane);
+                        else if (p.gn_cpg == 8) gn_stats_chunk<8>(fh, sums_b, fg, lane);
+                        else if (p.gn_cpg == 16) gn_stats_chunk<16>(fh, sums_b, fg, lane);
+                        else gn_stats_chunk<32>(fh, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): one group
+                    }
                 }
-                if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 2] = clock64();
+                __syncwarp();                                   // staging tile is reused by the next pass
+                if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 2] = clock64();
             }
-            if (p.trace && blockIdx.x == 0 && threadIdx.x == 128 && lt < 64) p.trace[2048 + lt * 4 + 2] = clock64();
+            if (tracing && lt < 64) p.trace[2048 + lt * 4 + 2] = clock64();
+            tile_m += step_m; rest += step_r;
+            if (tile_m >= p.m_tiles) { tile_m -= p.m_tiles; ++rest; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -423,28 +537,50 @@ static EncodeTiledFn get_encode() {
 
 struct TcPlan {
     int TW, TH, TN, BN, BK;
+    int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes;
 };
 
 // GH x GW = pixel grid of the GEMM (output grid for regular convs, input grid for the transposed gather)
-static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int in_stride, int classes, TcPlan& pl) {
-    if (GW > 128 || GW < 1 || (128 % GW) != 0) return false;
+static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int KH, int KW, int mode, int in_stride, int classes,
+                    TcPlan& pl) {
     if (Cin % 32 != 0 || Cout % 32 != 0) return false;
-    pl.TW = GW;
-    int th = 128 / GW;
-    if (th > GH) th = GH;
-    if (GH % th != 0) return false;
-    pl.TH = th;
-    pl.TN = 128 / (pl.TW * pl.TH);
+    pl.BK = (Cin % 64 == 0) ? 64 : 32;
+    // row-group mode: stride-1 KxK (K > 1) convs whose image splits into 16-row x 8-column tiles
+    pl.rg = (mode == 0 && in_stride == 1 && KH > 1 && KH <= 7 && GW % 8 == 0 && GH % 16 == 0) ? 1 : 0;
+    if (pl.rg) {
+        pl.TW = 8; pl.TH = 16; pl.TN = 1;
+    } else {
+        if (GW > 128 || GW < 1 || (128 % GW) != 0) return false;
+        pl.TW = GW;
+        int th = 128 / GW;
+        if (th > GH) th = GH;
+        if (GH % th != 0) return false;
+        pl.TH = th;
+        pl.TN = 128 / (pl.TW * pl.TH);
+    }
     if (pl.TW * pl.TH * pl.TN != 128) return false;
     if (pl.TW * in_stride > 256 || pl.TH * in_stride > 256) return false;      // TMA box limit
-    pl.BK = (Cin % 64 == 0) ? 64 : 32;
-    const long long m_tiles = (long long)((B + pl.TN - 1) / pl.TN) * (GH / pl.TH) * classes;
+    pl.nb = pl.rg ? KH : 1;
+    pl.a_bytes = (pl.TH + (pl.rg ? KH - 1 : 0)) * pl.TW * pl.TN * pl.BK * 2;
+    const long long K = (long long)KH * KW * Cin;
+    const long long m_tiles = (long long)((B + pl.TN - 1) / pl.TN) * (GH / pl.TH) * (GW / pl.TW) * classes;
     const int cands[4] = {256, 128, 64, 32};
+    static int force_bn = -1;                       // debugging aid: PIDM_TC_BN pins the n-tile width
+    if (force_bn < 0) { const char* ev = getenv("PIDM_TC_BN"); force_bn = ev ? atoi(ev) : 0; }
     pl.BN = 0;
     for (int i = 0; i < 4; ++i) {
-        int bn = cands[i];
+        const int bn = cands[i];
         if (Cout % bn != 0) continue;
-        pl.BN = bn;
+        if (force_bn > 0 && bn != force_bn && Cout % force_bn == 0) continue;
+        // weights resident in shared memory when the CTA only ever sees one n-tile and they leave room for the ring
+        const long long wbytes = (long long)bn * K * 2;
+        int resident = (mode == 0 && Cout == bn && wbytes <= 100 * 1024) ? 1 : 0;
+        int stage = pl.a_bytes + (resident ? 0 : pl.nb * bn * pl.BK * 2);
+        int stages = (int)((TC_OPERAND_BYTES - (resident ? wbytes : 0)) / stage);
+        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+        if (stages < 3) continue;
+        pl.BN = bn; pl.resident = resident; pl.res_bytes = resident ? (int)wbytes : 0;
+        pl.stage_bytes = stage; pl.stages = stages;
         if (m_tiles * (Cout / bn) >= 148) break;    // widest tile that still fills the machine
     }
     return pl.BN != 0;
@@ -452,14 +588,13 @@ static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int in_stride, int
 
 template <int BN, int BK>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, dim3 grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN, BK>;
     static bool attr = false;
     if (!attr) {
         PIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+                                       TC_SMEM_BYTES));
         attr = true;
     }
-    conv_tc_kernel<BN, BK><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+    conv_tc_kernel<BN, BK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mx, mw, p);
     PIDM_LAUNCH_CHECK("conv2d_tc");
     return 0;
 }
@@ -496,14 +631,16 @@ static bool tc_geometry(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, 
                 }
             }
     }
-    if (!tc_plan(B, p.GH, p.GW, Cin, Cout, p.in_stride, classes, pl)) return false;
-    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = p.GH / pl.TH;
+    if (!tc_plan(B, p.GH, p.GW, Cin, Cout, KH, KW, p.mode, p.in_stride, classes, pl)) return false;
+    p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = p.GH / pl.TH; p.tiles_w = p.GW / pl.TW;
+    p.rg = pl.rg; p.nb = pl.nb; p.a_bytes = pl.a_bytes; p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
+    p.resident = pl.resident; p.res_bytes = pl.res_bytes;
     return true;
 }
 
 static int tc_run(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
                   int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int transposed,
-                  float* gn_sums, int gn_groups, cudaStream_t st) {
+                  float* gn_sums, int gn_groups, int gn_sums_zeroed, cudaStream_t st) {
     TcParams p;
     TcPlan pl;
     int classes = 1;
@@ -526,7 +663,8 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
         // with elementStrides = s the box spans boxDim global elements and loads boxDim / s of them
-        cuuint32_t box[4] = {(cuuint32_t)pl.BK, (cuuint32_t)(pl.TW * s), (cuuint32_t)(pl.TH * s), (cuuint32_t)pl.TN};
+        const int box_h = pl.rg ? pl.TH + KH - 1 : pl.TH * s;
+        cuuint32_t box[4] = {(cuuint32_t)pl.BK, (cuuint32_t)(pl.TW * s), (cuuint32_t)box_h, (cuuint32_t)pl.TN};
         cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
         CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -552,9 +690,9 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         const int cpg = p.gn_cpg;
         PIDM_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16 || cpg % 32 == 0, "conv2d_tc: fused GroupNorm statistics need "
                      "4, 8, 16 or a multiple of 32 channels per group (got %d)", cpg);
-        PIDM_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)B * gn_groups * 2 * sizeof(float), st));
+        if (!gn_sums_zeroed) PIDM_CUDA(cudaMemsetAsync(gn_sums, 0, (size_t)B * gn_groups * 2 * sizeof(float), st));
     }
-    p.m_tiles = ((B + pl.TN - 1) / pl.TN) * p.tiles_h;
+    p.m_tiles = ((B + pl.TN - 1) / pl.TN) * p.tiles_h * p.tiles_w;
     p.n_tiles = Cout / pl.BN;
     p.n_classes = classes;
     static int sm_count = 0;
@@ -575,7 +713,7 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
 }  // namespace pidm
 using namespace pidm;
 
-// debugging aid: device buffer of >= 4096 int64 that receives a clock64 timeline of CTA 0 of every conv_tc launch
+// debugging aid: device buffer of >= 8192 int64 that receives a clock64 timeline of CTA 0 of every conv_tc launch
 extern "C" int pidm_debug_set_trace(void* buf) {
     g_tc_trace = (long long*)buf;
     return 0;
@@ -588,7 +726,7 @@ extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, 
 
 extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
                               int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
-    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, nullptr, 0,
+    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, nullptr, 0, 0,
                   (cudaStream_t)stream);
 }
 
@@ -600,7 +738,8 @@ extern "C" int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, in
 
 extern "C" int pidm_conv2d_tc_general(const void* x, const void* w_packed, const float* bias, const void* residual,
                                       void* y, int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
-                                      int stride, int pad, int transposed, float* gn_sums, int gn_groups, void* stream) {
+                                      int stride, int pad, int transposed, float* gn_sums, int gn_groups,
+                                      int gn_sums_zeroed, void* stream) {
     return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, transposed, gn_sums,
-                  gn_groups, (cudaStream_t)stream);
+                  gn_groups, gn_sums_zeroed, (cudaStream_t)stream);
 }

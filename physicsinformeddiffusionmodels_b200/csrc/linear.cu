@@ -81,73 +81,121 @@ struct MlpEntry {
     int n, pad_;
 };
 
-constexpr int MLP_BCHUNK = 32;
-// grid (entries, row-chunks of 64); warp per row, lanes over k; out[b, off+j] = b[j] + W[j,:] . s[b,:]
-__global__ void block_mlps_fwd_kernel(const MlpEntry* __restrict__ table, const float* __restrict__ s /*[B,td]*/,
-                                      int B, int td) {
+constexpr int MLP_BCHUNK = 32;      // samples per pass = lanes of a warp
+constexpr int MLP_ROWS = 32;        // output rows per CTA (fwd / wgrad)
+constexpr int MLP_DG_ROWS = 128;    // rows per CTA (dgrad)
+
+// out[b, j] = bias[j] + W[j,:] . s[b,:].  grid (entries, row chunks of MLP_ROWS), 256 threads.  A warp owns a row j,
+// its lanes are 32 samples: W[j,k] is one broadcast load per k, s[b,k] comes from a (td+1)-padded shared tile, and
+// no cross-lane reduction is needed.
+__global__ void __launch_bounds__(256) block_mlps_fwd_kernel(const MlpEntry* __restrict__ table,
+                                                             const float* __restrict__ s /*[B,td]*/, int B, int td) {
+    extern __shared__ float ss[];   // [MLP_BCHUNK][td + 1]
+    const MlpEntry e = table[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int r0 = blockIdx.y * MLP_ROWS;
+    if (r0 >= e.n) return;
+    const int r1 = min(r0 + MLP_ROWS, e.n);
+    const int ld = td + 1;
+    for (int b0 = 0; b0 < B; b0 += MLP_BCHUNK) {
+        const int nb = min(MLP_BCHUNK, B - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < MLP_BCHUNK * td; i += blockDim.x) {
+            const int b = i / td, k = i - b * td;
+            ss[b * ld + k] = b < nb ? s[(size_t)(b0 + b) * td + k] : 0.f;
+        }
+        __syncthreads();
+        const float* sl = ss + lane * ld;
+        for (int j = r0 + warp; j < r1; j += nw) {
+            const float4* wr = reinterpret_cast<const float4*>(e.W + (size_t)j * td);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int k4 = 0; k4 < td / 4; ++k4) {
+                const float4 w = __ldg(wr + k4);
+                a0 += w.x * sl[4 * k4]; a1 += w.y * sl[4 * k4 + 1]; a2 += w.z * sl[4 * k4 + 2]; a3 += w.w * sl[4 * k4 + 3];
+            }
+            if (lane < nb) e.out[(size_t)(b0 + lane) * e.n + j] = (a0 + a1) + (a2 + a3) + __ldg(e.b + j);
+        }
+    }
+}
+
+// dW[j,k] += sum_b d[b,j] s[b,k] ; db[j] += sum_b d[b,j]    (row j owned by exactly one warp; lane b holds d[b,j] and
+// broadcasts it by shuffle, lanes run over k for the s tile)
+__global__ void __launch_bounds__(256) block_mlps_wgrad_kernel(const MlpEntry* __restrict__ table,
+                                                               const float* __restrict__ s, int B, int td) {
     extern __shared__ float ss[];   // [MLP_BCHUNK][td]
     const MlpEntry e = table[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int r0 = blockIdx.y * 64;
+    const int r0 = blockIdx.y * MLP_ROWS;
     if (r0 >= e.n) return;
+    const int r1 = min(r0 + MLP_ROWS, e.n);
+    const int nk = td / 32;          // k values per lane (td % 32 == 0, td <= 768 -> <= 24)
     for (int b0 = 0; b0 < B; b0 += MLP_BCHUNK) {
-        int nb = min(MLP_BCHUNK, B - b0);
+        const int nb = min(MLP_BCHUNK, B - b0);
         __syncthreads();
-        for (int i = threadIdx.x; i < nb * td; i += blockDim.x) ss[i] = s[(size_t)b0 * td + i];
+        for (int i = threadIdx.x; i < MLP_BCHUNK * td; i += blockDim.x)
+            ss[i] = (i / td) < nb ? s[(size_t)b0 * td + i] : 0.f;
         __syncthreads();
-        for (int j = r0 + warp; j < min(r0 + 64, e.n); j += nw) {
-            const float* wr = e.W + (size_t)j * td;
-            float bj = e.b[j];
-            for (int b = 0; b < nb; ++b) {
-                float acc = 0.f;
-                for (int k = lane; k < td; k += 32) acc += wr[k] * ss[b * td + k];
-                acc = warp_sum(acc);
-                if (lane == 0) e.out[(size_t)(b0 + b) * e.n + j] = acc + bj;
-            }
-        }
-    }
-}
-
-// dW[j,k] += sum_b d[b, off+j] s[b,k] ; db[j] += sum_b d[b, off+j]    (row j owned by exactly one warp)
-__global__ void block_mlps_wgrad_kernel(const MlpEntry* __restrict__ table, const float* __restrict__ s, int B,
-                                        int td) {
-    extern __shared__ float ss[];
-    const MlpEntry e = table[blockIdx.x];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int r0 = blockIdx.y * 64;
-    if (r0 >= e.n) return;
-    for (int b0 = 0; b0 < B; b0 += MLP_BCHUNK) {
-        int nb = min(MLP_BCHUNK, B - b0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nb * td; i += blockDim.x) ss[i] = s[(size_t)b0 * td + i];
-        __syncthreads();
-        for (int j = r0 + warp; j < min(r0 + 64, e.n); j += nw) {
+        for (int j = r0 + warp; j < r1; j += nw) {
+            const float d = lane < nb ? e.dout[(size_t)(b0 + lane) * e.n + j] : 0.f;
             float* wr = e.dW + (size_t)j * td;
-            float dbj = 0.f;
-            for (int k = lane; k < td; k += 32) {
-                float acc = 0.f;
-                for (int b = 0; b < nb; ++b) acc += e.dout[(size_t)(b0 + b) * e.n + j] * ss[b * td + k];
-                wr[k] += acc;
+            for (int kk = 0; kk < nk; kk += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                const float* sk = ss + kk * 32 + lane;
+#pragma unroll 8
+                for (int b = 0; b < MLP_BCHUNK; ++b) {
+                    const float db_ = __shfl_sync(0xffffffffu, d, b);
+                    const float* sb = sk + b * td;
+                    a0 += db_ * sb[0];
+                    if (kk + 1 < nk) a1 += db_ * sb[32];
+                    if (kk + 2 < nk) a2 += db_ * sb[64];
+                    if (kk + 3 < nk) a3 += db_ * sb[96];
+                }
+                wr[kk * 32 + lane] += a0;
+                if (kk + 1 < nk) wr[(kk + 1) * 32 + lane] += a1;
+                if (kk + 2 < nk) wr[(kk + 2) * 32 + lane] += a2;
+                if (kk + 3 < nk) wr[(kk + 3) * 32 + lane] += a3;
             }
-            if (lane == 0) {
-                for (int b = 0; b < nb; ++b) dbj += e.dout[(size_t)(b0 + b) * e.n + j];
-                e.db[j] += dbj;
-            }
+            const float dsum = warp_sum(d);
+            if (lane == 0) e.db[j] += dsum;
         }
     }
 }
 
-// d_s[b,k] += sum_j dout_e[b, j] W_e[j,k]     grid (B, entries), block td; ds zeroed by the caller
-__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, float* __restrict__ ds, int td) {
-    extern __shared__ float sd[];   // [max_rows]
-    const int b = blockIdx.x, k = threadIdx.x;
-    const MlpEntry e = table[blockIdx.y];
-    for (int j = threadIdx.x; j < e.n; j += blockDim.x) sd[j] = e.dout[(size_t)b * e.n + j];
+// d_s[b,k] += sum_j dout_e[b,j] W_e[j,k].  grid (entries, row chunks of MLP_DG_ROWS, sample chunks of 32), block td:
+// thread k keeps 32 sample accumulators, W rows are read once per CTA (coalesced over k), dout comes from shared
+// memory as broadcast float4 reads; one atomicAdd per (sample, k) at the end.  ds zeroed by the caller.
+__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, float* __restrict__ ds, int B, int td) {
+    __shared__ __align__(16) float sd[MLP_DG_ROWS][MLP_BCHUNK];
+    const MlpEntry e = table[blockIdx.x];
+    const int r0 = blockIdx.y * MLP_DG_ROWS;
+    if (r0 >= e.n) return;
+    const int nr = min(MLP_DG_ROWS, e.n - r0);
+    const int b0 = blockIdx.z * MLP_BCHUNK;
+    const int nb = min(MLP_BCHUNK, B - b0);
+    for (int i = threadIdx.x; i < nr * MLP_BCHUNK; i += blockDim.x) {
+        const int b = i / nr, j = i - b * nr;          // consecutive threads walk j: coalesced reads of dout[b, r0 + j]
+        sd[j][b] = b < nb ? e.dout[(size_t)(b0 + b) * e.n + r0 + j] : 0.f;
+    }
     __syncthreads();
-    float acc = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < e.n; ++j) acc += sd[j] * e.W[(size_t)j * td + k];
-    atomicAdd(&ds[(size_t)b * td + k], acc);
+    const int k = threadIdx.x;
+    float acc[MLP_BCHUNK];
+#pragma unroll
+    for (int b = 0; b < MLP_BCHUNK; ++b) acc[b] = 0.f;
+    const float* wp = e.W + (size_t)r0 * td + k;
+#pragma unroll 2
+    for (int j = 0; j < nr; ++j) {
+        const float w = __ldg(wp + (size_t)j * td);
+        const float4* dj = reinterpret_cast<const float4*>(sd[j]);
+#pragma unroll
+        for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
+            const float4 d = dj[q];
+            acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < MLP_BCHUNK; ++b)
+        if (b < nb) atomicAdd(&ds[(size_t)(b0 + b) * td + k], acc[b]);
 }
 
 }  // namespace pidm
@@ -187,10 +235,10 @@ static int mlp_smem_attr(size_t bytes) {
 
 extern "C" int pidm_block_mlps_fwd(const void* table_dev, int n_entries, int max_rows, const float* silu_t, int B,
                                    int td, void* stream) {
-    PIDM_REQUIRE(td <= 768, "block_mlps: td <= 768 required");
-    size_t smem = (size_t)MLP_BCHUNK * td * sizeof(float);
+    PIDM_REQUIRE(td <= 704 && td % 32 == 0, "block_mlps: td must be a multiple of 32, <= 704");
+    size_t smem = (size_t)MLP_BCHUNK * (td + 1) * sizeof(float);
     if (int e = mlp_smem_attr(smem)) return e;
-    dim3 grid(n_entries, ceil_div(max_rows, 64));
+    dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
     block_mlps_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const MlpEntry*)table_dev, silu_t, B, td);
     PIDM_LAUNCH_CHECK("block_mlps_fwd");
     return 0;
@@ -199,14 +247,15 @@ extern "C" int pidm_block_mlps_fwd(const void* table_dev, int n_entries, int max
 // weight/bias grads accumulate into the table's dW/db pointers; d_silu_t is overwritten.
 extern "C" int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max_rows, const float* silu_t,
                                    float* d_silu_t, int B, int td, void* stream) {
-    PIDM_REQUIRE(td <= 768, "block_mlps: td <= 768 required");
+    PIDM_REQUIRE(td <= 704 && td % 32 == 0, "block_mlps: td must be a multiple of 32, <= 704");
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = (size_t)MLP_BCHUNK * td * sizeof(float);
+    size_t smem = (size_t)MLP_BCHUNK * (td + 1) * sizeof(float);
     if (int e = mlp_smem_attr(smem)) return e;
-    dim3 grid(n_entries, ceil_div(max_rows, 64));
+    dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
     block_mlps_wgrad_kernel<<<grid, 256, smem, st>>>((const MlpEntry*)table_dev, silu_t, B, td);
     PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
-    block_mlps_dgrad_kernel<<<dim3(B, n_entries), td, max_rows * sizeof(float), st>>>((const MlpEntry*)table_dev, d_silu_t, td);
+    dim3 dgrid(n_entries, ceil_div(max_rows, MLP_DG_ROWS), ceil_div(B, MLP_BCHUNK));
+    block_mlps_dgrad_kernel<<<dgrid, td, 0, st>>>((const MlpEntry*)table_dev, d_silu_t, B, td);
     PIDM_LAUNCH_CHECK("block_mlps_bwd");
     return 0;
 }

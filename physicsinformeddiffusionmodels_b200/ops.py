@@ -117,7 +117,34 @@ def concat(a, b):
 # ----------------------------------------------------------------------------------------------
 # convolution (implicit GEMM).  `spec` is a ConvSpec created by the owning module (packing.py).
 # ----------------------------------------------------------------------------------------------
-def _conv_launch(x, wp, bias, residual, y, g, transposed, gn_sums=None, gn_groups=0):
+# Pool of pre-zeroed fp32 scratch (fused GroupNorm statistics): one fill per network forward instead of one memset
+# node per convolution.  Slices stay alive through the tensors that view them (saved for backward).
+_ZERO_POOL = {'buf': None, 'cur': 0}
+
+
+def zero_pool_begin(nfloats, device):
+    _ZERO_POOL['buf'] = torch.zeros(int(nfloats), device=device, dtype=torch.float32)
+    _ZERO_POOL['cur'] = 0
+
+
+def zero_pool_end():
+    _ZERO_POOL['buf'] = None
+
+
+def _zero_take(*shape):
+    buf = _ZERO_POOL['buf']
+    n = 1
+    for d in shape:
+        n *= int(d)
+    n_al = (n + 31) // 32 * 32                     # keep slices 128-byte aligned
+    if buf is None or _ZERO_POOL['cur'] + n_al > buf.numel():
+        return None
+    out = buf[_ZERO_POOL['cur']:_ZERO_POOL['cur'] + n].view(*shape)
+    _ZERO_POOL['cur'] += n_al
+    return out
+
+
+def _conv_launch(x, wp, bias, residual, y, g, transposed, gn_sums=None, gn_groups=0, gn_zeroed=False):
     """g = (B,H,W,Cin,Ho,Wo,Cout,KH,KW,stride,pad).  Returns True if the fused GroupNorm statistics were produced."""
     B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = g
     tr = 1 if transposed else 0
@@ -126,7 +153,7 @@ def _conv_launch(x, wp, bias, residual, y, g, transposed, gn_sums=None, gn_group
         cpg = Cout // gn_groups if gn_groups else 0
         fuse = gn_sums is not None and (cpg in (4, 8, 16) or (cpg > 0 and cpg % 32 == 0))
         call('pidm_conv2d_tc_general', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, tr,
-             gn_sums if fuse else None, gn_groups if fuse else 0, stream())
+             gn_sums if fuse else None, gn_groups if fuse else 0, 1 if gn_zeroed else 0, stream())
         return fuse
     else:
         call('pidm_conv2d_simt', x, wp, bias, residual, y, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad,
@@ -144,10 +171,14 @@ class _Conv2d(torch.autograd.Function):
         Ho, Wo = spec.out_hw(H, W)
         y = torch.empty(B, Ho, Wo, spec.cout, device=x.device, dtype=x.dtype)
         g = (B, H, W, Cin, Ho, Wo, spec.cout, spec.kh, spec.kw, spec.stride, spec.pad)
-        sums = None
+        sums, zeroed = None, False
         if link is not None:
-            sums = torch.empty(B, link['groups'], 2, device=x.device, dtype=torch.float32)
-        fused = _conv_launch(x, spec.wp_fwd, bias, residual, y, g, spec.transposed, sums, link['groups'] if link else 0)
+            sums = _zero_take(B, link['groups'], 2)
+            zeroed = sums is not None
+            if sums is None:
+                sums = torch.empty(B, link['groups'], 2, device=x.device, dtype=torch.float32)
+        fused = _conv_launch(x, spec.wp_fwd, bias, residual, y, g, spec.transposed, sums, link['groups'] if link else 0,
+                             zeroed)
         if link is not None:
             link['sums'] = sums if fused else None
             link['bias'] = bias

@@ -313,6 +313,8 @@ class Unet3D(nn.Module):
             raise RuntimeError('Unet3D (B200 engine) needs CUDA tensors: no CPU fallback on the product path')
         dt = ops.act_dtype()
         self._packer.refresh(dt)
+        # pre-zeroed scratch for the GroupNorm statistics that the conv epilogues accumulate (<= 64 norms)
+        ops.zero_pool_begin(64 * (x.shape[0] * self.groups * 2 + 32), x.device)
         h = ops.nchw_to_nhwc(x.float(), self._cin_pad, dt)
         h = self._conv(self.init_conv, h)
         r = h
@@ -343,4 +345,5 @@ class Unet3D(nn.Module):
         h = self._resblock(self.final_conv[0], h, None)
         fc = self.final_conv[1]
         y = ops.head(h, fc.weight, fc.bias, self.sigmoid_last_channel)
+        ops.zero_pool_end()
         return y.unsqueeze(2) if video else y

@@ -10,23 +10,30 @@ w = torch.nn.Parameter(torch.randn(Cout, Cin, 1, k, k, device=dev) / math.sqrt(C
 b = torch.nn.Parameter(torch.zeros(Cout, device=dev))
 spec = packing.ConvSpec(w, 'conv', k, k, 1, k // 2)
 pk = packing.WeightPacker(); pk.add(spec); pk.refresh(torch.bfloat16)
-trace = torch.zeros(4096, dtype=torch.int64, device=dev)
+trace = torch.zeros(8192, dtype=torch.int64, device=dev)
+def graph_us(fn):
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(20):
+                fn()
+        g.replay(); side.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(5):
+            g.replay()
+        e1.record(side); side.synchronize()
+    return e0.elapsed_time(e1) * 1000 / 100
 with torch.no_grad():
-    for _ in range(3):
-        ops.conv2d(x, w, b, spec)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        ops.conv2d(x, w, b, spec)
-    e1.record(); torch.cuda.synchronize()
-    print('avg us per launch (no stats):', e0.elapsed_time(e1) * 1000 / 20)
-    link = {'groups': 8}
-    e0.record()
-    for _ in range(20):
-        ops.conv2d(x, w, b, spec, gn_link={'groups': 8})
-    e1.record(); torch.cuda.synchronize()
-    print('avg us per launch (gn stats):', e0.elapsed_time(e1) * 1000 / 20)
+    print(f'conv B={B} {H}x{H} {Cin}->{Cout} k={k}: us per launch (graph): no stats',
+          round(graph_us(lambda: ops.conv2d(x, w, b, spec)), 2), ' gn stats',
+          round(graph_us(lambda: ops.conv2d(x, w, b, spec, gn_link={'groups': 8})), 2))
+    if len(sys.argv) > 6:
+        sys.exit(0)
     call('pidm_debug_set_trace', trace)
     ops.conv2d(x, w, b, spec, gn_link={'groups': 8})
     torch.cuda.synchronize()
@@ -46,3 +53,7 @@ for lt in range(9):
     a = t[2048 + lt * 4 + 1]; row = t[3072 + lt * 4: 3072 + lt * 4 + 3]
     if row[0]: print(lt, [row[0] - a, row[1] - row[0], row[2] - row[1]])
 print('producer tile starts:', [t[i * 2] - t0 for i in range(9) if t[i * 2]])
+print('MMA K-steps: [full-wait done, issued] relative; producer issue time')
+for git in range(40):
+    a, b2, c = t[4096 + git * 2], t[4096 + git * 2 + 1], t[6144 + git]
+    if a: print(git, a - t0, b2 - t0, 'producer', (c - t0) if c else None)
