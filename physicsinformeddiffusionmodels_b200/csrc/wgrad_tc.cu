@@ -132,63 +132,69 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     if (n_iters > 0) {
         if (warp == 0) {
             if (wg_elect_one()) {
-                for (int it = 0; it < n_iters; ++it) {
-                    const int s = it % Cfg::STAGES;
-                    const uint32_t ph = (it / Cfg::STAGES) & 1;
-                    wg_mbar_wait(&empty[s], ph ^ 1);
-                    const int pt = pt_begin + it;
-                    const int tb = pt / p.tiles_h, th_idx = pt - tb * p.tiles_h;
-                    const int b0 = tb * p.TN, h0 = th_idx * p.TH;
-                    unsigned char* a_dst = ring + s * Cfg::STAGE_BYTES;
-                    unsigned char* b_dst = a_dst + Cfg::NA * Cfg::A_TILE;
-                    wg_mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                // per-box coordinates of this M' tile are loop invariant: resolve (tap, chunk) -> (c0, dw, dh) once
+                int ac[Cfg::NA], aw[Cfg::NA], ah[Cfg::NA];
 #pragma unroll
-                    for (int j = 0; j < Cfg::NA; ++j) {
-                        int pr = mt * Cfg::NA + j;
-                        if (pr >= n_pairs) pr = n_pairs - 1;      // padding rows of the last M' tile (discarded later)
-                        const int tap = pr / chunks, ch = pr - tap * chunks;
-                        const int r = tap / p.KW, q = tap - r * p.KW;
-                        wg_tma_4d(a_dst + j * Cfg::A_TILE, &map_x, &full[s], ch * ATOM_A, q - p.pad, p.a_stride * h0 + r - p.pad, b0);
-                    }
+                for (int j = 0; j < Cfg::NA; ++j) {
+                    int pr = mt * Cfg::NA + j;
+                    if (pr >= n_pairs) pr = n_pairs - 1;          // padding rows of the last M' tile (discarded later)
+                    const int tap = pr / chunks, ch = pr - tap * chunks;
+                    const int r = tap / p.KW, q = tap - r * p.KW;
+                    ac[j] = ch * ATOM_A; aw[j] = q - p.pad; ah[j] = r - p.pad;
+                }
+                int tb = pt_begin / p.tiles_h, th_idx = pt_begin - tb * p.tiles_h;
+                uint32_t st = 0, ph = 0;
+                unsigned char* a_dst = ring;
+                for (int it = 0; it < n_iters; ++it) {
+                    wg_mbar_wait(&empty[st], ph ^ 1);
+                    const int b0 = tb * p.TN, h0 = th_idx * p.TH;
+                    unsigned char* b_dst = a_dst + Cfg::NA * Cfg::A_TILE;
+                    wg_mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < Cfg::NA; ++j)
+                        wg_tma_4d(a_dst + j * Cfg::A_TILE, &map_x, &full[st], ac[j], aw[j], p.a_stride * h0 + ah[j], b0);
 #pragma unroll
                     for (int j = 0; j < Cfg::NB; ++j)
-                        wg_tma_4d(b_dst + j * Cfg::B_TILE, &map_dy, &full[s], n0 + j * ATOM_B, 0, h0, b0);
+                        wg_tma_4d(b_dst + j * Cfg::B_TILE, &map_dy, &full[st], n0 + j * ATOM_B, 0, h0, b0);
+                    if (++th_idx == p.tiles_h) { th_idx = 0; ++tb; }
+                    if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1; a_dst = ring; } else a_dst += Cfg::STAGE_BYTES;
                 }
             }
         } else if (warp == 1) {
             // D = f32, A = B = bf16, both MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int it = 0; it < n_iters; ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (it / Cfg::STAGES) & 1;
-                wg_mbar_wait(&full[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (wg_elect_one()) {
-                    const uint32_t a_addr = wg_smem_u32(ring + s * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::NA * Cfg::A_TILE;
+            if (wg_elect_one()) {          // one thread runs the whole issue loop; descriptors advance by adds only
+                const uint64_t da0 = umma_desc_mn<ATOM_A * 2>(wg_smem_u32(ring), Cfg::A_TILE);
+                const uint64_t db0 = umma_desc_mn<ATOM_B * 2>(wg_smem_u32(ring) + Cfg::NA * Cfg::A_TILE, Cfg::B_TILE);
+                constexpr uint32_t stage_lo = Cfg::STAGE_BYTES >> 4;
+                constexpr uint32_t ka_lo = (16 * ATOM_A * 2) >> 4, kb_lo = (16 * ATOM_B * 2) >> 4;
+                uint32_t st = 0, ph = 0, off_lo = 0, accum = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    wg_mbar_wait(&full[st], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {      // 8 x 16 pixels
-                        const uint64_t da = umma_desc_mn<ATOM_A * 2>(a_addr + k * 16 * ATOM_A * 2, Cfg::A_TILE);
-                        const uint64_t db = umma_desc_mn<ATOM_B * 2>(b_addr + k * 16 * ATOM_B * 2, Cfg::B_TILE);
-                        const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+                        const uint64_t da = da0 + (uint64_t)(off_lo + k * ka_lo);
+                        const uint64_t db = db0 + (uint64_t)(off_lo + k * kb_lo);
                         asm volatile(
                             "{\n\t.reg .pred p;\n\t"
                             "setp.ne.b32 p, %4, 0;\n\t"
                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
                             "l"(da), "l"(db), "r"(idesc), "r"(accum)
                             : "memory");
+                        accum = 1;
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     wg_smem_u32(&empty[s]))
+                                     wg_smem_u32(&empty[st]))
                                  : "memory");
-                    if (it == n_iters - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                         wg_smem_u32(acc_full))
-                                     : "memory");
+                    if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1; off_lo = 0; } else off_lo += stage_lo;
                 }
-                __syncwarp();
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 wg_smem_u32(acc_full))
+                             : "memory");
             }
+            __syncwarp();
         } else if (warp >= 4) {
             const int quarter = warp & 3;
             const int mrow = quarter * 32 + lane;             // accumulator row = (pair j, channel within atom)
@@ -352,7 +358,9 @@ extern "C" int pidm_conv2d_wgrad_tc(const void* a, const void* b, float* dw, int
     const int n_pairs = KH * KW * (CA / pl.AA);
     const int m_tiles = (n_pairs + na - 1) / na;
     const int n_tiles = CB / pl.NP;
-    int splits = (148 * 2 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+    // split the pixel range so that the grid is one wave of the 148 SMs (one CTA per SM: the ring takes the shared
+    // memory); fewer, longer CTAs also mean fewer red.global.add of partial tiles
+    int splits = 148 / (m_tiles * n_tiles);
     if (splits > p.n_pix_tiles) splits = p.n_pix_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_split = (p.n_pix_tiles + splits - 1) / splits;
