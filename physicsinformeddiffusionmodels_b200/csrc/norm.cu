@@ -7,6 +7,7 @@
 // element-wise dx kernel.  Nothing but the conv output x and the raw sums is saved for backward.
 #include "common.cuh"
 #include "pidm.h"
+#include <cooperative_groups.h>
 
 namespace pidm {
 
@@ -214,6 +215,137 @@ __global__ void gn_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ 
     }
 }
 
+// Single-pass backward for tensors whose per-sample (x, dy) pair fits the shared memory of one thread-block cluster:
+// one cluster of CL CTAs per sample.  Every CTA copies its slice of x and dy into shared memory once (cp.async, all
+// loads in flight together), reduces (dz, dz*xhat) per channel over its rows, the CL partial vectors are combined
+// through distributed shared memory, and dx is computed from the resident slice: x and dy are read from HBM exactly
+// once and no workspace / memset / second launch is needed.  Arithmetic order per element is the same as in the
+// two-kernel path (gn_bwd_reduce_kernel + gn_bwd_dx_kernel).
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS) gn_bwd_cluster_kernel(
+        const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums, const float* __restrict__ gamma,
+        const float* __restrict__ beta, const float* __restrict__ ss, T* __restrict__ dx, float* __restrict__ dss,
+        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int HW, int C, int G, float eps,
+        int rows_per_cta) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    extern __shared__ __align__(16) unsigned char gsm[];
+    float* part = reinterpret_cast<float*>(gsm);           // [C][2] partial sums of this CTA
+    float* Sf = part + 2 * C;                              // [C][2] sums over the whole sample
+    float* gm = Sf + 2 * C;                                // [G][2]
+    float* cs = gm + 2 * G;                                // [C] column sums of dx
+    T* xs = reinterpret_cast<T*>(cs + C);                  // [rows][C]
+    T* ds = xs + (size_t)rows_per_cta * C;
+    const int oct = C / 8, cpg = C / G;
+    const int b = blockIdx.x / CL;
+    const int o = threadIdx.x % oct, r0 = threadIdx.x / oct;
+    const int rows_per_pass = blockDim.x / oct;
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    const int row_begin = rank * rows_per_cta;
+    const int rows = min(rows_per_cta, HW - row_begin);
+    const size_t base = ((size_t)b * HW + row_begin) * C;
+    {   // bulk copy of the slice: 16-byte cp.async, everything in flight at once
+        const int vec = 16 / (int)sizeof(T);
+        const int n16 = rows * C / vec;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+            const uint32_t dxs = (uint32_t)__cvta_generic_to_shared(xs + (size_t)i * vec);
+            const uint32_t dds = (uint32_t)__cvta_generic_to_shared(ds + (size_t)i * vec);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dxs), "l"(x + base + (size_t)i * vec) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dds), "l"(dy + base + (size_t)i * vec) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) part[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * G + C; i += blockDim.x) gm[i] = 0.f;       // gm and cs are adjacent
+    float mean[2], rstd[2], gmv[8], bt[8], s1p[8], sh[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) gn_mean_rstd(sums, b, (o * 8 + h * 4) / cpg, G, inv_n, eps, mean[h], rstd[h]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = o * 8 + k;
+        gmv[k] = gamma[c]; bt[k] = beta[c];
+        s1p[k] = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        sh[k] = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float a1[8], a2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+    for (int p = r0; p < rows; p += rows_per_pass) {
+        float v[8], d[8];
+        ld8(xs + (size_t)p * C + o * 8, v);
+        ld8(ds + (size_t)p * C + o * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xh = (v[k] - mean[k >> 2]) * rstd[k >> 2];
+            float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
+            float dz = d[k] * silu_grad_f(z);
+            a1[k] += dz; a2[k] += dz * xh;
+        }
+    }
+    const bool pub1 = reduce_same_octet(a1, oct);
+    reduce_same_octet(a2, oct);
+    if (pub1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { atomicAdd(&part[(o * 8 + k) * 2], a1[k]); atomicAdd(&part[(o * 8 + k) * 2 + 1], a2[k]); }
+    }
+    cluster.sync();                                        // all partial vectors of the sample are complete
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < CL; ++r) t += cluster.map_shared_rank(part, r)[i];
+        Sf[i] = t;
+    }
+    cluster.sync();                                        // nobody reads a peer's `part` after this point
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float s1 = Sf[c * 2], s2 = Sf[c * 2 + 1];
+        const float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        atomicAdd(&gm[(c / cpg) * 2], gamma[c] * f * s1);
+        atomicAdd(&gm[(c / cpg) * 2 + 1], gamma[c] * f * s2);
+        if (rank == 0) {
+            if (dss) {
+                dss[(size_t)b * 2 * C + c] = gamma[c] * s2 + beta[c] * s1;   // d scale
+                dss[(size_t)b * 2 * C + C + c] = s1;                          // d shift
+            }
+            atomicAdd(&dgamma[c], f * s2);
+            atomicAdd(&dbeta[c], f * s1);
+        }
+    }
+    __syncthreads();
+    float m1[2], m2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int g = (o * 8 + h * 4) / cpg;
+        m1[h] = gm[g * 2] * inv_n;
+        m2[h] = gm[g * 2 + 1] * inv_n;
+    }
+    float colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = r0; p < rows; p += rows_per_pass) {
+        float v[8], d[8];
+        ld8(xs + (size_t)p * C + o * 8, v);
+        ld8(ds + (size_t)p * C + o * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xh = (v[k] - mean[k >> 2]) * rstd[k >> 2];
+            float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
+            float dz = d[k] * silu_grad_f(z);
+            float g = rstd[k >> 2] * (gmv[k] * s1p[k] * dz - m1[k >> 2] - xh * m2[k >> 2]);
+            v[k] = g;
+            colsum[k] += g;
+        }
+        st8(dx + base + (size_t)p * C + o * 8, v);
+    }
+    if (dbias) {
+        if (reduce_same_octet(colsum, oct)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&cs[o * 8 + k], colsum[k]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], cs[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // channel LayerNorm: y[m,c] = (x[m,c]-mean_m)/sqrt(var_m+eps)*gamma[c]
 // a group of L = min(32, C/8) lanes owns one pixel; lane handles octets lane, lane+L, ...
@@ -374,10 +506,47 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
                                        int B, int HW, int C, int G, float eps, int dtype, void* stream) {
     if (int e = gn_check(C, G)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    float* S = workspace;
-    PIDM_CUDA(cudaMemsetAsync(S, 0, (size_t)B * C * 2 * sizeof(float), st));
     int block, chunks;
     gn_launch_dims(HW, C, block, chunks);
+    {   // single-pass cluster kernel when a sample's (x, dy) fits the shared memory of <= 8 CTAs
+        const size_t esz = dtype == PIDM_BF16 ? 2 : 4;
+        const size_t fixed = (size_t)(4 * C + 2 * G + C) * sizeof(float);
+        const int rows_gran = block / (C / 8);
+        int cl = 0, rows_per_cta = 0;
+        for (int c = 1; c <= 8; c *= 2) {
+            int r = (HW + c - 1) / c;
+            r = (r + rows_gran - 1) / rows_gran * rows_gran;
+            if ((size_t)r * C * esz * 2 + fixed <= 100 * 1024 && (size_t)r * (c - 1) < (size_t)HW) { cl = c; rows_per_cta = r; break; }
+            if (c == 1 && (size_t)r * C * esz * 2 + fixed <= 100 * 1024) { cl = 1; rows_per_cta = r; break; }
+        }
+        if (cl > 0 && (long long)B * cl >= 32 && (C * esz) % 16 == 0) {
+            const size_t smem = (size_t)rows_per_cta * C * esz * 2 + fixed;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(B * cl));
+            cfg.blockDim = dim3((unsigned)block);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            static bool attr_done[2] = {false, false};
+            PIDM_DISPATCH_DTYPE(dtype, {
+                const int di = dtype == PIDM_BF16 ? 1 : 0;
+                if (!attr_done[di]) {
+                    PIDM_CUDA(cudaFuncSetAttribute(gn_bwd_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    attr_done[di] = true;
+                }
+                PIDM_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel<T>, (const T*)x, (const T*)dy, sums, gamma, beta,
+                                             scale_shift, (T*)dx, d_scale_shift, dgamma, dbeta, dbias_of_producer, HW, C, G,
+                                             eps, rows_per_cta));
+            });
+            PIDM_LAUNCH_CHECK("groupnorm_silu_bwd(cluster)");
+            return 0;
+        }
+    }
+    float* S = workspace;
+    PIDM_CUDA(cudaMemsetAsync(S, 0, (size_t)B * C * 2 * sizeof(float), st));
     PIDM_DISPATCH_DTYPE(dtype, {
         gn_bwd_reduce_kernel<T><<<dim3(chunks, B), block, 2 * C * sizeof(float), st>>>(
             (const T*)x, (const T*)dy, sums, gamma, beta, scale_shift, S, HW, C, G, eps);
