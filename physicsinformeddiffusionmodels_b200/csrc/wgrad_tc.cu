@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "pidm.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace pidm {
 
@@ -324,6 +325,12 @@ static int wg_launch(const CUtensorMap& mx, const CUtensorMap& my, const WgParam
     return 0;
 }
 
+// tap-complete 3x3 kernel (wgrad_tc3.cu)
+bool wgrad3_supported(int B, int HA, int WA, int CA, int CA_real, int GH, int GW, int CB, int KH, int KW, int a_stride,
+                      int pad, long long s_row);
+int wgrad3_run(const void* a, const void* b, float* dw, int B, int HA, int WA, int CA, int GH, int GW, int CB,
+               long long s_col, cudaStream_t st);
+
 }  // namespace pidm
 using namespace pidm;
 
@@ -338,6 +345,10 @@ extern "C" int pidm_conv2d_wgrad_tc_supported(int B, int GH, int GW, int CA, int
 extern "C" int pidm_conv2d_wgrad_tc(const void* a, const void* b, float* dw, int B, int HA, int WA, int CA, int CA_real,
                                     int GH, int GW, int CB, int KH, int KW, int a_stride, int pad, long long s_row,
                                     long long s_col, void* stream) {
+    static int use3 = -1;                       // PIDM_WGRAD3=0 falls back to the generic kernel (A/B testing)
+    if (use3 < 0) { const char* ev = getenv("PIDM_WGRAD3"); use3 = (ev && ev[0] == '0') ? 0 : 1; }
+    if (use3 && wgrad3_supported(B, HA, WA, CA, CA_real, GH, GW, CB, KH, KW, a_stride, pad, s_row))
+        return wgrad3_run(a, b, dw, B, HA, WA, CA, GH, GW, CB, s_col, (cudaStream_t)stream);
     WgPlan pl;
     PIDM_REQUIRE(KH == KW && wg_plan(B, GH, GW, CA, CB, a_stride, pl), "conv2d_wgrad_tc: unsupported geometry");
     static thread_local bool ctx_bound = false;
