@@ -133,6 +133,17 @@ int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* gamma, void
 /* ---- attention ------------------------------------------------------------------------------------------ */
 /* SpatialLinearAttention core between to_qkv and to_out (src/unet_model.py:286-297), dim_head = 32.
  * qkv [B,N,3*heads*32]; out [B,N,heads*32]; ctx [B,heads,32,32], kmax/kzinv [B,heads,32] kept for backward. */
+/* Linear attention fused with its to_qkv 1x1 projection (C = 32 input channels, 8 heads, bf16): q, k, v are recomputed
+ * per head on the tensor cores from xn = PreNorm(x) instead of being materialised (reference unet_model.py:275-297 --
+ * `qkv = self.to_qkv(x)` and everything after it).  w_qkv = packed to_qkv weights [768][32] bf16 (pidm_pack_weights).
+ * Forward keeps ctx / kmax / kzinv for backward; backward returns dqkv [B,N,768] (gradient w.r.t. xn W^T) for the
+ * ordinary dgrad / wgrad of to_qkv.  dctx is scratch. */
+int pidm_linattn_fused_supported(int C, int heads, int N, int dtype);
+int pidm_linattn_fused_workspace_floats(int B, int N);
+int pidm_linattn_fused_fwd(const void* xn, const void* w_qkv, void* out, float* ctx, float* kmax, float* kzinv,
+                           float* workspace, int B, int N, void* stream);
+int pidm_linattn_fused_bwd(const void* xn, const void* w_qkv, const void* dout, const float* ctx, const float* kmax,
+                           const float* kzinv, void* dqkv, float* dctx, int B, int N, void* stream);
 int pidm_linattn_workspace_floats(int B, int N, int heads);
 int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* kmax, float* kzinv, float* workspace, int B, int N,
                      int heads, int dtype, void* stream);

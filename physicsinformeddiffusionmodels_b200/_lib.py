@@ -48,6 +48,10 @@ _SIGS = {
     'pidm_layernorm_c_fwd': [P, P, P, L, I, F, I, P],
     'pidm_layernorm_c_bwd': [P, P, P, P, P, L, I, F, I, P],
     'pidm_linattn_workspace_floats': [I, I, I],
+    'pidm_linattn_fused_supported': [I, I, I, I],
+    'pidm_linattn_fused_workspace_floats': [I, I],
+    'pidm_linattn_fused_fwd': [P, P, P, P, P, P, P, I, I, P],
+    'pidm_linattn_fused_bwd': [P, P, P, P, P, P, P, P, I, I, P],
     'pidm_linattn_fwd': [P, P, P, P, P, P, I, I, I, I, P],
     'pidm_linattn_bwd': [P, P, P, P, P, P, P, I, I, I, I, P],
     'pidm_attn_fwd': [P, P, I, I, I, I, P],
@@ -69,6 +73,7 @@ _SIGS = {
 }
 # functions whose int return value is a result, not an error code
 _VALUE_RETURN = {'pidm_pack_entry_size', 'pidm_mlp_entry_size', 'pidm_linattn_workspace_floats', 'pidm_version',
+                 'pidm_linattn_fused_supported', 'pidm_linattn_fused_workspace_floats',
                  'pidm_conv2d_tc_supported', 'pidm_conv2d_wgrad_tc_supported', 'pidm_conv2d_tc_general_supported'}
 
 if not os.path.exists(LIB_PATH):

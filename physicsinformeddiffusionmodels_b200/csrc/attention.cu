@@ -20,23 +20,55 @@ constexpr int DH = 32;            // dim_head
 constexpr int LA_TN = 64;         // pixel tile of the context kernels
 
 // ---- pass 1: per-chunk column statistics of k -----------------------------------------------------------
+// part[b][chunk][c] = (max_n k[n,c], sum_n exp(k[n,c] - max)) over the rows of the chunk.  Thread = (row group,
+// channel octet): 16-byte loads, a max pass and an exp-sum pass (the chunk stays in L1/L2 between them) instead of
+// the serial online-softmax recurrence per row; the row groups are combined through shared memory.
 template <typename T>
 __global__ void la_kstats_kernel(const T* __restrict__ qkv, float* __restrict__ part /*[B][chunks][HID][2]*/, int N,
                                  int HID, int rows_per_chunk) {
-    const int b = blockIdx.y, chunk = blockIdx.x, c = threadIdx.x;
+    extern __shared__ float skm[];                 // [groups][HID] max, then [groups][HID] sums
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int oct = HID / 8;
+    const int o = threadIdx.x % oct, rg = threadIdx.x / oct, groups = blockDim.x / oct;
     const int n0 = chunk * rows_per_chunk;
     int n1 = n0 + rows_per_chunk;
     if (n1 > N) n1 = N;
-    float m = -INFINITY, s = 0.f;
-    const T* base = qkv + ((size_t)b * N) * 3 * HID + HID + c;
-    for (int n = n0; n < n1; ++n) {
-        float v = Act<T>::ld(base + (size_t)n * 3 * HID);
-        float mn = fmaxf(m, v);
-        s = s * __expf(m - mn) + __expf(v - mn);
-        m = mn;
+    const T* base = qkv + ((size_t)b * N) * 3 * HID + HID + o * 8;
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+    for (int n = n0 + rg; n < n1; n += groups) {
+        float v[8];
+        ld8(base + (size_t)n * 3 * HID, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
     }
-    float* o = part + (((size_t)b * gridDim.x + chunk) * HID + c) * 2;
-    o[0] = m; o[1] = s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) skm[rg * HID + o * 8 + k] = m[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float mm = -INFINITY;
+        for (int g = 0; g < groups; ++g) mm = fmaxf(mm, skm[g * HID + o * 8 + k]);
+        m[k] = mm;
+    }
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int n = n0 + rg; n < n1; n += groups) {
+        float v[8];
+        ld8(base + (size_t)n * 3 * HID, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += __expf(v[k] - m[k]);
+    }
+    float* ssum = skm + groups * HID;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ssum[rg * HID + o * 8 + k] = s[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < HID; c += blockDim.x) {
+        float mm = -INFINITY, t = 0.f;
+        for (int g = 0; g < groups; ++g) { mm = fmaxf(mm, skm[g * HID + c]); t += ssum[g * HID + c]; }
+        float* op = part + (((size_t)b * gridDim.x + chunk) * HID + c) * 2;
+        op[0] = mm; op[1] = t;
+    }
 }
 
 // ---- pass 2: context accumulation.  MODE 0: w = exp(k - M) (ctx, scaled by 1/(Z*N) at the end);
@@ -392,6 +424,15 @@ int la_mma_out(const void* qkv, const float* ctx, void* out, int B, int N, float
 int la_mma_bwd(const void* qkv, const void* dout, const float* ctx, const float* dctx, const float* kmax,
                const float* kzinv, void* dqkv, int B, int N, float scale, cudaStream_t st);
 
+// block = whole row groups of HID/8 threads, about 256 threads
+static int la_kstats_block(int HID) {
+    const int oct = HID / 8;
+    int groups = 256 / oct;
+    if (groups < 1) groups = 1;
+    return groups * oct;
+}
+static size_t la_kstats_smem(int HID) { return (size_t)2 * (la_kstats_block(HID) / (HID / 8)) * HID * sizeof(float); }
+
 static int la_chunks(int N) {
     int c = N / 128;
     if (c < 1) c = 1;
@@ -413,7 +454,7 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const float scale = 0.17677669529663687f;   // 32^-0.5
     PIDM_CUDA(cudaMemsetAsync(ctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
     if (dtype == PIDM_BF16 && heads == 8 && N % 64 == 0) {
-        la_kstats_kernel<__nv_bfloat16><<<dim3(chunks, B), HID, 0, st>>>((const __nv_bfloat16*)qkv, workspace, N, HID, rpc);
+        la_kstats_kernel<__nv_bfloat16><<<dim3(chunks, B), 256, la_kstats_smem(HID), st>>>((const __nv_bfloat16*)qkv, workspace, N, HID, rpc);
         if (int e = la_mma_ctx(0, qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, B, N, scale, st)) return e;
         if (int e = la_mma_out(qkv, ctx, out, B, N, scale, st)) return e;
         PIDM_LAUNCH_CHECK("linattn_fwd");
@@ -422,7 +463,7 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const int cchunks = (N + 255) / 256 > 16 ? 16 : (N + 255) / 256;
     const int crpc = ((N + cchunks - 1) / cchunks + LA_TN - 1) / LA_TN * LA_TN;
     PIDM_DISPATCH_DTYPE(dtype, {
-        la_kstats_kernel<T><<<dim3(chunks, B), HID, 0, st>>>((const T*)qkv, workspace, N, HID, rpc);
+        la_kstats_kernel<T><<<dim3(chunks, B), la_kstats_block(HID), la_kstats_smem(HID), st>>>((const T*)qkv, workspace, N, HID, rpc);
         la_context_kernel<T, 0><<<dim3((N + crpc - 1) / crpc, heads, B), 256, 0, st>>>(
             (const T*)qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, N, heads, crpc, scale);
         la_out_kernel<T><<<(unsigned)((long long)B * N / 32), 32 * heads, heads * DH * DH * sizeof(float), st>>>(

@@ -33,17 +33,22 @@ __global__ void posterior_kernel(const float4* __restrict__ xt, const float4* __
 }
 
 // ---- NCHW fp32 -> NHWC (channel-padded) activations -----------------------------------------------------
+// one thread per pixel: C coalesced plane reads, one channel-padded NHWC row written with 16-byte stores
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int Cpad,
-                                    long long total) {  // total = B*HW*Cpad
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % Cpad);
-        long long pix = i / Cpad;
-        int hw = (int)(pix % HW);
-        long long b = pix / HW;
-        float v = (c < C) ? src[(b * C + c) * HW + hw] : 0.f;
-        Act<T>::st(dst + i, v);
+                                    long long n_pix) {  // n_pix = B*HW, Cpad % 8 == 0
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < n_pix;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const long long b = pix / HW;
+        const int hw = (int)(pix - b * HW);
+        const float* sp = src + (size_t)b * C * HW + hw;
+        T* dp = dst + (size_t)pix * Cpad;
+        for (int c0 = 0; c0 < Cpad; c0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (c0 + k < C) ? sp[(size_t)(c0 + k) * HW] : 0.f;
+            st8(dp + c0, v);
+        }
     }
 }
 template <typename T>
@@ -250,9 +255,10 @@ extern "C" int pidm_posterior_step(const float* x_t, const float* x0_pred, const
 }
 
 extern "C" int pidm_nchw_to_nhwc(const float* src, void* dst, int B, int C, int HW, int Cpad, int dtype, void* stream) {
-    long long total = (long long)B * HW * Cpad;
-    PIDM_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   src, (T*)dst, C, HW, Cpad, total)));
+    PIDM_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "nchw_to_nhwc: padded channel count must be a multiple of 8, >= C");
+    long long n_pix = (long long)B * HW;
+    PIDM_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(n_pix, 128), 128, 0, (cudaStream_t)stream>>>(
+                                   src, (T*)dst, C, HW, Cpad, n_pix)));
     PIDM_LAUNCH_CHECK("nchw_to_nhwc");
     return 0;
 }

@@ -162,35 +162,43 @@ __global__ void __launch_bounds__(256) block_mlps_wgrad_kernel(const MlpEntry* _
     }
 }
 
-// d_s[b,k] += sum_j dout_e[b,j] W_e[j,k].  grid (entries, row chunks of MLP_DG_ROWS, sample chunks of 32), block td:
-// thread k keeps 32 sample accumulators, W rows are read once per CTA (coalesced over k), dout comes from shared
-// memory as broadcast float4 reads; one atomicAdd per (sample, k) at the end.  ds zeroed by the caller.
-__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, float* __restrict__ ds, int B, int td) {
+// d_s[b,k] += sum_e sum_j dout_e[b,j] W_e[j,k].  grid (MLP_DG_GROUPS, sample chunks of 32), block td.  The 128-row chunks
+// of all entries form one list; CTA g takes every MLP_DG_GROUPS-th chunk and keeps 32 sample accumulators per thread
+// (thread = k) across its chunks: W rows are read once (coalesced over k), dout comes from shared memory as broadcast
+// float4 reads, and only ONE atomicAdd per (sample, k) and CTA is issued at the end.  ds zeroed by the caller.
+constexpr int MLP_DG_GROUPS = 37;       // x sample chunks: a quarter of the SMs -- the whole problem is ~20 MFLOP
+__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, int n_entries, float* __restrict__ ds,
+                                        int B, int td) {
     __shared__ __align__(16) float sd[MLP_DG_ROWS][MLP_BCHUNK];
-    const MlpEntry e = table[blockIdx.x];
-    const int r0 = blockIdx.y * MLP_DG_ROWS;
-    if (r0 >= e.n) return;
-    const int nr = min(MLP_DG_ROWS, e.n - r0);
-    const int b0 = blockIdx.z * MLP_BCHUNK;
+    const int b0 = blockIdx.y * MLP_BCHUNK;
     const int nb = min(MLP_BCHUNK, B - b0);
-    for (int i = threadIdx.x; i < nr * MLP_BCHUNK; i += blockDim.x) {
-        const int b = i / nr, j = i - b * nr;          // consecutive threads walk j: coalesced reads of dout[b, r0 + j]
-        sd[j][b] = b < nb ? e.dout[(size_t)(b0 + b) * e.n + r0 + j] : 0.f;
-    }
-    __syncthreads();
     const int k = threadIdx.x;
     float acc[MLP_BCHUNK];
 #pragma unroll
     for (int b = 0; b < MLP_BCHUNK; ++b) acc[b] = 0.f;
-    const float* wp = e.W + (size_t)r0 * td + k;
+    int chunk_id = 0;
+    for (int ei = 0; ei < n_entries; ++ei) {
+        const MlpEntry e = table[ei];
+        for (int r0 = 0; r0 < e.n; r0 += MLP_DG_ROWS, ++chunk_id) {
+            if (chunk_id % MLP_DG_GROUPS != (int)blockIdx.x) continue;      // block-uniform
+            const int nr = min(MLP_DG_ROWS, e.n - r0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nr * MLP_BCHUNK; i += blockDim.x) {
+                const int b = i / nr, j = i - b * nr;      // consecutive threads walk j: coalesced reads of dout[b, r0 + j]
+                sd[j][b] = b < nb ? e.dout[(size_t)(b0 + b) * e.n + r0 + j] : 0.f;
+            }
+            __syncthreads();
+            const float* wp = e.W + (size_t)r0 * td + k;
 #pragma unroll 2
-    for (int j = 0; j < nr; ++j) {
-        const float w = __ldg(wp + (size_t)j * td);
-        const float4* dj = reinterpret_cast<const float4*>(sd[j]);
+            for (int j = 0; j < nr; ++j) {
+                const float w = __ldg(wp + (size_t)j * td);
+                const float4* dj = reinterpret_cast<const float4*>(sd[j]);
 #pragma unroll
-        for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
-            const float4 d = dj[q];
-            acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
+                for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
+                    const float4 d = dj[q];
+                    acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
+                }
+            }
         }
     }
 #pragma unroll
@@ -254,8 +262,8 @@ extern "C" int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max
     dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
     block_mlps_wgrad_kernel<<<grid, 256, smem, st>>>((const MlpEntry*)table_dev, silu_t, B, td);
     PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
-    dim3 dgrid(n_entries, ceil_div(max_rows, MLP_DG_ROWS), ceil_div(B, MLP_BCHUNK));
-    block_mlps_dgrad_kernel<<<dgrid, td, 0, st>>>((const MlpEntry*)table_dev, d_silu_t, B, td);
+    dim3 dgrid(MLP_DG_GROUPS, ceil_div(B, MLP_BCHUNK));
+    block_mlps_dgrad_kernel<<<dgrid, td, 0, st>>>((const MlpEntry*)table_dev, n_entries, d_silu_t, B, td);
     PIDM_LAUNCH_CHECK("block_mlps_bwd");
     return 0;
 }

@@ -451,6 +451,90 @@ __global__ void ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, con
     }
 }
 
+// Fast path for C = 32, 64, 128, 256 (C/8 a power of two <= 32): a group of L = C/8 lanes owns a pixel and every lane
+// exactly one channel octet, so x (and dy) are read ONCE into registers; LN_UNR pixels per group are in flight together.
+constexpr int LN_UNR = 4;
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) ln1_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                  const float* __restrict__ gamma, T* __restrict__ out,
+                                                  float* __restrict__ dgamma, long long M, int C, float eps) {
+    extern __shared__ float sdg[];  // [C] (BWD only)
+    const int L = C / 8;
+    const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L, gpw = 32 / L;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    float gmm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gmm[k] = gamma[sub * 8 + k];
+    if (BWD) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) sdg[i] = 0.f;
+        __syncthreads();
+    }
+    float dg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float inv_c = 1.f / (float)C;
+    const long long stride = (long long)gridDim.x * warps * gpw;          // pixels per sweep of the grid
+    const long long first = ((long long)blockIdx.x * warps + warp) * gpw + grp;
+    const long long iters = (M + stride * LN_UNR - 1) / (stride * LN_UNR);   // uniform trip count (shuffles)
+    for (long long it = 0; it < iters; ++it) {
+        float v[LN_UNR][8], d[LN_UNR][8];
+        bool ok[LN_UNR];
+#pragma unroll
+        for (int u = 0; u < LN_UNR; ++u) {
+            const long long m = first + (it * LN_UNR + u) * stride;
+            ok[u] = m < M;
+            if (ok[u]) {
+                ld8(x + m * C + sub * 8, v[u]);
+                if (BWD) ld8(dy + m * C + sub * 8, d[u]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { v[u][k] = 0.f; if (BWD) d[u][k] = 0.f; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LN_UNR; ++u) {
+            const long long m = first + (it * LN_UNR + u) * stride;
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s += v[u][k]; ss += v[u][k] * v[u][k]; }
+            for (int off = L >> 1; off > 0; off >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, off);
+                ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            }
+            const float mean = s * inv_c;
+            const float rstd = rsqrtf(fmaxf(ss * inv_c - mean * mean, 0.f) + eps);
+            float o[8];
+            if (!BWD) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = (v[u][k] - mean) * rstd * gmm[k];
+            } else {
+                float a = 0.f, bsum = 0.f, xh[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    xh[k] = (v[u][k] - mean) * rstd;
+                    const float dxh = d[u][k] * gmm[k];
+                    a += dxh; bsum += dxh * xh[k];
+                    dg[k] += d[u][k] * xh[k];
+                }
+                for (int off = L >> 1; off > 0; off >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, off);
+                    bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+                }
+                a *= inv_c; bsum *= inv_c;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = rstd * (d[u][k] * gmm[k] - a - xh[k] * bsum);
+            }
+            if (ok[u]) st8(out + m * C + sub * 8, o);
+        }
+    }
+    if (BWD) {
+        if (reduce_same_octet(dg, L)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&sdg[sub * 8 + k], dg[k]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dgamma[i], sdg[i]);
+    }
+}
+
 static int gn_block(int C) {
     int oct = C / 8;
     int rows = NORM_THREADS / oct;
@@ -565,6 +649,14 @@ extern "C" int pidm_layernorm_c_fwd(const void* x, const float* gamma, void* y, 
     while (L < 32 && L < oct) L <<= 1;
     long long groups = (M + (32 / L) * 8 - 1) / ((32 / L) * 8);
     int grid = (int)(groups < 148 * 8 ? (groups < 1 ? 1 : groups) : 148 * 8);
+    if (L == oct) {          // one octet per lane: register-resident kernel
+        long long g1 = (M + (32 / L) * 8 * LN_UNR - 1) / ((32 / L) * 8 * LN_UNR);
+        int grid1 = (int)(g1 < 148 * 8 ? (g1 < 1 ? 1 : g1) : 148 * 8);
+        PIDM_DISPATCH_DTYPE(dtype, (ln1_kernel<T, false><<<grid1, 256, 0, (cudaStream_t)stream>>>(
+                                       (const T*)x, nullptr, gamma, (T*)y, nullptr, M, C, eps)));
+        PIDM_LAUNCH_CHECK("layernorm_c_fwd");
+        return 0;
+    }
     PIDM_DISPATCH_DTYPE(dtype, (ln_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                    (const T*)x, nullptr, gamma, (T*)y, nullptr, M, C, eps)));
     PIDM_LAUNCH_CHECK("layernorm_c_fwd");
@@ -579,6 +671,14 @@ extern "C" int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* 
     while (L < 32 && L < oct) L <<= 1;
     long long groups = (M + (32 / L) * 8 - 1) / ((32 / L) * 8);
     int grid = (int)(groups < 148 * 4 ? (groups < 1 ? 1 : groups) : 148 * 4);
+    if (L == oct) {
+        long long g1 = (M + (32 / L) * 8 * LN_UNR - 1) / ((32 / L) * 8 * LN_UNR);
+        int grid1 = (int)(g1 < 148 * 4 ? (g1 < 1 ? 1 : g1) : 148 * 4);
+        PIDM_DISPATCH_DTYPE(dtype, (ln1_kernel<T, true><<<grid1, 256, C * sizeof(float), (cudaStream_t)stream>>>(
+                                       (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, M, C, eps)));
+        PIDM_LAUNCH_CHECK("layernorm_c_bwd");
+        return 0;
+    }
     PIDM_DISPATCH_DTYPE(dtype, (ln_kernel<T, true><<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>(
                                    (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, M, C, eps)));
     PIDM_LAUNCH_CHECK("layernorm_c_bwd");

@@ -189,43 +189,48 @@ class _Conv2d(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight, bias = ctx.saved_tensors
-        spec = ctx.spec
-        B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = ctx.g
         dy = dy.contiguous()
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            # dgrad: roles of input/output swap; regular conv -> transposed gather and vice versa.
-            # For stride 1 the transposed gather equals a regular conv with the flipped kernel, which the
-            # dgrad packing already encodes (pad' = K-1-pad), so the tensor-core kernel can take it.
-            if stride == 1 and not spec.transposed:
-                gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, 1, KH - 1 - pad)
-                _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, False)
-            else:
-                gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, stride, pad)
-                _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
-        gw_buf, gw_ret = _grad_buffer(weight)
-        gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
-        if ctx.link is not None and 'dbias' in ctx.link:
-            # the consuming GroupNorm's backward already reduced dy over pixels (= this conv's bias gradient)
-            gb_buf, gb_ret = None, ctx.link.pop('dbias')
-        use_tc = _STATE['use_tc'] and x.dtype == torch.bfloat16
-        if use_tc and not spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, Ho, Wo, Cin, Cout, KH, KW, stride):
-            # D[(tap, ci)][co]: gathered operand = x, reduction grid = output pixels
-            call('pidm_conv2d_wgrad_tc', x, dy, gw_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW, stride, pad,
-                 spec.w_stride_c, spec.w_stride_n, stream())
-            if gb_buf is not None:
-                call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
-        elif use_tc and spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, H, W, Cout, Cin, KH, KW, stride):
-            # ConvTranspose: D[(tap, co)][ci]: gathered operand = dy (sampled with the stride), grid = input pixels
-            call('pidm_conv2d_wgrad_tc', dy, x, gw_buf, B, Ho, Wo, Cout, Cout, H, W, Cin, KH, KW, stride, pad,
-                 spec.w_stride_n, spec.w_stride_c, stream())
-            if gb_buf is not None:
-                call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
-        else:
-            call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW,
-                 stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
+        dx, gw_ret, gb_ret = _conv_backward(x, weight, bias, ctx.spec, ctx.g, dy, ctx.needs_input_grad[0], ctx.link)
         return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None, None
+
+
+def _conv_backward(x, weight, bias, spec, g, dy, need_dx, link=None):
+    """dgrad + wgrad (+ bias gradient) of one convolution; returns (dx, grad_weight, grad_bias) as autograd expects."""
+    B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = g
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        # dgrad: roles of input/output swap; regular conv -> transposed gather and vice versa.
+        # For stride 1 the transposed gather equals a regular conv with the flipped kernel, which the
+        # dgrad packing already encodes (pad' = K-1-pad), so the tensor-core kernel can take it.
+        if stride == 1 and not spec.transposed:
+            gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, 1, KH - 1 - pad)
+            _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, False)
+        else:
+            gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, stride, pad)
+            _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
+    gw_buf, gw_ret = _grad_buffer(weight)
+    gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
+    if link is not None and 'dbias' in link:
+        # the consuming GroupNorm's backward already reduced dy over pixels (= this conv's bias gradient)
+        gb_buf, gb_ret = None, link.pop('dbias')
+    use_tc = _STATE['use_tc'] and x.dtype == torch.bfloat16
+    if use_tc and not spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, Ho, Wo, Cin, Cout, KH, KW, stride):
+        # D[(tap, ci)][co]: gathered operand = x, reduction grid = output pixels
+        call('pidm_conv2d_wgrad_tc', x, dy, gw_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW, stride, pad,
+             spec.w_stride_c, spec.w_stride_n, stream())
+        if gb_buf is not None:
+            call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
+    elif use_tc and spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, H, W, Cout, Cin, KH, KW, stride):
+        # ConvTranspose: D[(tap, co)][ci]: gathered operand = dy (sampled with the stride), grid = input pixels
+        call('pidm_conv2d_wgrad_tc', dy, x, gw_buf, B, Ho, Wo, Cout, Cout, H, W, Cin, KH, KW, stride, pad,
+             spec.w_stride_n, spec.w_stride_c, stream())
+        if gb_buf is not None:
+            call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
+    else:
+        call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW,
+             stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
+    return dx, gw_ret, gb_ret
 
 
 def conv2d(x, weight, bias, spec, residual=None, gn_link=None):
@@ -328,6 +333,49 @@ class _LinAttn(torch.autograd.Function):
         dctx = torch.empty_like(ctxm)
         call('pidm_linattn_bwd', qkv, dout, ctxm, kmax, kzinv, dqkv, dctx, B, H * W, ctx.heads, _code(qkv), stream())
         return dqkv, None
+
+
+class _LinAttnFused(torch.autograd.Function):
+    """to_qkv (1x1, no bias) + linear attention in one op: q, k, v are recomputed per head inside the kernels, the
+    [B, N, 768] qkv tensor is never written (reference unet_model.py:275-297).  Backward produces dqkv once and hands
+    it to the ordinary dgrad / wgrad of the projection."""
+
+    @staticmethod
+    def forward(ctx, xn, weight, spec, heads):
+        B, H, W, C = xn.shape
+        N = H * W
+        out = torch.empty(B, H, W, heads * 32, device=xn.device, dtype=xn.dtype)
+        ctxm = torch.empty(B, heads, 32, 32, device=xn.device, dtype=torch.float32)
+        kmax = torch.empty(B, heads, 32, device=xn.device, dtype=torch.float32)
+        kzinv = torch.empty_like(kmax)
+        ws = torch.empty(call('pidm_linattn_fused_workspace_floats', B, N), device=xn.device, dtype=torch.float32)
+        call('pidm_linattn_fused_fwd', xn, spec.wp_fwd, out, ctxm, kmax, kzinv, ws, B, N, stream())
+        ctx.save_for_backward(xn, weight, ctxm, kmax, kzinv)
+        ctx.spec, ctx.heads = spec, heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xn, weight, ctxm, kmax, kzinv = ctx.saved_tensors
+        spec = ctx.spec
+        B, H, W, C = xn.shape
+        dout = dout.contiguous()
+        dqkv = torch.empty(B, H, W, 3 * ctx.heads * 32, device=xn.device, dtype=xn.dtype)
+        dctx = torch.empty_like(ctxm)
+        call('pidm_linattn_fused_bwd', xn, spec.wp_fwd, dout, ctxm, kmax, kzinv, dqkv, dctx, B, H * W, stream())
+        g = (B, H, W, C, H, W, spec.cout, 1, 1, 1, 0)
+        dx, gw_ret, _ = _conv_backward(xn, weight, None, spec, g, dqkv, ctx.needs_input_grad[0])
+        return dx, gw_ret, None, None
+
+
+def linear_attention_fused_supported(xn, spec, heads):
+    B, H, W, C = xn.shape
+    return (_STATE['use_tc'] and xn.is_cuda and spec.kh == 1 and spec.kw == 1 and spec.cout == 3 * heads * 32
+            and bool(call('pidm_linattn_fused_supported', C, heads, H * W, _code(xn))))
+
+
+def linear_attention_fused(xn, weight, spec, heads):
+    return _LinAttnFused.apply(xn.contiguous(), weight, spec, heads)
 
 
 def linear_attention(qkv, heads):

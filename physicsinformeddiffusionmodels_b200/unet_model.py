@@ -276,8 +276,13 @@ class Unet3D(nn.Module):
     def _linear_attention(self, res, x):
         pre = res.fn
         xn = ops.layernorm_c(x, pre.norm.gamma, pre.norm.eps)
-        qkv = self._conv(pre.fn.to_qkv, xn)
-        a = ops.linear_attention(qkv, pre.fn.heads)
+        to_qkv = pre.fn.to_qkv
+        spec = self._spec[id(to_qkv)]
+        if getattr(to_qkv, 'bias', None) is None and ops.linear_attention_fused_supported(xn, spec, pre.fn.heads):
+            a = ops.linear_attention_fused(xn, to_qkv.weight, spec, pre.fn.heads)   # qkv never materialised
+        else:
+            qkv = self._conv(to_qkv, xn)
+            a = ops.linear_attention(qkv, pre.fn.heads)
         return self._conv(pre.fn.to_out, a, residual=x)
 
     def _mid_attention(self, res, x):

@@ -263,6 +263,42 @@ def test_linear_attention(pk, H, dtype, tol):
     assert rel(nchw(qd.grad), qr.grad) < 2 * tol
 
 
+@pytest.mark.parametrize('B,H', [(2, 64), (3, 16), (1, 32)])
+def test_linear_attention_fused_with_qkv_projection(pk, B, H):
+    """to_qkv 1x1 projection + linear attention in one op (qkv recomputed per head from the 32-channel input, never
+    written) vs an fp32 torch reference of conv + attention on bf16-representable operands, and vs the unfused
+    libpidm path (conv2d + linear_attention).  bf16 activations: 3e-2 like the other bf16 attention tests; the two
+    libpidm paths round at the same points and must agree much more tightly (5e-3)."""
+    ops, packing = pk
+    ops.set_precision('bf16')
+    g = torch.Generator().manual_seed(66)
+    heads, C = 8, 32
+    x = (torch.randn(B, C, H, H, generator=g)).bfloat16().float()
+    w = (torch.randn(3 * heads * 32, C, 1, 1, 1, generator=g) * (1.5 / math.sqrt(C))).bfloat16().float()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = _linattn_ref(F.conv2d(xr, wr[:, :, 0]), heads)
+    cot = torch.randn(yr.shape, generator=g)
+    (yr * cot).sum().backward()
+
+    def run(fused):
+        wd = torch.nn.Parameter(w.to(DEV))
+        spec = packing.ConvSpec(wd, 'conv', 1, 1, 1, 0)
+        pkr = packing.WeightPacker(); pkr.add(spec); pkr.refresh(torch.bfloat16)
+        xd = nhwc(x, torch.bfloat16).to(DEV).requires_grad_(True)
+        if fused:
+            assert ops.linear_attention_fused_supported(xd, spec, heads)
+            y = ops.linear_attention_fused(xd, wd, spec, heads)
+        else:
+            y = ops.linear_attention(ops.conv2d(xd, wd, None, spec), heads)
+        y.backward(nhwc(cot, torch.bfloat16).to(DEV))
+        return nchw(y), nchw(xd.grad), wd.grad.float().cpu()
+    yf, dxf, dwf = run(True)
+    yu, dxu, dwu = run(False)
+    assert rel(yf, yr) < 3e-2 and rel(dxf, xr.grad) < 6e-2 and rel(dwf, wr.grad) < 6e-2, \
+        (rel(yf, yr), rel(dxf, xr.grad), rel(dwf, wr.grad))
+    assert rel(yf, yu) < 5e-3 and rel(dxf, dxu) < 1e-2 and rel(dwf, dwu) < 1e-2, (rel(yf, yu), rel(dxf, dxu), rel(dwf, dwu))
+
+
 @pytest.mark.parametrize('dtype,tol', DTYPES)
 def test_mid_attention(pk, dtype, tol):
     ops, _ = pk
