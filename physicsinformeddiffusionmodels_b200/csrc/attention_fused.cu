@@ -8,7 +8,7 @@
 // `out` only, and backward reads xn + dout and writes dqkv once (consumed by the unchanged dgrad / wgrad of to_qkv).
 // All intermediate tiles stay in registers: accumulator fragments are converted to A fragments directly and to
 // transposed (K-major) fragments with movmatrix; only xn / dout tiles and the output staging touch shared memory.
-// q, k, v are rounded to bf16 where the unfused path materialises them, so both paths agree to rounding noise.
+// The two paths differ only by the bf16 rounding of the (here never materialised) q, k, v.
 #include "common.cuh"
 #include "mma_util.cuh"
 #include "pidm.h"
@@ -44,7 +44,8 @@ __device__ __forceinline__ void load_x_frags(uint32_t (&a)[MT][2][4], const __nv
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) frag_a_rowmajor(a[mt][ks], Xs, LW_PITCH, mt * 16, ks * 16, lane);
 }
-// c[mt][nt] = xn_tile(mt) * W^T, rounded to bf16 precision (what the unfused path stores)
+// c[mt][nt] = xn_tile(mt) * W^T in fp32.  (The unfused path rounds q, k, v to bf16 when it materialises them; the
+// fused path keeps the fp32 products -- closer to the fp32 reference, and conversions share the XU pipe with exp.)
 template <int MT>
 __device__ __forceinline__ void project(float (&c)[MT][4][4], const uint32_t (&a)[MT][2][4], const uint32_t (&w)[2][4][2]) {
 #pragma unroll
@@ -55,8 +56,6 @@ __device__ __forceinline__ void project(float (&c)[MT][4][4], const uint32_t (&a
             for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) mma_bf16(c[mt][nt], a[mt][ks], w[ks][nt][0], w[ks][nt][1]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) c[mt][nt][i] = rbf(c[mt][nt][i]);
         }
 }
 // softmax over the 32 columns of the two rows (g, g + 8) a thread shares with its quad, times mul
@@ -99,11 +98,11 @@ __device__ __forceinline__ void load_cols(float (&v)[8], const float* __restrict
     for (int nt = 0; nt < 4; ++nt) { v[nt * 2] = src[nt * 8 + 2 * t]; v[nt * 2 + 1] = src[nt * 8 + 2 * t + 1]; }
 }
 
-// ---- pass 1: per-chunk column statistics of k = xn Wk^T ------------------------------------------------------------
+// ---- pass 1: per-chunk column maxima of k = xn Wk^T (the exp-sums are accumulated by the context kernel) -------------
 constexpr int LFS_STAGES = 4;
-__global__ void __launch_bounds__(256) laf_kstats_kernel(const __nv_bfloat16* __restrict__ xn,
-                                                         const __nv_bfloat16* __restrict__ W, float* __restrict__ part,
-                                                         int N, int rows_per_chunk) {
+__global__ void __launch_bounds__(256) laf_kmax_kernel(const __nv_bfloat16* __restrict__ xn,
+                                                       const __nv_bfloat16* __restrict__ W, float* __restrict__ part,
+                                                       int N, int rows_per_chunk) {
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * (LFS_STAGES * LW_TILE);
@@ -118,9 +117,9 @@ __global__ void __launch_bounds__(256) laf_kstats_kernel(const __nv_bfloat16* __
     for (int s = 0; s < LFS_STAGES; ++s) issue(s);
     uint32_t wk[2][4][2];
     load_w_frags(wk, W + (size_t)(LM_HID + h * LM_D) * LF_C, lane);
-    float m[8], sm[8];
+    float m[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; sm[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
     for (int it = 0; it < n_tiles; ++it) {
         cp_wait<LFS_STAGES - 1>();
         __syncwarp();
@@ -133,36 +132,31 @@ __global__ void __launch_bounds__(256) laf_kstats_kernel(const __nv_bfloat16* __
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float v0 = ck[0][nt][j], v1 = ck[0][nt][2 + j], v2 = ck[1][nt][j], v3 = ck[1][nt][2 + j];
-                const float mo = m[nt * 2 + j];
-                const float mn = fmaxf(fmaxf(mo, fmaxf(v0, v1)), fmaxf(v2, v3));
-                sm[nt * 2 + j] = sm[nt * 2 + j] * __expf(mo - mn) + __expf(v0 - mn) + __expf(v1 - mn) + __expf(v2 - mn) +
-                                 __expf(v3 - mn);
-                m[nt * 2 + j] = mn;
-            }
+            for (int j = 0; j < 2; ++j)
+                m[nt * 2 + j] = fmaxf(fmaxf(m[nt * 2 + j], fmaxf(ck[0][nt][j], ck[0][nt][2 + j])),
+                                      fmaxf(ck[1][nt][j], ck[1][nt][2 + j]));
     }
-    // merge the 8 row-lanes (g) that share a column
 #pragma unroll
     for (int off = 4; off < 32; off <<= 1)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float m2 = __shfl_xor_sync(0xffffffffu, m[i], off), s2 = __shfl_xor_sync(0xffffffffu, sm[i], off);
-            const float mn = fmaxf(m[i], m2);
-            sm[i] = sm[i] * __expf(m[i] - mn) + s2 * __expf(m2 - mn);
-            m[i] = mn;
-        }
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], off));
     if (lane < 4) {
-        float* o = part + (((size_t)b * gridDim.x + chunk) * LM_HID + h * LM_D) * 2;
+        float* o = part + ((size_t)b * gridDim.x + chunk) * LM_HID + h * LM_D;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = nt * 8 + 2 * lane + j;
-                o[col * 2] = m[nt * 2 + j];
-                o[col * 2 + 1] = sm[nt * 2 + j];
-            }
+            for (int j = 0; j < 2; ++j) o[nt * 8 + 2 * lane + j] = m[nt * 2 + j];
     }
+}
+
+// ctx[b][h][d][:] *= 1 / Z[b][h][d]  and  kzinv = 1 / Z, after the context kernel has accumulated both
+__global__ void laf_finalize_kernel(float* __restrict__ ctx, float* __restrict__ kzinv, int n_rows) {
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const float zi = 1.f / kzinv[row];
+    ctx[(size_t)row * LM_D + lane] *= zi;
+    __syncwarp();
+    if (lane == 0) kzinv[row] = zi;
 }
 
 // ---- context (MODE 0) / dcontext (MODE 1) --------------------------------------------------------------------------
@@ -204,18 +198,15 @@ __global__ void __launch_bounds__(256) laf_ctx_kernel(const __nv_bfloat16* __res
     load_w_frags(w0, W + (size_t)((MODE == 0 ? LM_HID : 0) + h * LM_D) * LF_C, lane);
     if (MODE == 0) load_w_frags(w1, W + (size_t)(2 * LM_HID + h * LM_D) * LF_C, lane);
     float Mc[8];
-    if (MODE == 0) {                               // lane = channel d of this head: combine the per-chunk statistics
+    float zacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) zacc[i] = 0.f;
+    if (MODE == 0) {                               // lane = channel d of this head: combine the per-chunk maxima
         const int c = h * LM_D + lane;
         float M = -INFINITY;
-        for (int i = 0; i < n_stat_chunks; ++i) M = fmaxf(M, part[(((size_t)b * n_stat_chunks + i) * LM_HID + c) * 2]);
-        float Z = 0.f;
-        for (int i = 0; i < n_stat_chunks; ++i) {
-            const float* p = part + (((size_t)b * n_stat_chunks + i) * LM_HID + c) * 2;
-            Z += p[1] * __expf(p[0] - M);
-        }
+        for (int i = 0; i < n_stat_chunks; ++i) M = fmaxf(M, part[((size_t)b * n_stat_chunks + i) * LM_HID + c]);
         sM[lane] = M;
-        sZi[lane] = 1.f / Z;
-        if (chunk == 0) { kmax[(size_t)b * LM_HID + c] = M; kzinv[(size_t)b * LM_HID + c] = 1.f / Z; }
+        if (chunk == 0) kmax[(size_t)b * LM_HID + c] = M;
         __syncwarp();
         load_cols(Mc, sM, lane);
     }
@@ -253,7 +244,10 @@ __global__ void __launch_bounds__(256) laf_ctx_kernel(const __nv_bfloat16* __res
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) cw[mt][nt][i] = __expf(cw[mt][nt][i] - Mc[nt * 2 + (i & 1)]);
+                    for (int i = 0; i < 4; ++i) {
+                        cw[mt][nt][i] = __expf(cw[mt][nt][i] - Mc[nt * 2 + (i & 1)]);
+                        zacc[nt * 2 + (i & 1)] += cw[mt][nt][i];
+                    }
             float cv[2][4][4];
             project<2>(cv, ax, w1);
 #pragma unroll
@@ -283,13 +277,26 @@ __global__ void __launch_bounds__(256) laf_ctx_kernel(const __nv_bfloat16* __res
         }
     }
     const int g = lane >> 2, t = lane & 3;
+    if (MODE == 0) {                               // Z_d = sum_n exp(k[n,d] - M_d): column sums over the 8 row-lanes
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zacc[i] += __shfl_xor_sync(0xffffffffu, zacc[i], off);
+        if (lane < 4) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    atomicAdd(kzinv + (size_t)b * LM_HID + h * LM_D + nt * 8 + 2 * lane + j, zacc[nt * 2 + j]);
+        }
+    }
     float* cb = ctx + ((size_t)b * LM_HEADS + h) * LM_D * LM_D;
 #pragma unroll
     for (int md = 0; md < 2; ++md)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int d = md * 16 + g + half * 8;
-            const float f = (MODE == 0) ? sZi[d] / (float)N : 1.f;
+            const float f = (MODE == 0) ? 1.f / (float)N : 1.f;      // MODE 0: 1 / Z_d is applied by laf_finalize_kernel
 #pragma unroll
             for (int ne = 0; ne < 4; ++ne) {
                 const int e = ne * 8 + 2 * t;
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(256) laf_bwd_kernel(const __nv_bfloat16* __res
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { c1[0][nt][i] = rbf(c1[0][nt][i]); c2[nt][i] = 0.f; }
+            for (int i = 0; i < 4; ++i) c2[nt][i] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) mma_bf16(c2[nt], ag[ks], bc[ks][nt][0], bc[ks][nt][1]);
         }
@@ -481,7 +488,7 @@ __global__ void __launch_bounds__(256) laf_bwd_kernel(const __nv_bfloat16* __res
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                c1[0][nt][i] = rbf(__expf(c1[0][nt][i] - Mc[nt * 2 + (i & 1)]) * Zc[nt * 2 + (i & 1)]);
+                c1[0][nt][i] = __expf(c1[0][nt][i] - Mc[nt * 2 + (i & 1)]) * Zc[nt * 2 + (i & 1)];
         c_to_a(ak, c1[0]);
 #pragma unroll
         for (int half = 0; half < 2; ++half)
@@ -520,7 +527,7 @@ constexpr size_t LAF_BWD_SMEM = (size_t)LM_HEADS * (LFB_STAGES * LFB_STAGE_ELEMS
 static int laf_attrs() {
     static bool done = false;
     if (!done) {
-        PIDM_CUDA(cudaFuncSetAttribute(laf_kstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAF_STATS_SMEM));
+        PIDM_CUDA(cudaFuncSetAttribute(laf_kmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAF_STATS_SMEM));
         PIDM_CUDA(cudaFuncSetAttribute(laf_ctx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LfcCfg<0>::SMEM));
         PIDM_CUDA(cudaFuncSetAttribute(laf_ctx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LfcCfg<1>::SMEM));
         PIDM_CUDA(cudaFuncSetAttribute(laf_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAF_OUT_SMEM));
@@ -553,7 +560,7 @@ extern "C" int pidm_linattn_fused_supported(int C, int heads, int N, int dtype) 
     return (C == LF_C && heads == LM_HEADS && dtype == PIDM_BF16 && N % 128 == 0) ? 1 : 0;
 }
 
-extern "C" int pidm_linattn_fused_workspace_floats(int B, int N) { return B * laf_stat_chunks(N) * LM_HID * 2; }
+extern "C" int pidm_linattn_fused_workspace_floats(int B, int N) { return B * laf_stat_chunks(N) * LM_HID; }
 
 // xn [B,N,32] bf16 (the PreNorm output), w_qkv [768][32] bf16 (packed to_qkv weights, K-major), out [B,N,256] bf16.
 // ctx [B,8,32,32], kmax / kzinv [B,8,32] are outputs kept for backward; workspace: pidm_linattn_fused_workspace_floats.
@@ -566,13 +573,15 @@ extern "C" int pidm_linattn_fused_fwd(const void* xn, const void* w_qkv, void* o
     const __nv_bfloat16* x = (const __nv_bfloat16*)xn;
     const __nv_bfloat16* w = (const __nv_bfloat16*)w_qkv;
     PIDM_CUDA(cudaMemsetAsync(ctx, 0, (size_t)B * LM_HEADS * LM_D * LM_D * sizeof(float), st));
+    PIDM_CUDA(cudaMemsetAsync(kzinv, 0, (size_t)B * LM_HID * sizeof(float), st));
     const int chunks = laf_stat_chunks(N);
     const int rpc = N / chunks;
     PIDM_REQUIRE(rpc % 32 == 0 && rpc * chunks == N, "linattn_fused: bad statistics chunking for N=%d", N);
-    laf_kstats_kernel<<<dim3(chunks, B), 256, LAF_STATS_SMEM, st>>>(x, w, workspace, N, rpc);
+    laf_kmax_kernel<<<dim3(chunks, B), 256, LAF_STATS_SMEM, st>>>(x, w, workspace, N, rpc);
     const int cpx = laf_chunk_px(B, N, 2);
     laf_ctx_kernel<0><<<dim3((N + cpx - 1) / cpx, B), 256, LfcCfg<0>::SMEM, st>>>(x, w, nullptr, workspace, chunks, kmax, kzinv,
                                                                              ctx, N, cpx, scale);
+    laf_finalize_kernel<<<(B * LM_HID + 7) / 8, 256, 0, st>>>(ctx, kzinv, B * LM_HID);
     const int opx = laf_chunk_px(B, N, 2);
     laf_out_kernel<<<dim3((N + opx - 1) / opx, B), 256, LAF_OUT_SMEM, st>>>(x, w, ctx, (__nv_bfloat16*)out, N, opx, scale);
     PIDM_LAUNCH_CHECK("linattn_fused_fwd");

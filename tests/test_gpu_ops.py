@@ -268,7 +268,7 @@ def test_linear_attention_fused_with_qkv_projection(pk, B, H):
     """to_qkv 1x1 projection + linear attention in one op (qkv recomputed per head from the 32-channel input, never
     written) vs an fp32 torch reference of conv + attention on bf16-representable operands, and vs the unfused
     libpidm path (conv2d + linear_attention).  bf16 activations: 3e-2 like the other bf16 attention tests; the two
-    libpidm paths round at the same points and must agree much more tightly (5e-3)."""
+    libpidm paths differ only by the bf16 rounding of the (never materialised) q, k, v: 1e-2 / 2e-2."""
     ops, packing = pk
     ops.set_precision('bf16')
     g = torch.Generator().manual_seed(66)
@@ -296,7 +296,7 @@ def test_linear_attention_fused_with_qkv_projection(pk, B, H):
     yu, dxu, dwu = run(False)
     assert rel(yf, yr) < 3e-2 and rel(dxf, xr.grad) < 6e-2 and rel(dwf, wr.grad) < 6e-2, \
         (rel(yf, yr), rel(dxf, xr.grad), rel(dwf, wr.grad))
-    assert rel(yf, yu) < 5e-3 and rel(dxf, dxu) < 1e-2 and rel(dwf, dwu) < 1e-2, (rel(yf, yu), rel(dxf, dxu), rel(dwf, dwu))
+    assert rel(yf, yu) < 1e-2 and rel(dxf, dxu) < 2e-2 and rel(dwf, dwu) < 2e-2, (rel(yf, yu), rel(dxf, dxu), rel(dwf, dwu))
 
 
 @pytest.mark.parametrize('dtype,tol', DTYPES)
