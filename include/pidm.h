@@ -127,7 +127,8 @@ int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const float* sums, co
                             int dtype, void* stream);
 /* channel LayerNorm, gain only, biased variance (src/unet_model.py:201-210); dgamma ACCUMULATES */
 int pidm_layernorm_c_fwd(const void* x, const float* gamma, void* y, long long M, int C, float eps, int dtype, void* stream);
-int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma, long long M, int C,
+int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma,
+                         const void* dx_residual /* optional: added to dx (skip-connection gradient) */, long long M, int C,
                          float eps, int dtype, void* stream);
 
 /* ---- attention ------------------------------------------------------------------------------------------ */

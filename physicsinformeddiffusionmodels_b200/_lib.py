@@ -46,7 +46,7 @@ _SIGS = {
     'pidm_groupnorm_silu_fwd': [P, P, P, P, P, P, I, I, I, I, I, F, I, P],
     'pidm_groupnorm_silu_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     'pidm_layernorm_c_fwd': [P, P, P, L, I, F, I, P],
-    'pidm_layernorm_c_bwd': [P, P, P, P, P, L, I, F, I, P],
+    'pidm_layernorm_c_bwd': [P, P, P, P, P, P, L, I, F, I, P],
     'pidm_linattn_workspace_floats': [I, I, I],
     'pidm_linattn_fused_supported': [I, I, I, I],
     'pidm_linattn_fused_workspace_floats': [I, I],

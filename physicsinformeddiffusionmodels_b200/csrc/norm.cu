@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_bwd_cluster_kernel(
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool BWD>
 __global__ void ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ gamma,
-                          T* __restrict__ out, float* __restrict__ dgamma, long long M, int C, float eps) {
+                          T* __restrict__ out, float* __restrict__ dgamma, const T* __restrict__ res, long long M, int C,
+                          float eps) {
     extern __shared__ float sdg[];  // [C] (BWD only)
     const int oct = C / 8;
     int L = 1;
@@ -433,6 +434,12 @@ __global__ void ln_kernel(const T* __restrict__ x, const T* __restrict__ dy, con
                         float xh = (v[k] - mean) * rstd;
                         v[k] = rstd * (d[k] * gamma[o * 8 + k] - a - xh * bsum);
                     }
+                    if (res) {
+                        float rr[8];
+                        ld8(res + m * C + o * 8, rr);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] += rr[k];
+                    }
                     st8(out + m * C + o * 8, v);
                 }
         }
@@ -457,7 +464,8 @@ constexpr int LN_UNR = 4;
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) ln1_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                   const float* __restrict__ gamma, T* __restrict__ out,
-                                                  float* __restrict__ dgamma, long long M, int C, float eps) {
+                                                  float* __restrict__ dgamma, const T* __restrict__ res, long long M,
+                                                  int C, float eps) {
     extern __shared__ float sdg[];  // [C] (BWD only)
     const int L = C / 8;
     const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L, gpw = 32 / L;
@@ -521,6 +529,12 @@ __global__ void __launch_bounds__(256) ln1_kernel(const T* __restrict__ x, const
                 a *= inv_c; bsum *= inv_c;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] = rstd * (d[u][k] * gmm[k] - a - xh[k] * bsum);
+                if (res != nullptr && ok[u]) {          // gradient of a skip connection that bypasses the norm
+                    float rr[8];
+                    ld8(res + m * C + sub * 8, rr);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += rr[k];
+                }
             }
             if (ok[u]) st8(out + m * C + sub * 8, o);
         }
@@ -653,19 +667,20 @@ extern "C" int pidm_layernorm_c_fwd(const void* x, const float* gamma, void* y, 
         long long g1 = (M + (32 / L) * 8 * LN_UNR - 1) / ((32 / L) * 8 * LN_UNR);
         int grid1 = (int)(g1 < 148 * 8 ? (g1 < 1 ? 1 : g1) : 148 * 8);
         PIDM_DISPATCH_DTYPE(dtype, (ln1_kernel<T, false><<<grid1, 256, 0, (cudaStream_t)stream>>>(
-                                       (const T*)x, nullptr, gamma, (T*)y, nullptr, M, C, eps)));
+                                       (const T*)x, nullptr, gamma, (T*)y, nullptr, nullptr, M, C, eps)));
         PIDM_LAUNCH_CHECK("layernorm_c_fwd");
         return 0;
     }
     PIDM_DISPATCH_DTYPE(dtype, (ln_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                                   (const T*)x, nullptr, gamma, (T*)y, nullptr, M, C, eps)));
+                                   (const T*)x, nullptr, gamma, (T*)y, nullptr, nullptr, M, C, eps)));
     PIDM_LAUNCH_CHECK("layernorm_c_fwd");
     return 0;
 }
 
-// dgamma is ACCUMULATED.
+// dgamma is ACCUMULATED.  dx_residual (optional, same shape as dx) is added to dx: the gradient of a skip connection
+// that bypasses the norm, so that the caller needs no separate accumulation kernel.
 extern "C" int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma,
-                                    long long M, int C, float eps, int dtype, void* stream) {
+                                    const void* dx_residual, long long M, int C, float eps, int dtype, void* stream) {
     PIDM_REQUIRE(C % 8 == 0 && C <= 1024, "layernorm: C must be a multiple of 8 and <= 1024 (got %d)", C);
     int oct = C / 8, L = 1;
     while (L < 32 && L < oct) L <<= 1;
@@ -675,12 +690,12 @@ extern "C" int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* 
         long long g1 = (M + (32 / L) * 8 * LN_UNR - 1) / ((32 / L) * 8 * LN_UNR);
         int grid1 = (int)(g1 < 148 * 4 ? (g1 < 1 ? 1 : g1) : 148 * 4);
         PIDM_DISPATCH_DTYPE(dtype, (ln1_kernel<T, true><<<grid1, 256, C * sizeof(float), (cudaStream_t)stream>>>(
-                                       (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, M, C, eps)));
+                                       (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, (const T*)dx_residual, M, C, eps)));
         PIDM_LAUNCH_CHECK("layernorm_c_bwd");
         return 0;
     }
     PIDM_DISPATCH_DTYPE(dtype, (ln_kernel<T, true><<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>(
-                                   (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, M, C, eps)));
+                                   (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, (const T*)dx_residual, M, C, eps)));
     PIDM_LAUNCH_CHECK("layernorm_c_bwd");
     return 0;
 }

@@ -90,6 +90,38 @@ def add(a, b):
     return _Add.apply(a.contiguous(), b.contiguous())
 
 
+class _Stash(torch.autograd.Function):
+    """Identity whose backward parks the incoming gradient in `link['skip']` instead of returning it.  Used for the
+    skip branch of y = f(x) + x: the backward of the FIRST op of f (a convolution dgrad or the LayerNorm backward, both
+    take a residual) adds the parked gradient in its epilogue, so autograd has a single contribution for x and no
+    separate accumulation kernel runs.  Ordering: this node is created after every node of f, so the autograd engine
+    (highest sequence number first among ready nodes) runs it before any node of f can become ready."""
+
+    @staticmethod
+    def forward(ctx, x, link):
+        ctx.link = link
+        link['expect_skip'] = True
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.link['skip'] = g.contiguous()
+        return None, None
+
+
+def stash_grad(x, link):
+    return _Stash.apply(x, link)
+
+
+def _take_skip(link):
+    """gradient parked by _Stash / a stashing convolution for the op that owns `link` (None if there is no link)"""
+    if link is None or not link.get('expect_skip'):
+        return None
+    if 'skip' not in link:
+        raise RuntimeError('skip-connection gradient was expected but has not been produced yet (autograd order)')
+    return link.pop('skip')
+
+
 class _Concat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
@@ -166,7 +198,9 @@ class _Conv2d(torch.autograd.Function):
     fused statistics in link['sums']; the GroupNorm backward leaves this conv's bias gradient in link['dbias']."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, spec, link):
+    def forward(ctx, x, weight, bias, residual, spec, link, skip):
+        """skip (optional) = (mode, dict): mode 'take' -> this conv's dgrad adds the gradient parked in the dict;
+        mode 'park' -> this conv parks its own input gradient there instead of returning it."""
         B, H, W, Cin = x.shape
         Ho, Wo = spec.out_hw(H, W)
         y = torch.empty(B, Ho, Wo, spec.cout, device=x.device, dtype=x.dtype)
@@ -183,32 +217,41 @@ class _Conv2d(torch.autograd.Function):
             link['sums'] = sums if fused else None
             link['bias'] = bias
         ctx.save_for_backward(x, weight, bias)
-        ctx.spec, ctx.g, ctx.has_res, ctx.link = spec, g, residual is not None, link
+        ctx.spec, ctx.g, ctx.has_res, ctx.link, ctx.skip = spec, g, residual is not None, link, skip
+        if skip is not None and skip[0] == 'park':
+            skip[1]['expect_skip'] = True
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight, bias = ctx.saved_tensors
         dy = dy.contiguous()
-        dx, gw_ret, gb_ret = _conv_backward(x, weight, bias, ctx.spec, ctx.g, dy, ctx.needs_input_grad[0], ctx.link)
-        return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None, None
+        skip = ctx.skip
+        dgrad_res = _take_skip(skip[1]) if (skip is not None and skip[0] == 'take') else None
+        dx, gw_ret, gb_ret = _conv_backward(x, weight, bias, ctx.spec, ctx.g, dy, ctx.needs_input_grad[0], ctx.link,
+                                            dgrad_res)
+        if skip is not None and skip[0] == 'park':
+            skip[1]['skip'] = dx
+            dx = None
+        return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None, None, None
 
 
-def _conv_backward(x, weight, bias, spec, g, dy, need_dx, link=None):
-    """dgrad + wgrad (+ bias gradient) of one convolution; returns (dx, grad_weight, grad_bias) as autograd expects."""
+def _conv_backward(x, weight, bias, spec, g, dy, need_dx, link=None, dgrad_residual=None):
+    """dgrad + wgrad (+ bias gradient) of one convolution; returns (dx, grad_weight, grad_bias) as autograd expects.
+    dgrad_residual (same shape as x) is added to dx in the dgrad epilogue."""
     B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad = g
     dx = None
-    if need_dx:
+    if need_dx or dgrad_residual is not None:
         dx = torch.empty_like(x)
         # dgrad: roles of input/output swap; regular conv -> transposed gather and vice versa.
         # For stride 1 the transposed gather equals a regular conv with the flipped kernel, which the
         # dgrad packing already encodes (pad' = K-1-pad), so the tensor-core kernel can take it.
         if stride == 1 and not spec.transposed:
             gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, 1, KH - 1 - pad)
-            _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, False)
+            _conv_launch(dy, spec.wp_dgrad, None, dgrad_residual, dx, gd, False)
         else:
             gd = (B, Ho, Wo, Cout, H, W, Cin, KH, KW, stride, pad)
-            _conv_launch(dy, spec.wp_dgrad, None, None, dx, gd, not spec.transposed)
+            _conv_launch(dy, spec.wp_dgrad, None, dgrad_residual, dx, gd, not spec.transposed)
     gw_buf, gw_ret = _grad_buffer(weight)
     gb_buf, gb_ret = (None, None) if bias is None else _grad_buffer(bias)
     if link is not None and 'dbias' in link:
@@ -233,9 +276,9 @@ def _conv_backward(x, weight, bias, spec, g, dy, need_dx, link=None):
     return dx, gw_ret, gb_ret
 
 
-def conv2d(x, weight, bias, spec, residual=None, gn_link=None):
+def conv2d(x, weight, bias, spec, residual=None, gn_link=None, skip=None):
     return _Conv2d.apply(x.contiguous(), weight, bias, None if residual is None else residual.contiguous(), spec,
-                         gn_link)
+                         gn_link, skip)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -280,12 +323,12 @@ def groupnorm_silu(x, gamma, beta, scale_shift, groups, eps=1e-5, gn_link=None):
 
 class _LayerNormC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, eps):
+    def forward(ctx, x, gamma, eps, skip_link):
         C = x.shape[-1]
         y = torch.empty_like(x)
         call('pidm_layernorm_c_fwd', x, gamma, y, x.numel() // C, C, eps, _code(x), stream())
         ctx.save_for_backward(x, gamma)
-        ctx.eps = eps
+        ctx.eps, ctx.skip_link = eps, skip_link
         return y
 
     @staticmethod
@@ -295,13 +338,15 @@ class _LayerNormC(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         gg_buf, gg_ret = _grad_buffer(gamma)
-        call('pidm_layernorm_c_bwd', x, dy, gamma, dx, gg_buf, x.numel() // C, C, ctx.eps, _code(x), stream())
-        return dx, gg_ret, None
+        call('pidm_layernorm_c_bwd', x, dy, gamma, dx, gg_buf, _take_skip(ctx.skip_link), x.numel() // C, C, ctx.eps,
+             _code(x), stream())
+        return dx, gg_ret, None, None
 
 
-def layernorm_c(x, gamma, eps=1e-5):
-    """gamma: the reference's [1,C,1,1,1] parameter (contiguous, so it is a flat [C] buffer)."""
-    return _LayerNormC.apply(x.contiguous(), gamma, eps)
+def layernorm_c(x, gamma, eps=1e-5, skip_link=None):
+    """gamma: the reference's [1,C,1,1,1] parameter (contiguous, so it is a flat [C] buffer).
+    skip_link: dict shared with stash_grad() -- the parked skip-connection gradient is added to dx."""
+    return _LayerNormC.apply(x.contiguous(), gamma, eps, skip_link)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -254,28 +254,32 @@ class Unet3D(nn.Module):
         self._mlp_table = MlpTable(mlps)
 
     # ---- kernels ----------------------------------------------------------------------------------------
-    def _conv(self, mod, x, residual=None, gn_link=None):
+    def _conv(self, mod, x, residual=None, gn_link=None, skip=None):
         return ops.conv2d(x, mod.weight, getattr(mod, 'bias', None), self._spec[id(mod)], residual=residual,
-                          gn_link=gn_link)
+                          gn_link=gn_link, skip=skip)
 
     def _resblock(self, block, x, ss_list):
         ss = ss_list[block._mlp_index] if (block.mlp is not None and ss_list is not None) else None
         # conv -> GroupNorm pairs are linked: statistics come out of the conv epilogue, the conv's bias gradient
         # out of the GroupNorm backward
         l1, l2 = {'groups': block.groups}, {'groups': block.groups}
-        h = self._conv(block.block1.proj, x, gn_link=l1)
+        # x feeds both the first conv and the residual branch: the residual branch parks its gradient (ops._Stash /
+        # a 'park' conv) and the first conv's dgrad adds it in its epilogue -- no separate accumulation kernel
+        sk = {}
+        h = self._conv(block.block1.proj, x, gn_link=l1, skip=('take', sk))
         h = ops.groupnorm_silu(h, block.block1.norm.weight, block.block1.norm.bias, ss, block.groups,
                                block.block1.norm.eps, gn_link=l1)
         h = self._conv(block.block2.proj, h, gn_link=l2)
         h = ops.groupnorm_silu(h, block.block2.norm.weight, block.block2.norm.bias, None, block.groups,
                                block.block2.norm.eps, gn_link=l2)
         if isinstance(block.res_conv, nn.Identity):
-            return ops.add(h, x)
-        return self._conv(block.res_conv, x, residual=h)
+            return ops.add(h, ops.stash_grad(x, sk))
+        return self._conv(block.res_conv, x, residual=h, skip=('park', sk))
 
     def _linear_attention(self, res, x):
         pre = res.fn
-        xn = ops.layernorm_c(x, pre.norm.gamma, pre.norm.eps)
+        sk = {}                                    # gradient of the `+ x` skip is added inside the LayerNorm backward
+        xn = ops.layernorm_c(x, pre.norm.gamma, pre.norm.eps, skip_link=sk)
         to_qkv = pre.fn.to_qkv
         spec = self._spec[id(to_qkv)]
         if getattr(to_qkv, 'bias', None) is None and ops.linear_attention_fused_supported(xn, spec, pre.fn.heads):
@@ -283,15 +287,16 @@ class Unet3D(nn.Module):
         else:
             qkv = self._conv(to_qkv, xn)
             a = ops.linear_attention(qkv, pre.fn.heads)
-        return self._conv(pre.fn.to_out, a, residual=x)
+        return self._conv(pre.fn.to_out, a, residual=ops.stash_grad(x, sk))
 
     def _mid_attention(self, res, x):
         pre = res.fn
         att = pre.fn.fn
-        xn = ops.layernorm_c(x, pre.norm.gamma, pre.norm.eps)
+        sk = {}
+        xn = ops.layernorm_c(x, pre.norm.gamma, pre.norm.eps, skip_link=sk)
         qkv = self._conv(att.to_qkv, xn)
         a = ops.softmax_attention(qkv, att.heads)
-        return self._conv(att.to_out, a, residual=x)
+        return self._conv(att.to_out, a, residual=ops.stash_grad(x, sk))
 
     def forward_with_guidance_scale(self, *args, **kwargs):
         raise NotImplementedError('classifier-free residual-gradient guidance (cond=...) is outside the built hot path')
