@@ -86,7 +86,11 @@ class TrainEngine:
         fp = self.fp
         loss, data_l, rabs, _, _ = self.diffusion.model_estimation_loss(
             x0, residual_func=self.residuals, c_data=self.c_data, c_residual=self.c_residual, c_ineq=0., lambda_opt=0.)
-        loss.backward()
+        ops.side_stream_begin()                 # weight-gradient kernels overlap the dgrad chain (joined below)
+        try:
+            loss.backward()
+        finally:
+            ops.side_stream_join()
         allreduce_flat_grad(fp.grad, self.world)
         fp.gnorm_sq.zero_()
         call('pidm_sumsq', fp.grad, fp.total, fp.gnorm_sq, stream())

@@ -236,6 +236,36 @@ class _Conv2d(torch.autograd.Function):
         return dx, gw_ret, gb_ret, (dy if ctx.has_res else None), None, None, None
 
 
+# Weight-gradient kernels only feed the optimizer: inside TrainEngine they are launched on a side stream so that they
+# overlap the (latency-bound) dgrad / normalisation chain of the remaining layers.  Operand tensors are kept alive until
+# the join (they were allocated on the main stream).
+_SIDE = {'stream': None, 'keep': [], 'active': False}
+
+
+def side_stream_begin():
+    if _SIDE['stream'] is None:
+        _SIDE['stream'] = torch.cuda.Stream()
+    _SIDE['active'] = True
+    _SIDE['keep'] = []
+
+
+def side_stream_join():
+    if _SIDE['active']:
+        torch.cuda.current_stream().wait_stream(_SIDE['stream'])
+        _SIDE['keep'] = []
+        _SIDE['active'] = False
+
+
+def _wgrad_stream(*operands):
+    """stream handle for a wgrad-type launch whose operands are ready on the current stream"""
+    if not _SIDE['active']:
+        return stream()
+    side = _SIDE['stream']
+    side.wait_stream(torch.cuda.current_stream())
+    _SIDE['keep'].extend(operands)
+    return side.cuda_stream
+
+
 def _conv_backward(x, weight, bias, spec, g, dy, need_dx, link=None, dgrad_residual=None):
     """dgrad + wgrad (+ bias gradient) of one convolution; returns (dx, grad_weight, grad_bias) as autograd expects.
     dgrad_residual (same shape as x) is added to dx in the dgrad epilogue."""
@@ -258,21 +288,22 @@ def _conv_backward(x, weight, bias, spec, g, dy, need_dx, link=None, dgrad_resid
         # the consuming GroupNorm's backward already reduced dy over pixels (= this conv's bias gradient)
         gb_buf, gb_ret = None, link.pop('dbias')
     use_tc = _STATE['use_tc'] and x.dtype == torch.bfloat16
+    ws = _wgrad_stream(x, dy)
     if use_tc and not spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, Ho, Wo, Cin, Cout, KH, KW, stride):
         # D[(tap, ci)][co]: gathered operand = x, reduction grid = output pixels
         call('pidm_conv2d_wgrad_tc', x, dy, gw_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW, stride, pad,
-             spec.w_stride_c, spec.w_stride_n, stream())
+             spec.w_stride_c, spec.w_stride_n, ws)
         if gb_buf is not None:
-            call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
+            call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), ws)
     elif use_tc and spec.transposed and call('pidm_conv2d_wgrad_tc_supported', B, H, W, Cout, Cin, KH, KW, stride):
         # ConvTranspose: D[(tap, co)][ci]: gathered operand = dy (sampled with the stride), grid = input pixels
         call('pidm_conv2d_wgrad_tc', dy, x, gw_buf, B, Ho, Wo, Cout, Cout, H, W, Cin, KH, KW, stride, pad,
-             spec.w_stride_n, spec.w_stride_c, stream())
+             spec.w_stride_n, spec.w_stride_c, ws)
         if gb_buf is not None:
-            call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), stream())
+            call('pidm_colsum', dy, gb_buf, B * Ho * Wo, Cout, _code(dy), ws)
     else:
         call('pidm_conv2d_wgrad_simt', x, dy, gw_buf, gb_buf, B, H, W, Cin, spec.cin_real, Ho, Wo, Cout, KH, KW,
-             stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), stream())
+             stride, pad, 1 if spec.transposed else 0, spec.w_stride_n, spec.w_stride_c, _code(x), ws)
     return dx, gw_ret, gb_ret
 
 
