@@ -231,6 +231,30 @@ def breakdown_one_step(engine, x0):
     return agg
 
 
+def sampling_bench(model, res, dev, n_steps=250, batch=16):
+    """BASELINE.json configs[3]: ancestral sampling loop with per-step Darcy residual evaluation, one CUDA graph per
+    step replayed n_steps times (engine.SampleEngine).  Device-timed; the initial noise is drawn on the device."""
+    from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
+    from physicsinformeddiffusionmodels_b200.engine import SampleEngine
+    was_training = model.training
+    model.eval()
+    diff = DenoisingDiffusion(n_steps, dev)
+    eng = SampleEngine(model, diff, res, batch=batch)
+    eng.sample()                                      # captures the graph + one full warm-up loop
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x, r, _ = eng.sample()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    model.train(was_training)
+    return {'workload': f'Darcy 64x64 ancestral sampling (p_sample_loop), {n_steps} steps, batch {batch}, x0 = network '
+                        'output (mean mode), Darcy residual evaluated every step, bf16 activations',
+            'ms_per_loop': ms, 'ms_per_step': ms / n_steps, 'samples_per_s': batch / (ms * 1e-3),
+            'final_abs_residual_mean': float(r.abs().mean().item()), 'finite': bool(torch.isfinite(x).all().item())}
+
+
 def residual_kernel_sweep(pk):
     """Standalone HBM sweep of the Darcy residual kernel at B = 32768 (2.7 GB working set >> 126 MB L2)."""
     from physicsinformeddiffusionmodels_b200 import ops
@@ -281,6 +305,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sampling', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -392,6 +417,9 @@ def main():
         extra['gpu_launches'] = calls_per_step * args.steps * world
         extra['launches_note'] = (f'{calls_per_step} libpidm entry-point calls per step per GPU (each issues 1-3 kernels); '
                                   'replayed from a CUDA graph' if not args.no_graph else 'eager')
+        if not args.no_sampling:
+            log('sampling loop (configs[3]): 250 ancestral steps, batch 16')
+            extra['sampling'] = sampling_bench(model, res, dev)
         if not args.no_cpu_baseline:
             cb = cpu_reference_steps(3, 1)
             extra['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

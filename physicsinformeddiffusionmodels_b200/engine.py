@@ -134,3 +134,82 @@ class TrainEngine:
         for p, o in zip(self.fp.params, self.fp.offsets):
             sd[name_of[id(p)]] = self.fp.ema[o:o + p.numel()].view(p.shape).clone()
         return sd
+
+
+class SampleEngine:
+    """B200-native ancestral sampling loop (reference denoising_utils.py:388-545 p_sample / p_sample_loop, called from
+    sample.py:145): the same per-step work as DenoisingDiffusion.p_sample -- x0 estimate through the residual object
+    (network call, or the DDIM walk when use_ddim_x0), Darcy residual, posterior step with sigma_t = sqrt(beta_t) --
+    but with the time index and the posterior coefficients living on the DEVICE, so that ONE captured CUDA graph is
+    replayed n_steps times and nothing is decided on the host inside the loop.  `DenoisingDiffusion.p_sample_loop`
+    remains the drop-in API (host-side step index, CPU trajectory); this is the throughput path."""
+
+    def __init__(self, model, diffusion, residuals, batch, image_shape=(2, 64, 64), surpress_noise=True, use_graph=True):
+        from .denoising_utils import _axpby, image_to_b_xy_c, generalized_b_xy_c_to_image
+        self._axpby, self._to_rows, self._to_img = _axpby, image_to_b_xy_c, generalized_b_xy_c_to_image
+        self.model, self.diffusion, self.residuals = model, diffusion, residuals
+        self.use_graph, self.surpress_noise = use_graph, surpress_noise
+        dd = diffusion.diff_dict
+        dev = dd['alphas'].device
+        self.n_steps = diffusion.n_steps
+        self.x = torch.zeros(batch, *image_shape, device=dev)
+        self.t = torch.zeros(batch, device=dev, dtype=torch.long)
+        self.residual = None
+        self.c1 = dd['posterior_mean_coef1'].float().contiguous()
+        self.c2 = dd['posterior_mean_coef2'].float().contiguous()
+        sig = dd['betas'].float().sqrt().contiguous()
+        if surpress_noise:
+            sig = sig.clone()
+            sig[0] = 0.
+        self.sigma = sig
+        self._graph = None
+
+    def _step_body(self):
+        with torch.no_grad():
+            x, t = self.x, self.t
+            out = self.residuals.compute_residual(((self._to_rows(x), t),), reduce='per-batch', return_model_out=True,
+                                                  sample=True, ddim_func=self.diffusion.ddim_sample_x0)
+            model_out = out['model_out']
+            if model_out.dim() == 3:
+                model_out = self._to_img(model_out)
+            z = torch.randn_like(x)                                     # drawn at every step, t == 0 included
+            new_x = self._axpby(self.c1[t].contiguous(), model_out.float(), self.c2[t].contiguous(), x,
+                                self.sigma[t].contiguous(), z)
+            if self.residual is None:
+                self.residual = torch.empty_like(out['residual'])
+            self.residual.copy_(out['residual'])
+            self.x.copy_(new_x)
+            self.t.sub_(1)
+
+    def _capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.t.fill_(self.n_steps - 1)
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.t.fill_(self.n_steps - 1)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._step_body()
+
+    def sample(self, x_init=None, trajectory=False):
+        """Runs the whole loop; returns (x_0 [B,C,P,P], residual of the last step [B,P*P,3]) as device tensors and,
+        if asked, the trajectory [n_steps+1,B,C,P,P] (device)."""
+        if self.use_graph and self._graph is None:
+            self._capture()
+        if x_init is None:
+            x_init = torch.randn_like(self.x)
+        self.x.copy_(x_init)
+        self.t.fill_(self.n_steps - 1)
+        traj = [self.x.clone()] if trajectory else None
+        for _ in range(self.n_steps):
+            if self.use_graph:
+                self._graph.replay()
+            else:
+                self._step_body()
+            if trajectory:
+                traj.append(self.x.clone())
+        return self.x, self.residual, (torch.stack(traj) if trajectory else None)

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-B="python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline"
+B="python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-sampling"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/launches_run.log 2>&1; echo "launch list rc=$?"

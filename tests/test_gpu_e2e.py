@@ -125,6 +125,30 @@ def test_sampling_loop_matches_reference(env, golden, monkeypatch):
     assert rel(aux['residual'], gd['residual']) < 5e-3      # residual amplifies x0 differences by 1/h^2
 
 
+def test_sample_engine_matches_reference_and_graph_replay(env, golden, monkeypatch):
+    """SampleEngine (device-side time index, one captured step replayed n_steps times) against the reference's
+    trajectory with its own draws injected, and CUDA-graph replay against the eager loop on identical noise."""
+    env['ops'].set_precision('fp32')
+    from physicsinformeddiffusionmodels_b200.engine import SampleEngine
+    gd = golden('sample_loop_6.pt')
+    model, diff, res = env['build'](n_steps=6)
+    model.eval()
+    it = iter(list(gd['noises']))
+    monkeypatch.setattr(torch, 'randn_like', lambda *a, **k: next(it).to(DEV))
+    x, r, traj = SampleEngine(model, diff, res, batch=1, use_graph=False).sample(x_init=gd['x_T'].to(DEV), trajectory=True)
+    monkeypatch.undo()
+    assert traj.shape[0] == 7
+    assert rel(traj[1], gd['x_after_first']) < 1e-4
+    assert rel(x, gd['x_final']) < 5e-4
+    assert rel(r, gd['residual']) < 5e-3
+    zfix = gd['noises'][0].to(DEV)
+    monkeypatch.setattr(torch, 'randn_like', lambda *a, **k: zfix)
+    xe = SampleEngine(model, diff, res, batch=1, use_graph=False).sample(x_init=gd['x_T'].to(DEV))[0].clone()
+    xg = SampleEngine(model, diff, res, batch=1, use_graph=True).sample(x_init=gd['x_T'].to(DEV))[0].clone()
+    monkeypatch.undo()
+    assert rel(xg, xe) < 1e-4, rel(xg, xe)
+
+
 def test_engine_training_steps_match_oracle(env):
     """3 optimizer steps of the flat-buffer engine (eager and CUDA-graph) vs the oracle's autograd + Adam + EMA."""
     O, ops = env['O'], env['ops']
