@@ -437,8 +437,8 @@ def main():
                                       'residual loss + clip + Adam + EMA (configs[1])',
                           'global_batch': world * B, 'per_gpu_batch': B, 'parallelism': f'dp{world}',
                           'cuda_graph': not args.no_graph,
-                          'l2': 'no explicit flush: one step streams >1 GB of activations (qkv alone 201 MB) through the '
-                                '126 MB L2, so weights/activations are cold at every layer',
+                          'l2': 'no explicit flush: one step streams >1 GB of activations and gradients (dqkv alone 201 MB) '
+                                'through the 126 MB L2, so weights/activations are cold at every layer',
                           'model_tflops_at_value': tflops, 'last_loss': last_loss},
                'clocks': clocks,
                'e2e': {'value': sps_e2e, 'unit': 'samples/s', 'ms_per_step': ms_e2e / args.steps,
@@ -447,7 +447,15 @@ def main():
         out.update(extra)
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: ncclCommDestroy while CUDA graphs that captured NCCL kernels are
+        # still alive has been observed to hang; the result is printed, every rank is past the barrier, and the OS
+        # reclaims the rest.
+        faulthandler.cancel_dump_traceback_later()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
