@@ -115,10 +115,11 @@ int pidm_colsum(const void* x, float* out, long long M, int C, int dtype, void* 
 
 /* ---- normalisations ------------------------------------------------------------------------------------ */
 /* Block.forward tail: GroupNorm(G) -> *(scale+1)+shift -> SiLU (src/unet_model.py:233-241).  scale_shift [B,2C] or NULL.
- * sums [B,G,2] (sum, sum of squares) is written here and consumed by the backward. */
-int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const float* beta, const float* scale_shift, void* y,
-                            float* sums, int stats_precomputed, int B, int HW, int C, int G, float eps, int dtype,
-                            void* stream);
+ * residual (optional, same shape as y) is added after the SiLU: the `h + x` of a ResnetBlock whose res_conv is the
+ * identity (:262).  sums [B,G,2] (sum, sum of squares) is written here and consumed by the backward. */
+int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const float* beta, const float* scale_shift,
+                            const void* residual, void* y, float* sums, int stats_precomputed, int B, int HW, int C, int G,
+                            float eps, int dtype, void* stream);
 /* workspace: float[B*C*2]; dgamma/dbeta ACCUMULATE; d_scale_shift [B,2C] overwritten (may be NULL);
  * dbias_of_producer (may be NULL): column sums of dx ACCUMULATED = bias gradient of the convolution that produced x. */
 int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const float* sums, const float* gamma, const float* beta,

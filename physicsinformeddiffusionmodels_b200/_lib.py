@@ -43,7 +43,7 @@ _SIGS = {
     'pidm_conv2d_wgrad_tc': [P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, L, L, P],
     'pidm_conv2d_wgrad_tc_supported': [I, I, I, I, I, I, I, I],
     'pidm_colsum': [P, P, L, I, I, P],
-    'pidm_groupnorm_silu_fwd': [P, P, P, P, P, P, I, I, I, I, I, F, I, P],
+    'pidm_groupnorm_silu_fwd': [P, P, P, P, P, P, P, I, I, I, I, I, F, I, P],
     'pidm_groupnorm_silu_bwd': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     'pidm_layernorm_c_fwd': [P, P, P, L, I, F, I, P],
     'pidm_layernorm_c_bwd': [P, P, P, P, P, P, L, I, F, I, P],

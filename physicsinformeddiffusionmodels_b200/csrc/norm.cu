@@ -61,7 +61,8 @@ __device__ __forceinline__ void gn_mean_rstd(const float* sums, int b, int g, in
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ ss /*[B,2C] or null*/,
-                                T* __restrict__ y, int HW, int C, int G, float eps, long long total8) {
+                                const T* __restrict__ res /*added after the SiLU, or null*/, T* __restrict__ y, int HW,
+                                int C, int G, float eps, long long total8) {
     const int oct = C / 8, cpg = C / G;
     const float inv_n = 1.f / ((float)cpg * (float)HW);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
@@ -83,6 +84,12 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict
                 if (ss) a = a * (ss[(size_t)b * 2 * C + c] + 1.f) + ss[(size_t)b * 2 * C + C + c];
                 v[h * 4 + k] = silu_f(a);
             }
+        }
+        if (res) {
+            float r[8];
+            ld8(res + i * 8, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += r[k];
         }
         st8(y + i * 8, v);
     }
@@ -577,8 +584,8 @@ static void gn_launch_dims(int HW, int C, int& block, int& chunks) {
 // sums [B,G,2] holds (sum, sum of squares) per (sample, group): computed here unless stats_precomputed (then it was
 // filled by the producing convolution's epilogue); it must be kept for backward.
 extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const float* beta, const float* scale_shift,
-                                       void* y, float* sums, int stats_precomputed, int B, int HW, int C, int G,
-                                       float eps, int dtype, void* stream) {
+                                       const void* residual, void* y, float* sums, int stats_precomputed, int B, int HW,
+                                       int C, int G, float eps, int dtype, void* stream) {
     if (int e = gn_check(C, G)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     int block, chunks;
@@ -590,7 +597,8 @@ extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const 
     PIDM_DISPATCH_DTYPE(dtype, {
         if (!stats_precomputed)
             gn_stats_kernel<T><<<dim3(chunks, B), block, 2 * G * sizeof(float), st>>>((const T*)x, sums, HW, C, G);
-        gn_apply_kernel<T><<<g2, 256, 0, st>>>((const T*)x, sums, gamma, beta, scale_shift, (T*)y, HW, C, G, eps, total8);
+        gn_apply_kernel<T><<<g2, 256, 0, st>>>((const T*)x, sums, gamma, beta, scale_shift, (const T*)residual, (T*)y, HW, C, G,
+                                               eps, total8);
     });
     PIDM_LAUNCH_CHECK("groupnorm_silu_fwd");
     return 0;

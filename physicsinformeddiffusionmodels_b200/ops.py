@@ -256,6 +256,17 @@ def side_stream_join():
         _SIDE['active'] = False
 
 
+_FORK = {'stream': None}
+
+
+def fork_stream():
+    """a second stream that has been made to wait for everything queued on the current one"""
+    if _FORK['stream'] is None:
+        _FORK['stream'] = torch.cuda.Stream()
+    _FORK['stream'].wait_stream(torch.cuda.current_stream())
+    return _FORK['stream']
+
+
 def _wgrad_stream(*operands):
     """stream handle for a wgrad-type launch whose operands are ready on the current stream"""
     if not _SIDE['active']:
@@ -317,15 +328,15 @@ def conv2d(x, weight, bias, spec, residual=None, gn_link=None, skip=None):
 # ----------------------------------------------------------------------------------------------
 class _GroupNormSilu(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, link):
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, link, residual):
         B, H, W, C = x.shape
         y = torch.empty_like(x)
         pre = link is not None and link.get('sums') is not None
         sums = link['sums'] if pre else torch.empty(B, groups, 2, device=x.device, dtype=torch.float32)
-        call('pidm_groupnorm_silu_fwd', x, gamma, beta, scale_shift, y, sums, 1 if pre else 0, B, H * W, C, groups, eps,
-             _code(x), stream())
+        call('pidm_groupnorm_silu_fwd', x, gamma, beta, scale_shift, residual, y, sums, 1 if pre else 0, B, H * W, C,
+             groups, eps, _code(x), stream())
         ctx.save_for_backward(x, gamma, beta, scale_shift, sums)
-        ctx.groups, ctx.eps, ctx.link = groups, eps, link
+        ctx.groups, ctx.eps, ctx.link, ctx.has_res = groups, eps, link, residual is not None
         return y
 
     @staticmethod
@@ -345,11 +356,13 @@ class _GroupNormSilu(torch.autograd.Function):
             link['dbias'] = dbias_ret             # picked up by the producing convolution's backward
         call('pidm_groupnorm_silu_bwd', x, dy, sums, gamma, beta, ss, dx, gg_buf, gb_buf, dss, dbias, ws, B, H * W, C,
              ctx.groups, ctx.eps, _code(x), stream())
-        return dx, gg_ret, gb_ret, dss, None, None, None
+        return dx, gg_ret, gb_ret, dss, None, None, None, (dy if ctx.has_res else None)
 
 
-def groupnorm_silu(x, gamma, beta, scale_shift, groups, eps=1e-5, gn_link=None):
-    return _GroupNormSilu.apply(x.contiguous(), gamma, beta, scale_shift, groups, eps, gn_link)
+def groupnorm_silu(x, gamma, beta, scale_shift, groups, eps=1e-5, gn_link=None, residual=None):
+    """residual (optional): added after the SiLU (ResnetBlock `h + x` with an identity res_conv)."""
+    return _GroupNormSilu.apply(x.contiguous(), gamma, beta, scale_shift, groups, eps, gn_link,
+                                None if residual is None else residual.contiguous())
 
 
 class _LayerNormC(torch.autograd.Function):

@@ -270,10 +270,11 @@ class Unet3D(nn.Module):
         h = ops.groupnorm_silu(h, block.block1.norm.weight, block.block1.norm.bias, ss, block.groups,
                                block.block1.norm.eps, gn_link=l1)
         h = self._conv(block.block2.proj, h, gn_link=l2)
+        if isinstance(block.res_conv, nn.Identity):       # `+ x` rides on the GroupNorm/SiLU pass
+            return ops.groupnorm_silu(h, block.block2.norm.weight, block.block2.norm.bias, None, block.groups,
+                                      block.block2.norm.eps, gn_link=l2, residual=ops.stash_grad(x, sk))
         h = ops.groupnorm_silu(h, block.block2.norm.weight, block.block2.norm.bias, None, block.groups,
                                block.block2.norm.eps, gn_link=l2)
-        if isinstance(block.res_conv, nn.Identity):
-            return ops.add(h, ops.stash_grad(x, sk))
         return self._conv(block.res_conv, x, residual=h, skip=('park', sk))
 
     def _linear_attention(self, res, x):
@@ -322,17 +323,22 @@ class Unet3D(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('Unet3D (B200 engine) needs CUDA tensors: no CPU fallback on the product path')
         dt = ops.act_dtype()
-        self._packer.refresh(dt)
+        # the weight re-packing (one launch over all layers) runs on a forked stream and overlaps the input layout
+        # change and the time-conditioning MLPs; it is joined before the first convolution
+        pack_stream = ops.fork_stream()
+        with torch.cuda.stream(pack_stream):
+            self._packer.refresh(dt)
         # pre-zeroed scratch for the GroupNorm statistics that the conv epilogues accumulate (<= 64 norms)
         ops.zero_pool_begin(64 * (x.shape[0] * self.groups * 2 + 32), x.device)
         h = ops.nchw_to_nhwc(x.float(), self._cin_pad, dt)
-        h = self._conv(self.init_conv, h)
-        r = h
         tm = self.time_mlp
         if time.dim() == 0:
             time = time.reshape(1).expand(x.shape[0])
         silu_t, _ = ops.time_embed(time, tm[1].weight, tm[1].bias, tm[3].weight, tm[3].bias)
         ss = ops.block_mlps(silu_t, self._mlp_table)
+        torch.cuda.current_stream().wait_stream(pack_stream)
+        h = self._conv(self.init_conv, h)
+        r = h
         skips = []
         for b1, b2, la, down in self.downs:
             h = self._resblock(b1, h, ss)
