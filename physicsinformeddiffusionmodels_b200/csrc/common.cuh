@@ -117,6 +117,34 @@ __device__ __forceinline__ float silu_grad_f(float z) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The step is a chain of ~420 dependent kernels, many of them a few microseconds long: the kernel-to-kernel launch
+// latency is a first-order cost.  Kernels launched through launch_pdl() may start while their predecessor is still
+// draining: they run their prologue (barrier init, TMEM allocation, tensor-map prefetch, parameter loads that do not
+// depend on the predecessor) and then block in pdl_wait() until the predecessor grid has completed and flushed.
+// Every kernel calls pdl_trigger() first so that ITS successor can be scheduled as early as possible.  Both
+// instructions are no-ops for kernels launched without the attribute.  PIDM_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // dispatch on activation dtype code
 #define PIDM_DISPATCH_DTYPE(dtype, ...)                                       \
     do {                                                                      \

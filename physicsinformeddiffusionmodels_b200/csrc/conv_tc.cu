@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kc_per_tap = p.Cin / BK;
     const int total_tiles = p.m_tiles * p.n_tiles * p.n_classes;
+    pdl_trigger();
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // prologue done; everything below reads what the previous kernel wrote
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ===== TMA producers: three warps, one elected lane each, K-step `git` belongs to producer git % 3 ===========
@@ -594,7 +596,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
                                        TC_SMEM_BYTES));
         attr = true;
     }
-    conv_tc_kernel<BN, BK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mx, mw, p);
+    PIDM_CUDA(launch_pdl(conv_tc_kernel<BN, BK>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mx, mw, p));
     PIDM_LAUNCH_CHECK("conv2d_tc");
     return 0;
 }

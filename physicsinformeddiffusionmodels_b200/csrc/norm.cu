@@ -65,6 +65,8 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict
                                 int C, int G, float eps, long long total8) {
     const int oct = C / 8, cpg = C / G;
     const float inv_n = 1.f / ((float)cpg * (float)HW);
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
          i += (long long)gridDim.x * blockDim.x) {
         int o = (int)(i % oct);
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_bwd_cluster_kernel(
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char gsm[];
     float* part = reinterpret_cast<float*>(gsm);           // [C][2] partial sums of this CTA
     float* Sf = part + 2 * C;                              // [C][2] sums over the whole sample
@@ -474,6 +478,8 @@ __global__ void __launch_bounds__(256) ln1_kernel(const T* __restrict__ x, const
                                                   float* __restrict__ dgamma, const T* __restrict__ res, long long M,
                                                   int C, float eps) {
     extern __shared__ float sdg[];  // [C] (BWD only)
+    pdl_trigger();
+    pdl_wait();
     const int L = C / 8;
     const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L, gpw = 32 / L;
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
@@ -597,8 +603,8 @@ extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const 
     PIDM_DISPATCH_DTYPE(dtype, {
         if (!stats_precomputed)
             gn_stats_kernel<T><<<dim3(chunks, B), block, 2 * G * sizeof(float), st>>>((const T*)x, sums, HW, C, G);
-        gn_apply_kernel<T><<<g2, 256, 0, st>>>((const T*)x, sums, gamma, beta, scale_shift, (const T*)residual, (T*)y, HW, C, G,
-                                               eps, total8);
+        PIDM_CUDA(launch_pdl(gn_apply_kernel<T>, dim3(g2), dim3(256), 0, st, (const T*)x, (const float*)sums, gamma, beta,
+                             scale_shift, (const T*)residual, (T*)y, HW, C, G, eps, total8));
     });
     PIDM_LAUNCH_CHECK("groupnorm_silu_fwd");
     return 0;
@@ -632,10 +638,12 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
             cfg.blockDim = dim3((unsigned)block);
             cfg.dynamicSmemBytes = smem;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
             static bool attr_done[2] = {false, false};
             PIDM_DISPATCH_DTYPE(dtype, {
                 const int di = dtype == PIDM_BF16 ? 1 : 0;
@@ -674,8 +682,9 @@ extern "C" int pidm_layernorm_c_fwd(const void* x, const float* gamma, void* y, 
     if (L == oct) {          // one octet per lane: register-resident kernel
         long long g1 = (M + (32 / L) * 8 * LN_UNR - 1) / ((32 / L) * 8 * LN_UNR);
         int grid1 = (int)(g1 < 148 * 8 ? (g1 < 1 ? 1 : g1) : 148 * 8);
-        PIDM_DISPATCH_DTYPE(dtype, (ln1_kernel<T, false><<<grid1, 256, 0, (cudaStream_t)stream>>>(
-                                       (const T*)x, nullptr, gamma, (T*)y, nullptr, nullptr, M, C, eps)));
+        PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(ln1_kernel<T, false>, dim3(grid1), dim3(256), 0, (cudaStream_t)stream,
+                                                        (const T*)x, (const T*)nullptr, gamma, (T*)y, (float*)nullptr,
+                                                        (const T*)nullptr, M, C, eps)));
         PIDM_LAUNCH_CHECK("layernorm_c_fwd");
         return 0;
     }
@@ -697,8 +706,9 @@ extern "C" int pidm_layernorm_c_bwd(const void* x, const void* dy, const float* 
     if (L == oct) {
         long long g1 = (M + (32 / L) * 8 * LN_UNR - 1) / ((32 / L) * 8 * LN_UNR);
         int grid1 = (int)(g1 < 148 * 4 ? (g1 < 1 ? 1 : g1) : 148 * 4);
-        PIDM_DISPATCH_DTYPE(dtype, (ln1_kernel<T, true><<<grid1, 256, C * sizeof(float), (cudaStream_t)stream>>>(
-                                       (const T*)x, (const T*)dy, gamma, (T*)dx, dgamma, (const T*)dx_residual, M, C, eps)));
+        PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(ln1_kernel<T, true>, dim3(grid1), dim3(256), C * sizeof(float),
+                                                        (cudaStream_t)stream, (const T*)x, (const T*)dy, gamma, (T*)dx,
+                                                        dgamma, (const T*)dx_residual, M, C, eps)));
         PIDM_LAUNCH_CHECK("layernorm_c_bwd");
         return 0;
     }

@@ -4,12 +4,19 @@
 //   EMA shadow update mu=0.99                                       (denoising_utils.py:174-177, main.py:178-179)
 // and the error plumbing shared by all translation units.
 #include "common.cuh"
+#include <stdlib.h>
 #include "pidm.h"
 #include <stdarg.h>
 
 namespace pidm {
 
 thread_local char g_last_error[512] = {0};
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PIDM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;

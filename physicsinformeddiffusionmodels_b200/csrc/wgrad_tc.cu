@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     const int mt = blockIdx.x, n0 = blockIdx.y * NP;
     const int chunks = p.Cin / ATOM_A;                 // channel chunks per tap
     const int n_pairs = p.KH * p.KW * chunks;          // (tap, chunk) pairs = M' extent / ATOM_A
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (n_iters > 0) {
         if (warp == 0) {
@@ -241,6 +243,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dy, float* __restrict__ out, long long M, int C) {
     extern __shared__ float sacc[];   // [C]
+    pdl_trigger();
+    pdl_wait();
     const int oct = C / 8;
     const int o = threadIdx.x % oct, r0 = threadIdx.x / oct, rows = blockDim.x / oct;
     for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
@@ -320,7 +324,7 @@ static int wg_launch(const CUtensorMap& mx, const CUtensorMap& my, const WgParam
                                        Cfg::SMEM_BYTES));
         attr = true;
     }
-    wgrad_tc_kernel<NP, AA, AB><<<grid, WG_THREADS, Cfg::SMEM_BYTES, st>>>(mx, my, p);
+    PIDM_CUDA(launch_pdl(wgrad_tc_kernel<NP, AA, AB>, grid, dim3(WG_THREADS), Cfg::SMEM_BYTES, st, mx, my, p));
     PIDM_LAUNCH_CHECK("conv2d_wgrad_tc");
     return 0;
 }
@@ -392,8 +396,8 @@ extern "C" int pidm_colsum(const void* x, float* out, long long M, int C, int dt
     int grid1 = (int)((M + rows * 8 - 1) / (rows * 8));
     if (grid1 > 148 * 4) grid1 = 148 * 4;
     if (grid1 < 1) grid1 = 1;
-    PIDM_DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid1, oct * rows, C * sizeof(float), (cudaStream_t)stream>>>(
-                                   (const T*)x, out, M, C)));
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(colsum_kernel<T>, dim3(grid1), dim3(oct * rows), C * sizeof(float),
+                                                    (cudaStream_t)stream, (const T*)x, out, M, C)));
     PIDM_LAUNCH_CHECK("colsum");
     return 0;
 }

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) wgrad3_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     const int c0 = blockIdx.x * 32, n0 = blockIdx.y * NP;
     const int pt_begin = blockIdx.z * p.tiles_per_split;
     int pt_end = pt_begin + p.tiles_per_split;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) wgrad3_kernel(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (n_iters > 0) {
         if (warp == 0) {
@@ -299,7 +301,7 @@ static int w3_launch(const CUtensorMap& mx, const CUtensorMap& my, const W3Param
                                        Cfg::SMEM_BYTES));
         attr = true;
     }
-    wgrad3_kernel<NP, AB, RG><<<grid, W3_THREADS, Cfg::SMEM_BYTES, st>>>(mx, my, p);
+    PIDM_CUDA(launch_pdl(wgrad3_kernel<NP, AB, RG>, grid, dim3(W3_THREADS), Cfg::SMEM_BYTES, st, mx, my, p));
     PIDM_LAUNCH_CHECK("conv2d_wgrad_tc(3x3)");
     return 0;
 }
