@@ -11,6 +11,7 @@
 //     so no extra pass over N is needed for the k-softmax Jacobian.
 // (2) Mid-block softmax attention over <= 64 tokens (Attention.forward, unet_model.py:341-367): one CTA per
 //     (sample, head), everything in shared memory.
+#define PIDM_PDL_GROUP 1
 #include "common.cuh"
 #include "pidm.h"
 
@@ -26,6 +27,8 @@ constexpr int LA_TN = 64;         // pixel tile of the context kernels
 template <typename T>
 __global__ void la_kstats_kernel(const T* __restrict__ qkv, float* __restrict__ part /*[B][chunks][HID][2]*/, int N,
                                  int HID, int rows_per_chunk) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float skm[];                 // [groups][HID] max, then [groups][HID] sums
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int oct = HID / 8;
@@ -79,6 +82,8 @@ __global__ void __launch_bounds__(256) la_context_kernel(const T* __restrict__ q
                                                          float* __restrict__ kmax, float* __restrict__ kzinv,
                                                          float* __restrict__ ctx, int N, int heads,
                                                          int rows_per_chunk, float scale) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sM[DH], sZi[DH];
     __shared__ __align__(16) float Wt[LA_TN][DH + 1];
     __shared__ __align__(16) float Vt[LA_TN][DH];
@@ -169,6 +174,8 @@ __global__ void __launch_bounds__(256) la_context_kernel(const T* __restrict__ q
 template <typename T>
 __global__ void la_out_kernel(const T* __restrict__ qkv, const float* __restrict__ ctx, T* __restrict__ out, int N,
                               int heads, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float sctx[];   // [heads][32][32]
     const int HID = heads * DH;
     const long long pix0 = (long long)blockIdx.x * 32;
@@ -216,6 +223,8 @@ __global__ void __launch_bounds__(32 * LA_HB) la_bwd_pixel_kernel(const T* __res
                                                                   const float* __restrict__ kmax,
                                                                   const float* __restrict__ kzinv,
                                                                   T* __restrict__ dqkv, int N, int heads, float scale) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float sctx[LA_HB][DH][DH];
     __shared__ __align__(16) float sdctx[LA_HB][DH][DH];
     __shared__ float scd[LA_HB][DH], sM[LA_HB][DH], sZi[LA_HB][DH];
@@ -355,6 +364,8 @@ __device__ __forceinline__ void attn_load_scores(const T* __restrict__ qkv, S& s
 template <typename T>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n, int heads,
                                                        float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     AttnSmemF& sm = *reinterpret_cast<AttnSmemF*>(raw);
     const int h = blockIdx.x, b = blockIdx.y, HID = heads * DH, tid = threadIdx.x;
@@ -372,6 +383,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
 template <typename T>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout,
                                                        T* __restrict__ dqkv, int n, int heads, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     AttnSmemB& sm = *reinterpret_cast<AttnSmemB*>(raw);
     const int h = blockIdx.x, b = blockIdx.y, HID = heads * DH, tid = threadIdx.x;
@@ -454,7 +467,7 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const float scale = 0.17677669529663687f;   // 32^-0.5
     PIDM_CUDA(cudaMemsetAsync(ctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
     if (dtype == PIDM_BF16 && heads == 8 && N % 64 == 0) {
-        la_kstats_kernel<__nv_bfloat16><<<dim3(chunks, B), 256, la_kstats_smem(HID), st>>>((const __nv_bfloat16*)qkv, workspace, N, HID, rpc);
+        PIDM_CUDA(launch_pdl(la_kstats_kernel<__nv_bfloat16>, dim3(dim3(chunks, B)), dim3(256), (size_t)(la_kstats_smem(HID)), st, (const __nv_bfloat16*)qkv, workspace, N, HID, rpc));
         if (int e = la_mma_ctx(0, qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, B, N, scale, st)) return e;
         if (int e = la_mma_out(qkv, ctx, out, B, N, scale, st)) return e;
         PIDM_LAUNCH_CHECK("linattn_fwd");
@@ -463,11 +476,9 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const int cchunks = (N + 255) / 256 > 16 ? 16 : (N + 255) / 256;
     const int crpc = ((N + cchunks - 1) / cchunks + LA_TN - 1) / LA_TN * LA_TN;
     PIDM_DISPATCH_DTYPE(dtype, {
-        la_kstats_kernel<T><<<dim3(chunks, B), la_kstats_block(HID), la_kstats_smem(HID), st>>>((const T*)qkv, workspace, N, HID, rpc);
-        la_context_kernel<T, 0><<<dim3((N + crpc - 1) / crpc, heads, B), 256, 0, st>>>(
-            (const T*)qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, N, heads, crpc, scale);
-        la_out_kernel<T><<<(unsigned)((long long)B * N / 32), 32 * heads, heads * DH * DH * sizeof(float), st>>>(
-            (const T*)qkv, ctx, (T*)out, N, heads, scale);
+        PIDM_CUDA(launch_pdl(la_kstats_kernel<T>, dim3(dim3(chunks, B)), dim3(la_kstats_block(HID)), (size_t)(la_kstats_smem(HID)), st, (const T*)qkv, workspace, N, HID, rpc));
+        PIDM_CUDA(launch_pdl(la_context_kernel<T, 0>, dim3(dim3((N + crpc - 1) / crpc, heads, B)), dim3(256), (size_t)(0), st, (const T*)qkv, nullptr, workspace, chunks, kmax, kzinv, ctx, N, heads, crpc, scale));
+        PIDM_CUDA(launch_pdl(la_out_kernel<T>, dim3((unsigned)((long long)B * N / 32)), dim3(32 * heads), (size_t)(heads * DH * DH * sizeof(float)), st, (const T*)qkv, ctx, (T*)out, N, heads, scale));
     });
     PIDM_LAUNCH_CHECK("linattn_fwd");
     return 0;
@@ -492,10 +503,8 @@ extern "C" int pidm_linattn_bwd(const void* qkv, const void* dout, const float* 
     const int cchunks = (N + 255) / 256 > 16 ? 16 : (N + 255) / 256;
     const int crpc = ((N + cchunks - 1) / cchunks + LA_TN - 1) / LA_TN * LA_TN;
     PIDM_DISPATCH_DTYPE(dtype, {
-        la_context_kernel<T, 1><<<dim3((N + crpc - 1) / crpc, heads, B), 256, 0, st>>>(
-            (const T*)qkv, (const T*)dout, nullptr, 0, nullptr, nullptr, dctx, N, heads, crpc, scale);
-        la_bwd_pixel_kernel<T><<<dim3((unsigned)((long long)B * N / 32), heads / LA_HB), 32 * LA_HB, 0, st>>>(
-            (const T*)qkv, (const T*)dout, ctx, dctx, kmax, kzinv, (T*)dqkv, N, heads, scale);
+        PIDM_CUDA(launch_pdl(la_context_kernel<T, 1>, dim3(dim3((N + crpc - 1) / crpc, heads, B)), dim3(256), (size_t)(0), st, (const T*)qkv, (const T*)dout, nullptr, 0, nullptr, nullptr, dctx, N, heads, crpc, scale));
+        PIDM_CUDA(launch_pdl(la_bwd_pixel_kernel<T>, dim3(dim3((unsigned)((long long)B * N / 32), heads / LA_HB)), dim3(32 * LA_HB), (size_t)(0), st, (const T*)qkv, (const T*)dout, ctx, dctx, kmax, kzinv, (T*)dqkv, N, heads, scale));
     });
     PIDM_LAUNCH_CHECK("linattn_bwd");
     return 0;
@@ -512,8 +521,8 @@ extern "C" int pidm_attn_fwd(const void* qkv, void* out, int B, int n_tokens, in
                                            (int)sizeof(AttnSmemF)));
             flag = true;
         }
-        attn_fwd_kernel<T><<<dim3(heads, B), 256, sizeof(AttnSmemF), (cudaStream_t)stream>>>((const T*)qkv, (T*)out,
-                                                                                            n_tokens, heads, scale);
+        PIDM_CUDA(launch_pdl(attn_fwd_kernel<T>, dim3(dim3(heads, B)), dim3(256), (size_t)(sizeof(AttnSmemF)), (cudaStream_t)stream, (const T*)qkv, (T*)out,
+                                                                                            n_tokens, heads, scale));
     });
     PIDM_LAUNCH_CHECK("attn_fwd");
     return 0;
@@ -531,8 +540,7 @@ extern "C" int pidm_attn_bwd(const void* qkv, const void* dout, void* dqkv, int 
                                            (int)sizeof(AttnSmemB)));
             flag = true;
         }
-        attn_bwd_kernel<T><<<dim3(heads, B), 256, sizeof(AttnSmemB), (cudaStream_t)stream>>>(
-            (const T*)qkv, (const T*)dout, (T*)dqkv, n_tokens, heads, scale);
+        PIDM_CUDA(launch_pdl(attn_bwd_kernel<T>, dim3(dim3(heads, B)), dim3(256), (size_t)(sizeof(AttnSmemB)), (cudaStream_t)stream, (const T*)qkv, (const T*)dout, (T*)dqkv, n_tokens, heads, scale));
     });
     PIDM_LAUNCH_CHECK("attn_bwd");
     return 0;

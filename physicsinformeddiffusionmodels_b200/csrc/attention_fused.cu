@@ -9,6 +9,7 @@
 // All intermediate tiles stay in registers: accumulator fragments are converted to A fragments directly and to
 // transposed (K-major) fragments with movmatrix; only xn / dout tiles and the output staging touch shared memory.
 // The two paths differ only by the bf16 rounding of the (here never materialised) q, k, v.
+#define PIDM_PDL_GROUP 1
 #include "common.cuh"
 #include "mma_util.cuh"
 #include "pidm.h"
@@ -103,6 +104,8 @@ constexpr int LFS_STAGES = 4;
 __global__ void __launch_bounds__(256) laf_kmax_kernel(const __nv_bfloat16* __restrict__ xn,
                                                        const __nv_bfloat16* __restrict__ W, float* __restrict__ part,
                                                        int N, int rows_per_chunk) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * (LFS_STAGES * LW_TILE);
@@ -151,6 +154,8 @@ __global__ void __launch_bounds__(256) laf_kmax_kernel(const __nv_bfloat16* __re
 
 // ctx[b][h][d][:] *= 1 / Z[b][h][d]  and  kzinv = 1 / Z, after the context kernel has accumulated both
 __global__ void laf_finalize_kernel(float* __restrict__ ctx, float* __restrict__ kzinv, int n_rows) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const float zi = 1.f / kzinv[row];
@@ -173,6 +178,8 @@ __global__ void __launch_bounds__(256) laf_ctx_kernel(const __nv_bfloat16* __res
                                                       const __nv_bfloat16* __restrict__ dout, const float* __restrict__ part,
                                                       int n_stat_chunks, float* __restrict__ kmax, float* __restrict__ kzinv,
                                                       float* __restrict__ ctx, int N, int chunk_px, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     constexpr int LFC_STAGES = LfcCfg<MODE>::STAGES, LFC_STAGE_ELEMS = LfcCfg<MODE>::STAGE_ELEMS;
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
@@ -311,6 +318,8 @@ constexpr int LFO_STAGES = 4;
 __global__ void __launch_bounds__(256) laf_out_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __restrict__ W,
                                                       const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out, int N,
                                                       int chunk_px, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * ((LFO_STAGES + 1) * LW_TILE);
@@ -381,6 +390,8 @@ __global__ void __launch_bounds__(256) laf_bwd_kernel(const __nv_bfloat16* __res
                                                       const float* __restrict__ dctx, const float* __restrict__ kmax,
                                                       const float* __restrict__ kzinv, __nv_bfloat16* __restrict__ dqkv,
                                                       int N, int chunk_px, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * (LFB_STAGES * LFB_STAGE_ELEMS + LFB_OUT_ELEMS);
@@ -577,13 +588,13 @@ extern "C" int pidm_linattn_fused_fwd(const void* xn, const void* w_qkv, void* o
     const int chunks = laf_stat_chunks(N);
     const int rpc = N / chunks;
     PIDM_REQUIRE(rpc % 32 == 0 && rpc * chunks == N, "linattn_fused: bad statistics chunking for N=%d", N);
-    laf_kmax_kernel<<<dim3(chunks, B), 256, LAF_STATS_SMEM, st>>>(x, w, workspace, N, rpc);
+    PIDM_CUDA(launch_pdl(laf_kmax_kernel, dim3(dim3(chunks, B)), dim3(256), (size_t)(LAF_STATS_SMEM), st, x, w, workspace, N, rpc));
     const int cpx = laf_chunk_px(B, N, 2);
-    laf_ctx_kernel<0><<<dim3((N + cpx - 1) / cpx, B), 256, LfcCfg<0>::SMEM, st>>>(x, w, nullptr, workspace, chunks, kmax, kzinv,
-                                                                             ctx, N, cpx, scale);
-    laf_finalize_kernel<<<(B * LM_HID + 7) / 8, 256, 0, st>>>(ctx, kzinv, B * LM_HID);
+    PIDM_CUDA(launch_pdl(laf_ctx_kernel<0>, dim3(dim3((N + cpx - 1) / cpx, B)), dim3(256), (size_t)(LfcCfg<0>::SMEM), st, x, w, nullptr, workspace, chunks, kmax, kzinv,
+                                                                             ctx, N, cpx, scale));
+    PIDM_CUDA(launch_pdl(laf_finalize_kernel, dim3((B * LM_HID + 7) / 8), dim3(256), (size_t)(0), st, ctx, kzinv, B * LM_HID));
     const int opx = laf_chunk_px(B, N, 2);
-    laf_out_kernel<<<dim3((N + opx - 1) / opx, B), 256, LAF_OUT_SMEM, st>>>(x, w, ctx, (__nv_bfloat16*)out, N, opx, scale);
+    PIDM_CUDA(launch_pdl(laf_out_kernel, dim3(dim3((N + opx - 1) / opx, B)), dim3(256), (size_t)(LAF_OUT_SMEM), st, x, w, ctx, (__nv_bfloat16*)out, N, opx, scale));
     PIDM_LAUNCH_CHECK("linattn_fused_fwd");
     return 0;
 }
@@ -600,11 +611,11 @@ extern "C" int pidm_linattn_fused_bwd(const void* xn, const void* w_qkv, const v
     const __nv_bfloat16* w = (const __nv_bfloat16*)w_qkv;
     PIDM_CUDA(cudaMemsetAsync(dctx, 0, (size_t)B * LM_HEADS * LM_D * LM_D * sizeof(float), st));
     const int cpx = laf_chunk_px(B, N, 2);
-    laf_ctx_kernel<1><<<dim3((N + cpx - 1) / cpx, B), 256, LfcCfg<1>::SMEM, st>>>(x, w, (const __nv_bfloat16*)dout, nullptr, 0,
-                                                                             nullptr, nullptr, dctx, N, cpx, scale);
+    PIDM_CUDA(launch_pdl(laf_ctx_kernel<1>, dim3(dim3((N + cpx - 1) / cpx, B)), dim3(256), (size_t)(LfcCfg<1>::SMEM), st, x, w, (const __nv_bfloat16*)dout, nullptr, 0,
+                                                                             nullptr, nullptr, dctx, N, cpx, scale));
     const int bpx = laf_chunk_px(B, N, 1);
-    laf_bwd_kernel<<<dim3((N + bpx - 1) / bpx, B), 256, LAF_BWD_SMEM, st>>>(x, w, (const __nv_bfloat16*)dout, ctx, dctx, kmax,
-                                                                          kzinv, (__nv_bfloat16*)dqkv, N, bpx, scale);
+    PIDM_CUDA(launch_pdl(laf_bwd_kernel, dim3(dim3((N + bpx - 1) / bpx, B)), dim3(256), (size_t)(LAF_BWD_SMEM), st, x, w, (const __nv_bfloat16*)dout, ctx, dctx, kmax,
+                                                                          kzinv, (__nv_bfloat16*)dqkv, N, bpx, scale));
     PIDM_LAUNCH_CHECK("linattn_fused_bwd");
     return 0;
 }

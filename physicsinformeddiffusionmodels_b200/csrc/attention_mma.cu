@@ -11,6 +11,7 @@
 //   la_ctx_mma<1>: dctx[h][d][e] += sum_n softmax_d(q[n,:])[d]*s * dout[n,e]
 //   la_out_mma   : out[n,h,e]     = sum_d softmax_d(q[n,:])[d]*s * ctx[h][d][e]
 //   la_bwd_mma   : dq, dk, dv per pixel from dout, ctx, dctx and the saved column statistics
+#define PIDM_PDL_GROUP 1
 #include "common.cuh"
 #include "mma_util.cuh"
 #include "pidm.h"
@@ -28,6 +29,8 @@ __global__ void __launch_bounds__(256) la_ctx_mma_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ part, int n_stat_chunks,
                                                          float* __restrict__ kmax, float* __restrict__ kzinv,
                                                          float* __restrict__ ctx, int N, int chunk_px, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * (LC_STAGES * 2 * LW_TILE);
@@ -128,6 +131,8 @@ constexpr int LO_STAGES = 4;
 __global__ void __launch_bounds__(256) la_out_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                          const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out,
                                                          int N, int chunk_px, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * (LO_STAGES * LW_TILE);
@@ -204,6 +209,8 @@ __global__ void __launch_bounds__(256) la_bwd_mma_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ ctx, const float* __restrict__ dctx,
                                                          const float* __restrict__ kmax, const float* __restrict__ kzinv,
                                                          __nv_bfloat16* __restrict__ dqkv, int N, int chunk_px, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char raw[];
     const int b = blockIdx.y, chunk = blockIdx.x, lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(raw) + (size_t)h * (LB_STAGES * LB_TILE);
@@ -366,11 +373,11 @@ int la_mma_ctx(int mode, const void* qkv, const void* dout, const float* part, i
     const int cpx = la_chunk_px(B, N, 2);
     dim3 grid((N + cpx - 1) / cpx, B);
     if (mode == 0)
-        la_ctx_mma_kernel<0><<<grid, 256, LA_CTX_SMEM, st>>>((const __nv_bfloat16*)qkv, nullptr, part, n_stat_chunks, kmax,
-                                                            kzinv, ctx, N, cpx, scale);
+        PIDM_CUDA(launch_pdl(la_ctx_mma_kernel<0>, dim3(grid), dim3(256), (size_t)(LA_CTX_SMEM), st, (const __nv_bfloat16*)qkv, nullptr, part, n_stat_chunks, kmax,
+                                                            kzinv, ctx, N, cpx, scale));
     else
-        la_ctx_mma_kernel<1><<<grid, 256, LA_CTX_SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, nullptr,
-                                                            0, nullptr, nullptr, ctx, N, cpx, scale);
+        PIDM_CUDA(launch_pdl(la_ctx_mma_kernel<1>, dim3(grid), dim3(256), (size_t)(LA_CTX_SMEM), st, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, nullptr,
+                                                            0, nullptr, nullptr, ctx, N, cpx, scale));
     PIDM_LAUNCH_CHECK("la_ctx_mma");
     return 0;
 }
@@ -378,7 +385,7 @@ int la_mma_out(const void* qkv, const float* ctx, void* out, int B, int N, float
     if (int e = la_mma_attrs()) return e;
     const int cpx = la_chunk_px(B, N, 2);
     dim3 grid((N + cpx - 1) / cpx, B);
-    la_out_mma_kernel<<<grid, 256, LA_OUT_SMEM, st>>>((const __nv_bfloat16*)qkv, ctx, (__nv_bfloat16*)out, N, cpx, scale);
+    PIDM_CUDA(launch_pdl(la_out_mma_kernel, dim3(grid), dim3(256), (size_t)(LA_OUT_SMEM), st, (const __nv_bfloat16*)qkv, ctx, (__nv_bfloat16*)out, N, cpx, scale));
     PIDM_LAUNCH_CHECK("la_out_mma");
     return 0;
 }
@@ -387,8 +394,8 @@ int la_mma_bwd(const void* qkv, const void* dout, const float* ctx, const float*
     if (int e = la_mma_attrs()) return e;
     const int cpx = la_chunk_px(B, N, 2);
     dim3 grid((N + cpx - 1) / cpx, B);
-    la_bwd_mma_kernel<<<grid, 256, LA_BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ctx, dctx, kmax,
-                                                     kzinv, (__nv_bfloat16*)dqkv, N, cpx, scale);
+    PIDM_CUDA(launch_pdl(la_bwd_mma_kernel, dim3(grid), dim3(256), (size_t)(LA_BWD_SMEM), st, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ctx, dctx, kmax,
+                                                     kzinv, (__nv_bfloat16*)dqkv, N, cpx, scale));
     PIDM_LAUNCH_CHECK("la_bwd_mma");
     return 0;
 }

@@ -127,7 +127,14 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-bool pdl_enabled();
+// PIDM_PDL = bit mask of kernel groups launched with the attribute: 0 conv / wgrad / norm, 1 attention,
+// 2 element-wise, 3 linear / optimizer / residual.  Default 1: on one B200 the step takes 4.34 ms without PDL, 4.02 ms
+// with group 0 only, 4.15 ms with all groups (kernels whose first instruction is the wait gain nothing and their
+// early-scheduled CTAs only take SM slots from the forked weight-gradient stream).
+#ifndef PIDM_PDL_GROUP
+#define PIDM_PDL_GROUP 0
+#endif
+bool pdl_enabled(int group);
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -141,7 +148,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl_enabled(PIDM_PDL_GROUP) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -14,6 +14,7 @@
 // written with 128-bit coalesced stores (48 contiguous bytes per thread, 1536 per warp).
 // Loss-fused variants never materialise r: warp-shuffle + one atomic per CTA for the sums, and the
 // gradient is produced in the same pass (adjoint stencils applied to the residual plane held in smem).
+#define PIDM_PDL_GROUP 3
 #include "common.cuh"
 #include "pidm.h"
 #include <stddef.h>
@@ -229,7 +230,9 @@ __global__ void __launch_bounds__(DARCY_THREADS) darcy_kernel(
         mbar_init(&S.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();                 // barriers are set up; x0hat is produced by the previous kernel
     const uint32_t bytes = 2 * PP * sizeof(float);
     int n_local = 0;
     // prologue: first sample of this CTA
@@ -366,6 +369,8 @@ __global__ void __launch_bounds__(DARCY_THREADS) darcy_kernel(
 // single derivative field (StencilGradients.forward, grad_utils.py:161-175); global-memory version, forward only
 __global__ void fd_stencil_kernel(const float* __restrict__ u, float* __restrict__ out, int planes, int mode,
                                   float inv_h0, float inv_h1) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float su[PP];
     __shared__ float st[PP];
     for (int pl = blockIdx.x; pl < planes; pl += gridDim.x) {
@@ -423,9 +428,9 @@ static int launch_darcy(const float* x0hat, const float* fs, float* residual, co
     const int ctas_per_sm = (int)(220 * 1024 / smem);        // smem-limited residency
     int grid = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     if (grid > B) grid = B;
-    darcy_kernel<MODE><<<grid, DARCY_THREADS, smem, stream>>>(x0hat, fs, residual, cot, grad_x0hat, target, model_out,
+    PIDM_CUDA(launch_pdl(darcy_kernel<MODE>, dim3(grid), dim3(DARCY_THREADS), (size_t)(smem), stream, x0hat, fs, residual, cot, grad_x0hat, target, model_out,
                                                              grad_model_out, t, p2w, pvar, c_data, c_res, sums, B,
-                                                             make_geom(domain_length, reverse_d1, pixels_at_boundary));
+                                                             make_geom(domain_length, reverse_d1, pixels_at_boundary)));
     PIDM_LAUNCH_CHECK("darcy_kernel");
     return 0;
 }
@@ -439,7 +444,7 @@ extern "C" int pidm_fd_stencil(const float* u, float* out, int planes, int pixel
     PIDM_REQUIRE(pixels == P, "fd_stencil is built for %d x %d fields (got %d)", P, P, pixels);
     PIDM_REQUIRE(mode >= 0 && mode <= 4, "fd_stencil: mode must be 0..4 (d_d0, d_d1, d_d00, d_d11, d_d01)");
     int grid = planes < 148 * 4 ? planes : 148 * 4;
-    fd_stencil_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, out, planes, mode, 1.f / d0, 1.f / d1);
+    PIDM_CUDA(launch_pdl(fd_stencil_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, u, out, planes, mode, 1.f / d0, 1.f / d1));
     PIDM_LAUNCH_CHECK("fd_stencil");
     return 0;
 }

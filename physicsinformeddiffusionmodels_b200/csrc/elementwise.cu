@@ -1,6 +1,7 @@
 // HBM-bound element-wise pieces of the PIDM step: q_sample, ancestral posterior step, layout changes
 // (NCHW fp32 <-> NHWC activations), channel concat/split, residual add, and the tiny-N output head
 // (final 1x1 conv -> NCHW fp32, optional sigmoid on the last channel).  128-bit vectorised accesses.
+#define PIDM_PDL_GROUP 2
 #include "common.cuh"
 #include "pidm.h"
 
@@ -10,6 +11,8 @@ namespace pidm {
 __global__ void qsample_kernel(const float4* __restrict__ x0, const float4* __restrict__ eps,
                                const long long* __restrict__ t, const float* __restrict__ sa,
                                const float* __restrict__ sb, float4* __restrict__ xt, int per_sample4, long long total4) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
         int b = (int)(i / per_sample4);
@@ -24,6 +27,8 @@ __global__ void qsample_kernel(const float4* __restrict__ x0, const float4* __re
 __global__ void posterior_kernel(const float4* __restrict__ xt, const float4* __restrict__ x0p,
                                  const float4* __restrict__ z, float4* __restrict__ out, float c1, float c2, float sig,
                                  long long total4) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
         float4 a = xt[i], b = x0p[i], n = z[i];
@@ -36,7 +41,9 @@ __global__ void posterior_kernel(const float4* __restrict__ xt, const float4* __
 // one thread per pixel: C coalesced plane reads, one channel-padded NHWC row written with 16-byte stores
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int Cpad,
-                                    long long n_pix) {  // n_pix = B*HW, Cpad % 8 == 0
+                                    long long n_pix) {
+    pdl_trigger();
+    pdl_wait();  // n_pix = B*HW, Cpad % 8 == 0
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < n_pix;
          pix += (long long)gridDim.x * blockDim.x) {
         const long long b = pix / HW;
@@ -53,7 +60,9 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 }
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW, int Cpad,
-                                    long long total) {  // total = B*C*HW
+                                    long long total) {
+    pdl_trigger();
+    pdl_wait();  // total = B*C*HW
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         int hw = (int)(i % HW);
@@ -67,6 +76,8 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
 // ---- add, concat, split along channels (NHWC rows) ------------------------------------------------------
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n8) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
          i += (long long)gridDim.x * blockDim.x) {
         float x[8], y[8];
@@ -81,6 +92,8 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
 template <typename T>
 __global__ void concat_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int Ca8, int Cb8,
                               long long rows) {
+    pdl_trigger();
+    pdl_wait();
     const int Ct8 = Ca8 + Cb8;
     const long long total = rows * Ct8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -96,6 +109,8 @@ __global__ void concat_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 template <typename T>
 __global__ void split_kernel(const T* __restrict__ g, T* __restrict__ ga, T* __restrict__ gb, int Ca8, int Cb8,
                              long long rows) {
+    pdl_trigger();
+    pdl_wait();
     const int Ct8 = Ca8 + Cb8;
     const long long total = rows * Ct8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -113,6 +128,8 @@ __global__ void split_kernel(const T* __restrict__ g, T* __restrict__ ga, T* __r
 __global__ void axpby_ps_kernel(const float* __restrict__ a, const float4* __restrict__ x, const float* __restrict__ b,
                                 const float4* __restrict__ y, const float* __restrict__ c, const float4* __restrict__ z,
                                 float4* __restrict__ out, int per4, long long total4) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
         int s = (int)(i / per4);
@@ -124,6 +141,8 @@ __global__ void axpby_ps_kernel(const float* __restrict__ a, const float4* __res
 }
 
 __global__ void scale_kernel(float* __restrict__ x, const float* __restrict__ alpha, long long n) {
+    pdl_trigger();
+    pdl_wait();
     const float a = *alpha;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         x[i] *= a;
@@ -134,6 +153,8 @@ __global__ void scale_kernel(float* __restrict__ x, const float* __restrict__ al
 template <typename T, int O>
 __global__ void head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                 float* __restrict__ y, int C, int HW, long long M, int sigmoid_last) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sw[];  // [O][C]
     for (int i = threadIdx.x; i < O * C; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
@@ -167,6 +188,8 @@ template <typename T, int O>
 __global__ void head_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y,
                                 const float* __restrict__ dy, T* __restrict__ dx, float* __restrict__ dw,
                                 float* __restrict__ db, int C, int HW, long long M, int sigmoid_last) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];   // sw[O*C] | sdw[O*C] | sdb[O]
     float* sw = sm;
     float* sdw = sm + O * C;
@@ -239,8 +262,7 @@ extern "C" int pidm_qsample(const float* x0, const float* noise, const long long
                             const float* sqrt_1mab, float* xt, int B, int per_sample, void* stream) {
     PIDM_REQUIRE(per_sample % 4 == 0, "q_sample: per-sample size must be a multiple of 4");
     long long total4 = (long long)B * per_sample / 4;
-    qsample_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const float4*)x0, (const float4*)noise, t, sqrt_ab, sqrt_1mab, (float4*)xt, per_sample / 4, total4);
+    PIDM_CUDA(launch_pdl(qsample_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x0, (const float4*)noise, t, sqrt_ab, sqrt_1mab, (float4*)xt, per_sample / 4, total4));
     PIDM_LAUNCH_CHECK("qsample");
     return 0;
 }
@@ -248,8 +270,7 @@ extern "C" int pidm_qsample(const float* x0, const float* noise, const long long
 extern "C" int pidm_posterior_step(const float* x_t, const float* x0_pred, const float* z, float* out, float coef1,
                                    float coef2, float sigma, long long n, void* stream) {
     PIDM_REQUIRE(n % 4 == 0, "posterior_step: size must be a multiple of 4");
-    posterior_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const float4*)x_t, (const float4*)x0_pred, (const float4*)z, (float4*)out, coef1, coef2, sigma, n / 4);
+    PIDM_CUDA(launch_pdl(posterior_kernel, dim3(grid_for(n / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x_t, (const float4*)x0_pred, (const float4*)z, (float4*)out, coef1, coef2, sigma, n / 4));
     PIDM_LAUNCH_CHECK("posterior_step");
     return 0;
 }
@@ -257,24 +278,21 @@ extern "C" int pidm_posterior_step(const float* x_t, const float* x0_pred, const
 extern "C" int pidm_nchw_to_nhwc(const float* src, void* dst, int B, int C, int HW, int Cpad, int dtype, void* stream) {
     PIDM_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "nchw_to_nhwc: padded channel count must be a multiple of 8, >= C");
     long long n_pix = (long long)B * HW;
-    PIDM_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(n_pix, 128), 128, 0, (cudaStream_t)stream>>>(
-                                   src, (T*)dst, C, HW, Cpad, n_pix)));
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(nchw_to_nhwc_kernel<T>, dim3(grid_for(n_pix, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, src, (T*)dst, C, HW, Cpad, n_pix)));
     PIDM_LAUNCH_CHECK("nchw_to_nhwc");
     return 0;
 }
 
 extern "C" int pidm_nhwc_to_nchw(const void* src, float* dst, int B, int C, int HW, int Cpad, int dtype, void* stream) {
     long long total = (long long)B * HW * C;
-    PIDM_DISPATCH_DTYPE(dtype, (nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const T*)src, dst, C, HW, Cpad, total)));
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(nhwc_to_nchw_kernel<T>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const T*)src, dst, C, HW, Cpad, total)));
     PIDM_LAUNCH_CHECK("nhwc_to_nchw");
     return 0;
 }
 
 extern "C" int pidm_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
     PIDM_REQUIRE(n % 8 == 0, "add: size must be a multiple of 8");
-    PIDM_DISPATCH_DTYPE(dtype, (add_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const T*)a, (const T*)b, (T*)out, n / 8)));
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(add_kernel<T>, dim3(grid_for(n / 8, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const T*)a, (const T*)b, (T*)out, n / 8)));
     PIDM_LAUNCH_CHECK("add");
     return 0;
 }
@@ -283,8 +301,7 @@ extern "C" int pidm_concat_channels(const void* a, const void* b, void* out, lon
                                     void* stream) {
     PIDM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat: channel counts must be multiples of 8");
     long long total = rows * (Ca + Cb) / 8;
-    PIDM_DISPATCH_DTYPE(dtype, (concat_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const T*)a, (const T*)b, (T*)out, Ca / 8, Cb / 8, rows)));
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(concat_kernel<T>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const T*)a, (const T*)b, (T*)out, Ca / 8, Cb / 8, rows)));
     PIDM_LAUNCH_CHECK("concat");
     return 0;
 }
@@ -293,8 +310,7 @@ extern "C" int pidm_split_channels(const void* g, void* ga, void* gb, long long 
                                    void* stream) {
     PIDM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "split: channel counts must be multiples of 8");
     long long total = rows * (Ca + Cb) / 8;
-    PIDM_DISPATCH_DTYPE(dtype, (split_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                   (const T*)g, (T*)ga, (T*)gb, Ca / 8, Cb / 8, rows)));
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(split_kernel<T>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const T*)g, (T*)ga, (T*)gb, Ca / 8, Cb / 8, rows)));
     PIDM_LAUNCH_CHECK("split");
     return 0;
 }
@@ -303,14 +319,13 @@ extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float
                                      const float* z, float* out, int B, int per_sample, void* stream) {
     PIDM_REQUIRE(per_sample % 4 == 0, "axpby_per_sample: per-sample size must be a multiple of 4");
     long long total4 = (long long)B * per_sample / 4;
-    axpby_ps_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-        a, (const float4*)x, b, (const float4*)y, c, (const float4*)z, (float4*)out, per_sample / 4, total4);
+    PIDM_CUDA(launch_pdl(axpby_ps_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, (const float4*)x, b, (const float4*)y, c, (const float4*)z, (float4*)out, per_sample / 4, total4));
     PIDM_LAUNCH_CHECK("axpby_per_sample");
     return 0;
 }
 
 extern "C" int pidm_scale_inplace(float* x, const float* alpha_dev, long long n, void* stream) {
-    scale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, alpha_dev, n);
+    PIDM_CUDA(launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, alpha_dev, n));
     PIDM_LAUNCH_CHECK("scale");
     return 0;
 }
@@ -321,7 +336,7 @@ extern "C" int pidm_head_fwd(const void* x, const float* w, const float* bias, f
     long long M = (long long)B * HW;
     size_t smem = (size_t)O * C * sizeof(float);
 #define HEAD_F(OO)                                                                                     \
-    PIDM_DISPATCH_DTYPE(dtype, (head_fwd_kernel<T, OO><<<grid_for(M, 256), 256, smem, (cudaStream_t)stream>>>( \
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(head_fwd_kernel<T, OO>, dim3(grid_for(M, 256)), dim3(256), (size_t)(smem), (cudaStream_t)stream, \
                                    (const T*)x, w, bias, y, C, HW, M, sigmoid_last)))
     switch (O) { case 1: HEAD_F(1); break; case 2: HEAD_F(2); break; case 3: HEAD_F(3); break; default: HEAD_F(4); }
 #undef HEAD_F
@@ -335,7 +350,7 @@ extern "C" int pidm_head_bwd(const void* x, const float* w, const float* y, cons
     long long M = (long long)B * HW;
     size_t smem = (size_t)(2 * O * C + O) * sizeof(float);
 #define HEAD_B(OO)                                                                                     \
-    PIDM_DISPATCH_DTYPE(dtype, (head_bwd_kernel<T, OO><<<grid_for(M, 256, 148 * 2), 256, smem, (cudaStream_t)stream>>>( \
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(head_bwd_kernel<T, OO>, dim3(grid_for(M, 256, 148 * 2)), dim3(256), (size_t)(smem), (cudaStream_t)stream, \
                                    (const T*)x, w, y, dy, (T*)dx, dw, db, C, HW, M, sigmoid_last)))
     switch (O) { case 1: HEAD_B(1); break; case 2: HEAD_B(2); break; case 3: HEAD_B(3); break; default: HEAD_B(4); }
 #undef HEAD_B

@@ -3,6 +3,7 @@
 //                  reference unet_model.py:147-159, 464-469
 //   * block_mlps : every ResnetBlock's Linear(4dim, 2*C_out) on SiLU(t) (unet_model.py:246-249,258-262),
 //                  ALL blocks in one launch through a device-side table (they share the same input).
+#define PIDM_PDL_GROUP 3
 #include "common.cuh"
 #include "pidm.h"
 
@@ -19,6 +20,8 @@ __global__ void time_embed_fwd_kernel(const long long* __restrict__ t, const flo
                                       const float* __restrict__ b2, float* __restrict__ emb /*[B,dim]*/,
                                       float* __restrict__ h1 /*[B,td]*/, float* __restrict__ temb /*[B,td]*/,
                                       float* __restrict__ silu_t /*[B,td]*/, int dim, int td) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];   // e[dim] | a1[td]
     float* e = sm;
     float* a1 = sm + dim;
@@ -49,6 +52,8 @@ __global__ void time_embed_bwd_kernel(const float* __restrict__ d_silu, const fl
                                       const float* __restrict__ h1, const float* __restrict__ temb,
                                       const float* __restrict__ W2, float* __restrict__ dW1, float* __restrict__ db1,
                                       float* __restrict__ dW2, float* __restrict__ db2, int dim, int td) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];   // e[dim] | a1[td] | dt[td] | dh[td]
     float* e = sm;
     float* a1 = e + dim;
@@ -90,6 +95,8 @@ constexpr int MLP_DG_ROWS = 128;    // rows per CTA (dgrad)
 // no cross-lane reduction is needed.
 __global__ void __launch_bounds__(256) block_mlps_fwd_kernel(const MlpEntry* __restrict__ table,
                                                              const float* __restrict__ s /*[B,td]*/, int B, int td) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float ss[];   // [MLP_BCHUNK][td + 1]
     const MlpEntry e = table[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -123,6 +130,8 @@ __global__ void __launch_bounds__(256) block_mlps_fwd_kernel(const MlpEntry* __r
 // broadcasts it by shuffle, lanes run over k for the s tile)
 __global__ void __launch_bounds__(256) block_mlps_wgrad_kernel(const MlpEntry* __restrict__ table,
                                                                const float* __restrict__ s, int B, int td) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float ss[];   // [MLP_BCHUNK][td]
     const MlpEntry e = table[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -169,6 +178,8 @@ __global__ void __launch_bounds__(256) block_mlps_wgrad_kernel(const MlpEntry* _
 constexpr int MLP_DG_GROUPS = 37;       // x sample chunks: a quarter of the SMs -- the whole problem is ~20 MFLOP
 __global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, int n_entries, float* __restrict__ ds,
                                         int B, int td) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float sd[MLP_DG_ROWS][MLP_BCHUNK];
     const int b0 = blockIdx.y * MLP_BCHUNK;
     const int nb = min(MLP_BCHUNK, B - b0);
@@ -213,8 +224,8 @@ extern "C" int pidm_time_embed_fwd(const long long* t, const float* W1, const fl
                                    const float* b2, float* emb, float* h1, float* temb, float* silu_t, int B, int dim,
                                    int td, void* stream) {
     PIDM_REQUIRE(td <= 1024 && dim <= td && dim % 2 == 0 && dim >= 4, "time_embed: need 4<=dim<=td<=1024, dim even");
-    time_embed_fwd_kernel<<<B, td, (dim + td) * sizeof(float), (cudaStream_t)stream>>>(t, W1, b1, W2, b2, emb, h1, temb,
-                                                                                      silu_t, dim, td);
+    PIDM_CUDA(launch_pdl(time_embed_fwd_kernel, dim3(B), dim3(td), (size_t)((dim + td) * sizeof(float)), (cudaStream_t)stream, t, W1, b1, W2, b2, emb, h1, temb,
+                                                                                      silu_t, dim, td));
     PIDM_LAUNCH_CHECK("time_embed_fwd");
     return 0;
 }
@@ -223,8 +234,7 @@ extern "C" int pidm_time_embed_bwd(const float* d_silu_t, const float* emb, cons
                                    const float* W2, float* dW1, float* db1, float* dW2, float* db2, int B, int dim,
                                    int td, void* stream) {
     PIDM_REQUIRE(td <= 1024 && dim <= td, "time_embed_bwd: need dim<=td<=1024");
-    time_embed_bwd_kernel<<<B, td, (dim + 3 * td) * sizeof(float), (cudaStream_t)stream>>>(
-        d_silu_t, emb, h1, temb, W2, dW1, db1, dW2, db2, dim, td);
+    PIDM_CUDA(launch_pdl(time_embed_bwd_kernel, dim3(B), dim3(td), (size_t)((dim + 3 * td) * sizeof(float)), (cudaStream_t)stream, d_silu_t, emb, h1, temb, W2, dW1, db1, dW2, db2, dim, td));
     PIDM_LAUNCH_CHECK("time_embed_bwd");
     return 0;
 }
@@ -247,7 +257,7 @@ extern "C" int pidm_block_mlps_fwd(const void* table_dev, int n_entries, int max
     size_t smem = (size_t)MLP_BCHUNK * (td + 1) * sizeof(float);
     if (int e = mlp_smem_attr(smem)) return e;
     dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
-    block_mlps_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const MlpEntry*)table_dev, silu_t, B, td);
+    PIDM_CUDA(launch_pdl(block_mlps_fwd_kernel, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, (const MlpEntry*)table_dev, silu_t, B, td));
     PIDM_LAUNCH_CHECK("block_mlps_fwd");
     return 0;
 }
@@ -260,10 +270,10 @@ extern "C" int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max
     size_t smem = (size_t)MLP_BCHUNK * (td + 1) * sizeof(float);
     if (int e = mlp_smem_attr(smem)) return e;
     dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
-    block_mlps_wgrad_kernel<<<grid, 256, smem, st>>>((const MlpEntry*)table_dev, silu_t, B, td);
+    PIDM_CUDA(launch_pdl(block_mlps_wgrad_kernel, dim3(grid), dim3(256), (size_t)(smem), st, (const MlpEntry*)table_dev, silu_t, B, td));
     PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
     dim3 dgrid(MLP_DG_GROUPS, ceil_div(B, MLP_BCHUNK));
-    block_mlps_dgrad_kernel<<<dgrid, td, 0, st>>>((const MlpEntry*)table_dev, n_entries, d_silu_t, B, td);
+    PIDM_CUDA(launch_pdl(block_mlps_dgrad_kernel, dim3(dgrid), dim3(td), (size_t)(0), st, (const MlpEntry*)table_dev, n_entries, d_silu_t, B, td));
     PIDM_LAUNCH_CHECK("block_mlps_bwd");
     return 0;
 }

@@ -643,7 +643,7 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
             attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl_enabled(0) ? 2 : 1;
             static bool attr_done[2] = {false, false};
             PIDM_DISPATCH_DTYPE(dtype, {
                 const int di = dtype == PIDM_BF16 ? 1 : 0;

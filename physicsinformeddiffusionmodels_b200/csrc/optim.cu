@@ -3,6 +3,7 @@
 //   Adam(lr, betas=(0.9,0.999), eps=1e-8)                          (main.py:143,166)
 //   EMA shadow update mu=0.99                                       (denoising_utils.py:174-177, main.py:178-179)
 // and the error plumbing shared by all translation units.
+#define PIDM_PDL_GROUP 3
 #include "common.cuh"
 #include <stdlib.h>
 #include "pidm.h"
@@ -12,10 +13,10 @@ namespace pidm {
 
 thread_local char g_last_error[512] = {0};
 
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("PIDM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
+bool pdl_enabled(int group) {
+    static int mask = -1;
+    if (mask < 0) { const char* e = getenv("PIDM_PDL"); mask = e ? atoi(e) : 0x1;     // measured: only group 0 (prologue-heavy persistent kernels) gains }
+    return ((mask >> group) & 1) != 0;
 }
 
 int set_error(int code, const char* fmt, ...) {
@@ -28,6 +29,8 @@ int set_error(int code, const char* fmt, ...) {
 
 __global__ void sumsq_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ tail, int ntail,
                              float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     float s = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = x[i];
@@ -50,6 +53,8 @@ __global__ void adam_ema_kernel(float* __restrict__ p, float* __restrict__ g, fl
                                 float eps, float bc1, float bc2, const int* __restrict__ step_dev,
                                 const float* __restrict__ gnorm_sq, float grad_scale, float max_norm, float ema_mu,
                                 int ema_on, int zero_grad) {
+    pdl_trigger();
+    pdl_wait();
     if (step_dev) {   // CUDA-graph friendly: the 1-based step count lives on the device
         const float st = (float)(*step_dev);
         bc1 = 1.f - powf(b1, st);
@@ -72,7 +77,9 @@ __global__ void adam_ema_kernel(float* __restrict__ p, float* __restrict__ g, fl
     }
 }
 
-__global__ void incr_kernel(int* c) { *c += 1; }
+__global__ void incr_kernel(int* c) {
+    pdl_trigger();
+    pdl_wait(); *c += 1; }
 
 }  // namespace pidm
 using namespace pidm;
@@ -88,7 +95,7 @@ extern "C" int pidm_sumsq(const float* x, long long n, float* out, void* stream)
     int grid = (int)((n4 + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, n4, x + n4 * 4, (int)(n - n4 * 4), out);
+    PIDM_CUDA(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x, n4, x + n4 * 4, (int)(n - n4 * 4), out));
     PIDM_LAUNCH_CHECK("sumsq");
     return 0;
 }
@@ -98,13 +105,13 @@ extern "C" int pidm_adam_ema_step(float* param, float* grad, float* exp_avg, flo
                                   int* step_counter_dev, const float* grad_norm_sq_dev, float grad_scale, float max_norm, float ema_mu,
                                   int ema_on, int zero_grad, void* stream) {
     PIDM_REQUIRE(step >= 1 || step_counter_dev, "adam: step is 1-based");
-    if (step_counter_dev) incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev);   // counter holds steps done so far
+    if (step_counter_dev) PIDM_CUDA(launch_pdl(incr_kernel, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)stream, step_counter_dev));   // counter holds steps done so far
     float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    adam_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, ema_shadow, n, lr, beta1,
+    PIDM_CUDA(launch_pdl(adam_ema_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, ema_shadow, n, lr, beta1,
                                                            beta2, eps, bc1, bc2, step_counter_dev, grad_norm_sq_dev, grad_scale,
-                                                           max_norm, ema_mu, ema_on, zero_grad);
+                                                           max_norm, ema_mu, ema_on, zero_grad));
     PIDM_LAUNCH_CHECK("adam_ema_step");
     return 0;
 }
