@@ -15,7 +15,8 @@ thread_local char g_last_error[512] = {0};
 
 bool pdl_enabled(int group) {
     static int mask = -1;
-    if (mask < 0) { const char* e = getenv("PIDM_PDL"); mask = e ? atoi(e) : 0x1;     // measured: only group 0 (prologue-heavy persistent kernels) gains }
+    // default 0x1: only group 0 (the prologue-heavy persistent kernels) gains, see common.cuh
+    if (mask < 0) { const char* e = getenv("PIDM_PDL"); mask = e ? atoi(e) : 0x1; }
     return ((mask >> group) & 1) != 0;
 }
 
