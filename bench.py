@@ -200,15 +200,19 @@ def breakdown_one_step(engine, x0):
     detail = []
     for name, a, e0, e1 in records:
         ms = e0.elapsed_time(e1)
+        nbytes = 0.0
         detail.append((round(ms * 1e3, 1), name, [x for x in a if isinstance(x, int) and not isinstance(x, bool) and x < (1 << 24)][:14]))
         flop = 0.0
         if name in ('pidm_conv2d_tc',):
             B, H, W, Cin, Cout, KH, KW = a[5], a[6], a[7], a[8], a[9], a[10], a[11]
             flop = 2.0 * B * H * W * Cout * KH * KW * Cin
         elif name == 'pidm_conv2d_tc_general':
-            B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[5], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
+            B, Hin, Win, Cin, Ho, Wo, Cout, KH, KW, stride, tr = (a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13],
+                                                                 a[14], a[16])
             taps = KH * KW / (stride * stride) if tr else KH * KW
             flop = 2.0 * B * Ho * Wo * Cout * taps * Cin
+            # algorithmic bytes: input + output (+ residual) activations in bf16, packed weights once
+            nbytes = 2.0 * (B * Hin * Win * Cin + B * Ho * Wo * Cout * (2 if a[3] is not None else 1) + KH * KW * Cin * Cout)
         elif name == 'pidm_conv2d_simt':
             B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[5], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
             taps = KH * KW / (stride * stride) if tr else KH * KW       # useful taps of the transposed gather
@@ -220,10 +224,11 @@ def breakdown_one_step(engine, x0):
             B, Cin, Ho, Wo, Cout, KH, KW, stride, tr = a[4], a[7], a[9], a[10], a[11], a[12], a[13], a[14], a[16]
             taps = KH * KW / (stride * stride) if tr else KH * KW
             flop = 2.0 * B * Ho * Wo * Cout * taps * Cin
-        d = agg.setdefault(name, {'ms': 0.0, 'calls': 0, 'flop': 0.0})
+        d = agg.setdefault(name, {'ms': 0.0, 'calls': 0, 'flop': 0.0, 'bytes': 0.0})
         d['ms'] += ms
         d['calls'] += 1
         d['flop'] += flop
+        d['bytes'] += nbytes
     if os.environ.get('PIDM_BENCH_DETAIL'):
         with open(os.environ['PIDM_BENCH_DETAIL'], 'w') as f:
             for us, name, ints in sorted(detail, key=lambda r: -r[0]):
@@ -405,6 +410,22 @@ def main():
                     'share_of_step_kernel_time': d['ms'] / total_ms, 'peak_source': pk['source'] + ', sustained figure',
                     'how': 'algorithmic 2*M*N*K FLOPs of every launch of this entry point in one eager step / '
                            'CUDA-event time around those launches'}
+            if d.get('bytes'):
+                # the U-Net is narrow (32..256 channels): its convolutions are bound by operand / activation movement
+                # long before the tensor pipe, so the same launches are also reported against the HBM roofline
+                roof['algorithmic_bytes'] = d['bytes']
+                roof['hbm_view'] = {'achieved': d['bytes'] / (d['ms'] * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                    'frac': d['bytes'] / (d['ms'] * 1e-3) / 1e9 / pk['hbm_gbs']}
+            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_step_traffic.json')
+            if os.path.exists(tpath):
+                prefix = {'pidm_conv2d_tc_general': 'conv_tc_kernel', 'pidm_conv2d_tc': 'conv_tc_kernel',
+                          'pidm_conv2d_wgrad_tc': 'wgrad'}.get(name)
+                if prefix:
+                    tr = json.load(open(tpath))
+                    roof['traffic'] = sum(v['dram_bytes'] for k, v in tr.items() if k.startswith(prefix))
+                    roof['traffic_note'] = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of this '
+                                            'kernel in ONE step (ncu launch list, profiles/r01_step_traffic.json); '
+                                            'compare with algorithmic_bytes')
         else:
             roof = {'bound': 'hbm', 'kernel': name, 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
                     'traffic': None, 'share_of_step_kernel_time': d['ms'] / total_ms}
