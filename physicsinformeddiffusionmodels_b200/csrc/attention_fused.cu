@@ -23,7 +23,6 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
-__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // B fragments of a 32-row block of the K-major projection weights W[n][c] (bf16): B[k = c][n] = W[n][c]
 __device__ __forceinline__ void load_w_frags(uint32_t (&w)[2][4][2], const __nv_bfloat16* __restrict__ Wrows, int lane) {

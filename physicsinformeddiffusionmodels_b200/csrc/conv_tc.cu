@@ -1,22 +1,34 @@
-// Stride-1 KxK convolution ("same" padding) on NHWC bf16 activations as an implicit GEMM on the 5th-generation
-// tensor cores (tcgen05), operands staged by TMA, fp32 accumulators in tensor memory (TMEM).
+// Convolutions of the U-Net on NHWC bf16 activations as implicit GEMMs on the 5th-generation tensor cores (tcgen05),
+// operands staged by TMA, fp32 accumulators in tensor memory (TMEM).
 //
-//   y[b,h,w,n] = sum_{r,q,c} x[b, h+r-pad, w+q-pad, c] * Wp[n][(r*KW+q)*Cin + c] (+ bias[n]) (+ residual[b,h,w,n])
+//   y[b,h,w,n] = sum_{r,q,c} x[b, s*h+r-pad, s*w+q-pad, c] * Wp[n][(r*KW+q)*Cin + c] (+ bias[n]) (+ residual[b,h,w,n])
 //
-// This is the kernel behind every 3x3 / 1x1 layer of the U-Net (ResnetBlock convs, res_conv, to_qkv, to_out,
-// reference unet_model.py:227,253,275,279) and behind their dgrad (same kernel, 180-degree-rotated packed weights).
+// One kernel covers every layer of the network and its dgrad: 3x3 / 1x1 / 7x7 stride-1 layers (ResnetBlock convs,
+// res_conv, to_qkv, to_out, stem: reference unet_model.py:227,253,275,279,453), the 4x4/stride-2 down-sampling conv
+// (:197, TMA elementStrides) and the 4x4/stride-2 transposed conv (:163, four output-parity classes).
 //
-// Tiling.  GEMM M = 128 output pixels = a TN x TH x TW box of the image (TW = W), N = BN output channels,
-// K = taps * Cin walked in (tap, BK-channel) steps.  For one K step the A operand is ONE 4-D TMA box
-// {BK channels, TW, TH, TN} of the NHWC tensor at spatial offset (r-pad, q-pad): the im2col gather, the zero
-// padding (TMA out-of-bounds fill) and the 128B/64B shared-memory swizzle all happen in the copy engine.
-// The B operand is a 2-D TMA box {BK, BN} of the K-major packed weights.  Both land in the canonical K-major
-// swizzled layout that the UMMA shared-memory descriptors expect, so no thread ever touches the operands.
+// Tiling.  GEMM M = 128 output pixels, N = BN output channels, K = taps * Cin walked in K-steps.
+//   plain mode     : the pixel tile is a TN x TH x TW box (TW = W); one K-step = one tap x BK channels; the A operand
+//                    is ONE 4-D TMA box {BK, TW, TH, TN} at spatial offset (r-pad, q-pad) -- the im2col gather, the zero
+//                    padding (TMA out-of-bounds fill) and the 128B/64B swizzle all happen in the copy engine.
+//   row-group mode : (stride-1 KxK layers whose image splits into 16x8 tiles) one K-step = one kernel COLUMN q x BK
+//                    channels; its A box holds (16 + KH - 1) x 8 pixels and the KH kernel rows are row-shifted views of
+//                    that one shared-memory tile (a shift of 8 pixels = one swizzle period), so L2 -> SM operand
+//                    traffic drops from KH*KW to KW*(16+KH-1)/16 tiles per output tile.
+//   The B operand (K-major packed weights) is a 2-D TMA box per tap, or resident in shared memory for the whole kernel
+//   when the layer has a single n-tile.  Both land in the canonical K-major swizzled layout that the UMMA descriptors
+//   expect: no thread ever touches the operands.
 //
-// Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane,
-// tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16), warp 2 = TMEM allocator, warps 4-7 = epilogue
-// (tcgen05.ld 32x32b.x32 -> +bias +residual -> bf16 -> 128-bit global stores).  smem full/empty mbarrier ring
-// between producer and MMA, tcgen05.commit releases stages and publishes the accumulator.
+// Persistent, warp-specialised (256 threads, one CTA per SM, tiles walked with stride gridDim.x):
+//   warps 0,2,3  TMA producers (one elected lane each, K-step i belongs to producer i % 3), <= 12-stage mbarrier ring
+//                that runs across tile boundaries
+//   warp 1       MMA issuer: ONE thread, tcgen05.mma.cta_group::1.kind::f16 M128 x BN x K16, descriptors advanced by
+//                integer adds; tcgen05.commit releases ring stages / publishes the accumulator
+//   warp 2       also allocates TMEM (2 x BN columns: the epilogue of tile i overlaps the mainloop of tile i+1)
+//   warps 4-7    epilogue: tcgen05.ld -> +bias +residual -> GroupNorm sum / sum-of-squares (optional) -> bf16 ->
+//                XOR-swizzled smem transpose -> 64/128-byte coalesced row-segment stores
+// What bounds it (clock64 traces, scripts/trace_conv.py): at Cin = 32 the TMA engine delivers one 64-byte box row per
+// ~4 cycles; an M128 x N32 x K16 MMA takes ~61 cycles (A-operand fetch) whatever N <= 64; a launch costs >= 5.5 us.
 #include "common.cuh"
 #include "pidm.h"
 #include <cuda.h>
