@@ -23,6 +23,38 @@ __global__ void qsample_kernel(const float4* __restrict__ x0, const float4* __re
     }
 }
 
+// scalar variants for per-sample sizes that are not multiples of 4 (the 65x65 fields of the mechanics branch: samples
+// then start at addresses that are not 16-byte aligned)
+__global__ void qsample_scalar_kernel(const float* __restrict__ x0, const float* __restrict__ eps,
+                                      const long long* __restrict__ t, const float* __restrict__ sa,
+                                      const float* __restrict__ sb, float* __restrict__ xt, int per_sample, long long total) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long tb = t[i / per_sample];
+        xt[i] = sa[tb] * x0[i] + sb[tb] * eps[i];
+    }
+}
+__global__ void posterior_scalar_kernel(const float* __restrict__ xt, const float* __restrict__ x0p,
+                                        const float* __restrict__ z, float* __restrict__ out, float c1, float c2, float sig,
+                                        long long total) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = c1 * x0p[i] + c2 * xt[i] + sig * z[i];
+}
+__global__ void axpby_ps_scalar_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ b,
+                                       const float* __restrict__ y, const float* __restrict__ c,
+                                       const float* __restrict__ z, float* __restrict__ out, int per_sample,
+                                       long long total) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / per_sample;
+        out[i] = a[s] * x[i] + b[s] * y[i] + c[s] * z[i];
+    }
+}
+
 // ---- posterior step: x_{t-1} = c1 x0_pred + c2 x_t + sigma z     (denoising_utils.py:441-455) ------------
 __global__ void posterior_kernel(const float4* __restrict__ xt, const float4* __restrict__ x0p,
                                  const float4* __restrict__ z, float4* __restrict__ out, float c1, float c2, float sig,
@@ -260,7 +292,13 @@ using namespace pidm;
 
 extern "C" int pidm_qsample(const float* x0, const float* noise, const long long* t, const float* sqrt_ab,
                             const float* sqrt_1mab, float* xt, int B, int per_sample, void* stream) {
-    PIDM_REQUIRE(per_sample % 4 == 0, "q_sample: per-sample size must be a multiple of 4");
+    if (per_sample % 4 != 0) {
+        const long long total = (long long)B * per_sample;
+        PIDM_CUDA(launch_pdl(qsample_scalar_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, x0,
+                             noise, t, sqrt_ab, sqrt_1mab, xt, per_sample, total));
+        PIDM_LAUNCH_CHECK("qsample");
+        return 0;
+    }
     long long total4 = (long long)B * per_sample / 4;
     PIDM_CUDA(launch_pdl(qsample_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x0, (const float4*)noise, t, sqrt_ab, sqrt_1mab, (float4*)xt, per_sample / 4, total4));
     PIDM_LAUNCH_CHECK("qsample");
@@ -269,7 +307,12 @@ extern "C" int pidm_qsample(const float* x0, const float* noise, const long long
 
 extern "C" int pidm_posterior_step(const float* x_t, const float* x0_pred, const float* z, float* out, float coef1,
                                    float coef2, float sigma, long long n, void* stream) {
-    PIDM_REQUIRE(n % 4 == 0, "posterior_step: size must be a multiple of 4");
+    if (n % 4 != 0) {
+        PIDM_CUDA(launch_pdl(posterior_scalar_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, x_t,
+                             x0_pred, z, out, coef1, coef2, sigma, n));
+        PIDM_LAUNCH_CHECK("posterior_step");
+        return 0;
+    }
     PIDM_CUDA(launch_pdl(posterior_kernel, dim3(grid_for(n / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x_t, (const float4*)x0_pred, (const float4*)z, (float4*)out, coef1, coef2, sigma, n / 4));
     PIDM_LAUNCH_CHECK("posterior_step");
     return 0;
@@ -317,7 +360,13 @@ extern "C" int pidm_split_channels(const void* g, void* ga, void* gb, long long 
 
 extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float* b, const float* y, const float* c,
                                      const float* z, float* out, int B, int per_sample, void* stream) {
-    PIDM_REQUIRE(per_sample % 4 == 0, "axpby_per_sample: per-sample size must be a multiple of 4");
+    if (per_sample % 4 != 0) {
+        const long long total = (long long)B * per_sample;
+        PIDM_CUDA(launch_pdl(axpby_ps_scalar_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, a, x,
+                             b, y, c, z, out, per_sample, total));
+        PIDM_LAUNCH_CHECK("axpby_per_sample");
+        return 0;
+    }
     long long total4 = (long long)B * per_sample / 4;
     PIDM_CUDA(launch_pdl(axpby_ps_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, (const float4*)x, b, (const float4*)y, c, (const float4*)z, (float4*)out, per_sample / 4, total4));
     PIDM_LAUNCH_CHECK("axpby_per_sample");

@@ -149,6 +149,58 @@ def test_sample_engine_matches_reference_and_graph_replay(env, golden, monkeypat
     assert rel(xg, xe) < 1e-4, rel(xg, xe)
 
 
+def test_mechanics_training_loss_matches_oracle(env, monkeypatch):
+    """configs[2]: one loss evaluation + backward of the mechanics (topology-optimisation) branch -- q_sample on the
+    65x65 fields, bilinear 65->64, Unet3D(channels=10, out_dim=3, sigmoid on the density channel), bilinear 64->65 of the
+    displacements, matrix-free K(rho)u - f residual, compliance and volume-fraction terms (reference
+    denoising_utils.py:629-710, residuals_mechanics_K.py:198-274) -- against the oracle composition in fp32."""
+    O, ops = env['O'], env['ops']
+    ops.set_precision('fp32')
+    from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
+    from physicsinformeddiffusionmodels_b200.residuals_mechanics_K import ResidualsMechanics
+    from physicsinformeddiffusionmodels_b200.unet_model import Unet3D
+    cfg = O.unet_config(dim=32, channels=10, out_dim=3, sigmoid_last_channel=True)
+    sd = O.make_test_state_dict(cfg, 3)
+    model = Unet3D(dim=32, channels=10, out_dim=3, sigmoid_last_channel=True).to(DEV)
+    model.load_state_dict(sd)
+    diff = DenoisingDiffusion(100, DEV)
+    res = ResidualsMechanics(model=model, pixels_per_dim=64, pixels_at_boundary=True, no_BC_folder='', device=DEV)
+    g = torch.Generator().manual_seed(77)
+    B = 2
+    cond = torch.rand(B, 3, 65, 65, generator=g)
+    cond[:, 0] = torch.tensor([0.4, 0.55])[:, None, None]                     # volume fraction plane
+    x0 = torch.cat((0.2 * torch.randn(B, 2, 65, 65, generator=g), torch.rand(B, 1, 65, 65, generator=g)), dim=1)
+    bcs = torch.zeros(B, 4, 65, 65)
+    bcs[:, 0, :, 0] = 1.; bcs[:, 1, :, 0] = 1.                                # clamped left edge
+    bcs[:, 3, 32, 64] = -1.                                                   # point load
+    t = torch.tensor([17, 63])
+    noise = torch.randn(B, 3, 65, 65, generator=g)
+    c_data, c_res, lam = 1.0, 1e-2, 1e-3
+    # ---- oracle (CPU, fp32)
+    tabs = O.diffusion_tables(100)
+    xt = O.q_sample(x0, t, noise, tabs)
+    net_in = torch.cat((O.bilinear_resize(torch.cat((xt, cond), dim=1), 64), O.bilinear_resize(bcs, 64)), dim=1)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    y = O.unet_forward({**sd, **params}, cfg, net_in, t)
+    r, comp, _ = O.mechanics_residual(y, bcs, cond[:, 0, 0, 0])
+    mo = torch.cat((O.bilinear_resize(y[:, :2], 65), torch.nn.functional.pad(y[:, 2], (0, 1, 0, 1)).unsqueeze(1)), dim=1)
+    mse = ((x0 - mo) ** 2).reshape(B, -1).mean(dim=1)
+    p2w = tabs['p2_loss_weight'][t].float()
+    var = tabs['posterior_variance_clipped'][t].float()
+    loss_o = c_data * (mse * p2w).mean() + (c_res * 0.5 * r ** 2 / var[:, None]).mean() + (lam * comp).mean()
+    loss_o.backward()
+    # ---- engine
+    monkeypatch.setattr(torch, 'randn_like', lambda *a, **k: noise.to(DEV))
+    inp = torch.cat((cond, x0, bcs), dim=1).to(DEV)
+    loss, data_l, rabs, _, opt = res.training_loss(diff, inp, t.to(DEV), c_data, c_res, 0., lam)
+    monkeypatch.undo()
+    assert abs(loss.item() / loss_o.item() - 1) < 2e-4, (loss.item(), loss_o.item())
+    loss.backward()
+    for name in ('final_conv.1.weight', 'init_conv.weight', 'mid_block1.block1.proj.weight'):
+        p = dict(model.named_parameters())[name]
+        assert rel(p.grad, params[name].grad) < 3e-3, (name, rel(p.grad, params[name].grad))
+
+
 def test_engine_training_steps_match_oracle(env):
     """3 optimizer steps of the flat-buffer engine (eager and CUDA-graph) vs the oracle's autograd + Adam + EMA."""
     O, ops = env['O'], env['ops']
