@@ -227,7 +227,7 @@ class _Conv2d(torch.autograd.Function):
         x, weight, bias = ctx.saved_tensors
         dy = dy.contiguous()
         skip = ctx.skip
-        dgrad_res = _take_skip(skip[1]) if (skip is not None and skip[0] == 'take') else None
+        dgrad_res = _take_skip(skip[1]) if (skip is not None and skip[0] == 'take' and ctx.needs_input_grad[0]) else None
         dx, gw_ret, gb_ret = _conv_backward(x, weight, bias, ctx.spec, ctx.g, dy, ctx.needs_input_grad[0], ctx.link,
                                             dgrad_res)
         if skip is not None and skip[0] == 'park':
@@ -382,7 +382,8 @@ class _LayerNormC(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         gg_buf, gg_ret = _grad_buffer(gamma)
-        call('pidm_layernorm_c_bwd', x, dy, gamma, dx, gg_buf, _take_skip(ctx.skip_link), x.numel() // C, C, ctx.eps,
+        call('pidm_layernorm_c_bwd', x, dy, gamma, dx, gg_buf,
+             _take_skip(ctx.skip_link) if ctx.needs_input_grad[0] else None, x.numel() // C, C, ctx.eps,
              _code(x), stream())
         return dx, gg_ret, None, None
 

@@ -149,6 +149,29 @@ def test_sample_engine_matches_reference_and_graph_replay(env, golden, monkeypat
     assert rel(xg, xe) < 1e-4, rel(xg, xe)
 
 
+@pytest.mark.parametrize('B', [1, 3, 5, 16])
+def test_unet_tensor_core_path_at_odd_batch_sizes(env, B):
+    """Tile / chunk / cluster planning depends on the batch size (TN samples per pixel tile, per-sample pixel chunks of
+    the attention kernels, one-wave pixel splits of the wgrads ...).  bf16 tensor-core path vs the fp32 CUDA-core path
+    of the same engine (itself pinned to the oracle above) on the same weights and inputs: forward and gradients."""
+    ops = env['ops']
+    g = torch.Generator().manual_seed(100 + B)
+    x = torch.randn(B, 2, 64, 64, generator=g).to(DEV)
+    t = torch.randint(0, 100, (B,), generator=g).to(DEV)
+    cot = torch.randn(B, 2, 64, 64, generator=g).to(DEV)
+    outs = {}
+    for mode in ('fp32', 'bf16'):
+        ops.set_precision(mode)
+        model, _, _ = env['build']()
+        y = model(x, t)
+        (y * cot).sum().backward()
+        outs[mode] = (y.detach().clone(), model.init_conv.weight.grad.clone(),
+                      model.downs[3][0].block1.proj.weight.grad.clone(), model.final_conv[1].weight.grad.clone())
+    assert torch.isfinite(outs['bf16'][0]).all()
+    for a, b in zip(outs['bf16'], outs['fp32']):
+        assert rel(a, b) < 4e-2, rel(a, b)
+
+
 def test_mechanics_training_loss_matches_oracle(env, monkeypatch):
     """configs[2]: one loss evaluation + backward of the mechanics (topology-optimisation) branch -- q_sample on the
     65x65 fields, bilinear 65->64, Unet3D(channels=10, out_dim=3, sigmoid on the density channel), bilinear 64->65 of the
