@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) block_mlps_fwd_kernel(const MlpEntry* __r
         for (int j = r0 + warp; j < r1; j += nw) {
             const float4* wr = reinterpret_cast<const float4*>(e.W + (size_t)j * td);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+#pragma unroll 8
             for (int k4 = 0; k4 < td / 4; ++k4) {
                 const float4 w = __ldg(wr + k4);
                 a0 += w.x * sl[4 * k4]; a1 += w.y * sl[4 * k4 + 1]; a2 += w.z * sl[4 * k4 + 2]; a3 += w.w * sl[4 * k4 + 3];
@@ -200,14 +200,22 @@ __global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, int 
             }
             __syncthreads();
             const float* wp = e.W + (size_t)r0 * td + k;
-#pragma unroll 2
-            for (int j = 0; j < nr; ++j) {
-                const float w = __ldg(wp + (size_t)j * td);
-                const float4* dj = reinterpret_cast<const float4*>(sd[j]);
+            // 8 weight rows are fetched before they are used: the loop is bound by the latency of these loads, not by
+            // the 32 FMAs per row
+            for (int j0 = 0; j0 < nr; j0 += 8) {
+                float w8[8];
 #pragma unroll
-                for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
-                    const float4 d = dj[q];
-                    acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
+                for (int u = 0; u < 8; ++u) w8[u] = (j0 + u < nr) ? __ldg(wp + (size_t)(j0 + u) * td) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (j0 + u >= nr) break;
+                    const float w = w8[u];
+                    const float4* dj = reinterpret_cast<const float4*>(sd[j0 + u]);
+#pragma unroll
+                    for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
+                        const float4 d = dj[q];
+                        acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
+                    }
                 }
             }
         }
