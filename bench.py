@@ -169,8 +169,33 @@ def conv_flops(args_tuple):
     return 0
 
 
+def _graph_time_ms(orig_call, name, a, side):
+    """Device time of one libpidm call: 20 launches captured into a CUDA graph on a private stream, replayed 5 times
+    between two CUDA events (no host launch overhead, the conditions of the graph-replayed training step)."""
+    a = list(a)
+    a[-1] = side.cuda_stream                                  # the stream handle is the last argument of every entry point
+    with torch.cuda.stream(side):
+        orig_call(name, *a)
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(20):
+                orig_call(name, *a)
+        g.replay()
+        side.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(5):
+            g.replay()
+        e1.record(side)
+        side.synchronize()
+    return e0.elapsed_time(e1) / 100.0
+
+
 def breakdown_one_step(engine, x0):
-    """Per-entry-point device time of ONE eager step, CUDA events on the launching stream around every libpidm call."""
+    """Per-entry-point device time of the libpidm calls of ONE step.  The calls (with their live operands) are recorded
+    during an eager step; every distinct call is then timed by CUDA-graph replay with CUDA events on its stream
+    (_graph_time_ms).  Calls that must not be repeated (the in-place optimizer update) keep the eager event time."""
     from physicsinformeddiffusionmodels_b200 import _lib, ops, packing, denoising_utils, engine as eng_mod, residuals_darcy
     records = []
     orig = _lib.call
@@ -196,10 +221,26 @@ def breakdown_one_step(engine, x0):
         engine.world = world
         for mo in mods:
             mo.call = orig
+    def key_of(name, a):
+        return (name,) + tuple(x for x in a if isinstance(x, int) and not isinstance(x, bool) and x < (1 << 24))
+    graph_ms = {}
+    side = torch.cuda.Stream()
+    for name, a, e0, e1 in records:
+        k = key_of(name, a)
+        if k in graph_ms or name in ('pidm_adam_ema_step',):
+            continue
+        try:
+            graph_ms[k] = _graph_time_ms(orig, name, a, side)
+        except Exception as ex:                                   # keep the eager number for this call
+            log(f'graph timing of {name} failed ({ex}); using the eager event time')
+            graph_ms[k] = None
+    torch.cuda.synchronize()
     agg = {}
     detail = []
     for name, a, e0, e1 in records:
-        ms = e0.elapsed_time(e1)
+        ms = graph_ms.get(key_of(name, a))
+        if ms is None:
+            ms = e0.elapsed_time(e1)
         nbytes = 0.0
         detail.append((round(ms * 1e3, 1), name, [x for x in a if isinstance(x, int) and not isinstance(x, bool) and x < (1 << 24)][:14]))
         flop = 0.0
@@ -408,8 +449,8 @@ def main():
             roof = {'bound': 'tensor', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': ach / peak, 'traffic': None, 'launches_per_step': d['calls'],
                     'share_of_step_kernel_time': d['ms'] / total_ms, 'peak_source': pk['source'] + ', sustained figure',
-                    'how': 'algorithmic 2*M*N*K FLOPs of every launch of this entry point in one eager step / '
-                           'CUDA-event time around those launches'}
+                    'how': 'algorithmic 2*M*N*K FLOPs of every launch of this entry point in one step / device time of '
+                           'those launches (each distinct call replayed from a CUDA graph, CUDA events on its stream)'}
             if d.get('bytes'):
                 # the U-Net is narrow (32..256 channels): its convolutions are bound by operand / activation movement
                 # long before the tensor pipe, so the same launches are also reported against the HBM roofline
