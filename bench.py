@@ -165,10 +165,6 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------
-def conv_flops(args_tuple):
-    return 0
-
-
 def _graph_time_ms(orig_call, name, a, side):
     """Device time of one libpidm call: 20 launches captured into a CUDA graph on a private stream, replayed 5 times
     between two CUDA events (no host launch overhead, the conditions of the graph-replayed training step)."""
