@@ -254,6 +254,15 @@ class Unet3D(nn.Module):
         self._mlp_table = MlpTable(mlps)
 
     # ---- kernels ----------------------------------------------------------------------------------------
+    # set by engine.TrainEngine: called during backward when the gradients of a parameter group are complete
+    _boundary_cb = None
+
+    def _boundary(self, group, h):
+        cb = self._boundary_cb
+        if cb is not None and h.requires_grad:
+            h.register_hook(lambda g, _cb=cb, _k=group: _cb(_k))       # returns None: the gradient is left untouched
+        return h
+
     def _conv(self, mod, x, residual=None, gn_link=None, skip=None):
         return ops.conv2d(x, mod.weight, getattr(mod, 'bias', None), self._spec[id(mod)], residual=residual,
                           gn_link=gn_link, skip=skip)
@@ -340,7 +349,9 @@ class Unet3D(nn.Module):
         h = self._conv(self.init_conv, h)
         r = h
         skips = []
-        for b1, b2, la, down in self.downs:
+        for lvl, (b1, b2, la, down) in enumerate(self.downs):
+            if lvl == 2:
+                h = self._boundary(1, h)       # backward has finished downs[2:], mid (and everything after them)
             h = self._resblock(b1, h, ss)
             h = self._resblock(b2, h, ss)
             h = self._linear_attention(la, h)
@@ -350,6 +361,7 @@ class Unet3D(nn.Module):
         h = self._resblock(self.mid_block1, h, ss)
         h = self._mid_attention(self.mid_spatial_attn, h)
         h = self._resblock(self.mid_block2, h, ss)
+        h = self._boundary(2, h)               # backward has finished the up path and the output head
         for b1, b2, la, up in self.ups:
             h = ops.concat(h, skips.pop())
             h = self._resblock(b1, h, ss)
