@@ -37,8 +37,8 @@ int pidm_posterior_step(const float* x_t, const float* x0_pred, const float* z, 
  * (src/denoising_utils.py:755-785) collapses to this form */
 int pidm_axpby_per_sample(const float* a, const float* x, const float* b, const float* y, const float* c,
                           const float* z, float* out, int B, int per_sample, void* stream);
-/* x *= *alpha_dev  (chain-rule scaling of a precomputed gradient by the upstream scalar) */
-int pidm_scale_inplace(float* x, const float* alpha_dev, long long n, void* stream);
+/* out = x * *alpha_dev  (chain-rule scaling of a precomputed gradient by the upstream scalar; out may alias x) */
+int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream);
 
 /* ---- Darcy residual (src/residuals_darcy.py:134-183 + src/grad_utils.py:64-146) ------------------------- */
 /* x0hat [B,2,P,P] fp32 NCHW (p, K); f_s [P*P]; residual [B,P*P,3] = (eq_0, bc_x0, bc_x1).  P must be 64. */
@@ -178,10 +178,13 @@ int pidm_head_bwd(const void* x, const float* w, const float* y, const float* dy
 
 /* ---- step glue on flat buffers (main.py:163-166,178-183; src/denoising_utils.py:163-205) ----------------- */
 int pidm_sumsq(const float* x, long long n, float* out, void* stream);
+/* Adam (torch.optim.Adam semantics, bias corrections evaluated in double) + global-norm clip + EMA shadow, one pass.
+ * step: 1-based host step count, ignored when step_counter_dev != NULL (device counter, incremented by the call).
+ * ema_first_step: 0 = no EMA update; k >= 1 = update the shadow from the k-th step on (main.py:178 => ema_start+2). */
 int pidm_adam_ema_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* ema_shadow, long long n,
-                       float lr, float beta1, float beta2, float eps, int step, int* step_counter_dev,
-                       const float* grad_norm_sq_dev, float grad_scale, float max_norm, float ema_mu, int ema_on,
-                       int zero_grad, void* stream);
+                       float lr, double beta1, double beta2, float eps, int step, int* step_counter_dev,
+                       const float* grad_norm_sq_dev, float grad_scale, float max_norm, float ema_mu,
+                       int ema_first_step, int zero_grad, void* stream);
 
 /* ---- mechanics residual, matrix-free (src/residuals_mechanics_K.py:166-274) ------------------------------ */
 /* u [B,2,65,65] nodal displacements, rho [B,64,64], bcs [B,4,65,65] = (bc_x, bc_y, load_x, load_y), KE [8,8].

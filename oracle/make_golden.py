@@ -188,6 +188,20 @@ def main():
     save('sample_loop_6.pt', dict(x_T=x_T, noises=torch.stack(zs), x_final=x_seq[-1], x_after_first=x_seq[1],
                                   x0_pred_last=interm[-1], residual=aux['residual'].detach()))
 
+    # ---- ancestral sampling loop, the reference's default 100 diffusion steps, B=1 ---------------
+    # The 101 draws are not stored (3.3 MB): tests replay them with torch.manual_seed(78) on the CPU generator and
+    # check `noise_checksum` first, so a generator mismatch is reported as such and not as a parity failure.
+    d100 = DenoisingDiffusion(100, 'cpu')
+    torch.manual_seed(78)
+    (x_seq, _), aux = d100.p_sample_loop(None, (1, 2, 64, 64), save_output=True, surpress_noise=True,
+                                         residual_func=res, eval_residuals=True)
+    torch.manual_seed(78)
+    draws = torch.stack([torch.randn(1, 2, 64, 64) for _ in range(101)])
+    assert torch.equal(draws[0], x_seq[0])
+    save('sample_loop_100.pt', dict(seed=torch.tensor(78), noise_checksum=draws.double().sum(dim=(1, 2, 3, 4)),
+                                    x_25=x_seq[25], x_50=x_seq[50], x_75=x_seq[75], x_final=x_seq[-1],
+                                    residual_abs_mean=aux['residual'].detach().abs().mean()))
+
     # ---- mechanics residual on given fields (A13) ---------------------------------------------
     with tempfile.TemporaryDirectory() as td:
         write_mesh(td)

@@ -15,12 +15,13 @@ P = ctypes.c_void_p
 I = ctypes.c_int
 L = ctypes.c_longlong
 F = ctypes.c_float
+D = ctypes.c_double
 
 # name -> argument ctypes (return type is always int unless noted)
 _SIGS = {
     'pidm_qsample': [P, P, P, P, P, P, I, I, P],
     'pidm_posterior_step': [P, P, P, P, F, F, F, L, P],
-    'pidm_scale_inplace': [P, P, L, P],
+    'pidm_scale': [P, P, P, L, P],
     'pidm_axpby_per_sample': [P, P, P, P, P, P, P, I, I, P],
     'pidm_fd_stencil': [P, P, I, I, I, F, F, P],
     'pidm_darcy_residual_fwd': [P, P, P, I, I, F, I, I, P],
@@ -64,7 +65,7 @@ _SIGS = {
     'pidm_head_fwd': [P, P, P, P, I, I, I, I, I, I, P],
     'pidm_head_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     'pidm_sumsq': [P, L, P, P],
-    'pidm_adam_ema_step': [P, P, P, P, P, L, F, F, F, F, I, P, P, F, F, F, I, I, P],
+    'pidm_adam_ema_step': [P, P, P, P, P, L, F, D, D, F, I, P, P, F, F, F, I, I, P],
     'pidm_mechanics_residual_fwd': [P, P, P, P, P, P, I, I, P],
     'pidm_mechanics_residual_bwd': [P, P, P, P, P, P, P, P, P, I, I, P],
     'pidm_bilinear_resize_fwd': [P, P, I, I, I, P],

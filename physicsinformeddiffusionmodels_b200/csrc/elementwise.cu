@@ -172,12 +172,12 @@ __global__ void axpby_ps_kernel(const float* __restrict__ a, const float4* __res
     }
 }
 
-__global__ void scale_kernel(float* __restrict__ x, const float* __restrict__ alpha, long long n) {
+__global__ void scale_kernel(const float* x, const float* __restrict__ alpha, float* out, long long n) {
     pdl_trigger();
     pdl_wait();
     const float a = *alpha;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        x[i] *= a;
+        out[i] = x[i] * a;
 }
 
 // ---- output head: y[b,o,hw] = sum_c x[b,hw,c] w[o,c] + bias[o]; sigmoid on last channel if asked --------
@@ -373,8 +373,8 @@ extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float
     return 0;
 }
 
-extern "C" int pidm_scale_inplace(float* x, const float* alpha_dev, long long n, void* stream) {
-    PIDM_CUDA(launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, alpha_dev, n));
+extern "C" int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream) {
+    PIDM_CUDA(launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, alpha_dev, out, n));
     PIDM_LAUNCH_CHECK("scale");
     return 0;
 }

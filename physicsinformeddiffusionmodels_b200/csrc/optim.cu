@@ -49,24 +49,37 @@ __global__ void sumsq_kernel(const float4* __restrict__ x, long long n4, const f
     }
 }
 
+// Bias corrections follow torch.optim.Adam, which evaluates 1 - beta^step in double precision on the host: with the
+// step count on the device (CUDA-graph replay) one thread per CTA evaluates them in double and shares them.  In fp32
+// 1 - 0.999^1 already carries a relative error of 6e-5 (cancellation), which would show up in the step size.
+// ema_first_step: 0 = no EMA; k >= 1 = the shadow is updated from the k-th (1-based) optimizer step on
+// (reference main.py:52,178 `if iteration > ema_start`, iteration 0-based => k = ema_start + 2).
 __global__ void adam_ema_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                float* __restrict__ v, float* __restrict__ ema, long long n, float lr, float b1, float b2,
-                                float eps, float bc1, float bc2, const int* __restrict__ step_dev,
+                                float* __restrict__ v, float* __restrict__ ema, long long n, float lr, double b1d,
+                                double b2d, float eps, int step_host, const int* __restrict__ step_dev,
                                 const float* __restrict__ gnorm_sq, float grad_scale, float max_norm, float ema_mu,
-                                int ema_on, int zero_grad) {
+                                int ema_first_step, int zero_grad) {
     pdl_trigger();
     pdl_wait();
-    if (step_dev) {   // CUDA-graph friendly: the 1-based step count lives on the device
-        const float st = (float)(*step_dev);
-        bc1 = 1.f - powf(b1, st);
-        bc2 = 1.f - powf(b2, st);
+    __shared__ float s_step, s_rs;
+    __shared__ int s_ema;
+    if (threadIdx.x == 0) {
+        const int st = step_dev ? *step_dev : step_host;          // 1-based count of this step
+        const double bc1 = 1.0 - pow(b1d, (double)st);
+        const double bc2 = 1.0 - pow(b2d, (double)st);
+        s_step = (float)((double)lr / bc1);
+        s_rs = (float)(1.0 / sqrt(bc2));
+        s_ema = (ema_first_step > 0 && st >= ema_first_step) ? 1 : 0;
     }
+    __syncthreads();
+    const float b1 = (float)b1d, b2 = (float)b2d;
     float coef = grad_scale;
     if (gnorm_sq && max_norm > 0.f) {
         float total = sqrtf(*gnorm_sq) * grad_scale;
         coef *= fminf(max_norm / (total + 1e-6f), 1.f);
     }
-    const float step = lr / bc1, rs = rsqrtf(bc2);
+    const float step = s_step, rs = s_rs;
+    const bool ema_on = s_ema != 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i] * coef;
         float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -102,17 +115,16 @@ extern "C" int pidm_sumsq(const float* x, long long n, float* out, void* stream)
 }
 
 extern "C" int pidm_adam_ema_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* ema_shadow,
-                                  long long n, float lr, float beta1, float beta2, float eps, int step,
+                                  long long n, float lr, double beta1, double beta2, float eps, int step,
                                   int* step_counter_dev, const float* grad_norm_sq_dev, float grad_scale, float max_norm, float ema_mu,
-                                  int ema_on, int zero_grad, void* stream) {
+                                  int ema_first_step, int zero_grad, void* stream) {
     PIDM_REQUIRE(step >= 1 || step_counter_dev, "adam: step is 1-based");
     if (step_counter_dev) PIDM_CUDA(launch_pdl(incr_kernel, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)stream, step_counter_dev));   // counter holds steps done so far
-    float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     PIDM_CUDA(launch_pdl(adam_ema_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, ema_shadow, n, lr, beta1,
-                                                           beta2, eps, bc1, bc2, step_counter_dev, grad_norm_sq_dev, grad_scale,
-                                                           max_norm, ema_mu, ema_on, zero_grad));
+                                                           beta2, eps, step, step_counter_dev, grad_norm_sq_dev, grad_scale,
+                                                           max_norm, ema_mu, ema_first_step, zero_grad));
     PIDM_LAUNCH_CHECK("adam_ema_step");
     return 0;
 }

@@ -215,17 +215,31 @@ class DenoisingDiffusion(nn.Module):
         return ops.q_sample(x_0, noise, t, alphas_bar_sqrt, one_minus_alphas_bar_sqrt)
 
     # ---- A3: training loss (reference :616-710) ------------------------------------------------------------
-    def model_estimation_loss(self, input, residual_func=None, c_data=1., c_residual=0., c_ineq=0., lambda_opt=0.):
+    def model_estimation_loss(self, input, residual_func=None, c_data=1., c_residual=0., c_ineq=0., lambda_opt=0.,
+                              sync_scalars=None, draw_shard=None):
+        """Reference signature plus two keyword extensions used by engine.TrainEngine:
+        sync_scalars=False returns the tracked scalars as device tensors (no host sync; default: self.sync_scalars);
+        draw_shard=(rank, world): t / eps are drawn for the GLOBAL batch (world * len(input) rows) and sliced to this
+        rank's rows -- with identical generator states on all ranks the data-parallel job consumes the same random
+        numbers as the one-process run on the concatenated batch."""
         batch_size = len(input)
-        t = torch.randint(0, self.n_steps, size=(batch_size,), device=input.device)      # RNG draw 1 (reference :625)
+        sync = self.sync_scalars if sync_scalars is None else sync_scalars
+        rank, world = draw_shard if draw_shard is not None else (0, 1)
+        lo, hi = rank * batch_size, (rank + 1) * batch_size
+        t = torch.randint(0, self.n_steps, size=(batch_size * world,), device=input.device)[lo:hi]   # draw 1 (ref :625)
         if residual_func.gov_eqs == 'darcy':
-            e = torch.randn_like(input)                                                  # RNG draw 2 (reference :636)
-            return self.darcy_loss_from_draws(input, t, e, residual_func, c_data, c_residual)
+            if world == 1:
+                e = torch.randn_like(input)                                              # RNG draw 2 (reference :636)
+            else:
+                e = torch.randn((batch_size * world,) + tuple(input.shape[1:]), device=input.device,
+                                dtype=input.dtype)[lo:hi]
+            return self.darcy_loss_from_draws(input, t, e, residual_func, c_data, c_residual, sync_scalars=sync)
         if residual_func.gov_eqs == 'mechanics':
-            return residual_func.training_loss(self, input, t, c_data, c_residual, c_ineq, lambda_opt)
+            return residual_func.training_loss(self, input, t, c_data, c_residual, c_ineq, lambda_opt,
+                                               sync_scalars=sync, draw_shard=draw_shard)
         raise ValueError('Unknown governing equations.')
 
-    def darcy_loss_from_draws(self, x_0, t, e, residual_func, c_data=1., c_residual=0.):
+    def darcy_loss_from_draws(self, x_0, t, e, residual_func, c_data=1., c_residual=0., sync_scalars=None):
         """The RNG-free body of model_estimation_loss for Darcy: q_sample -> U-Net (-> DDIM walk) -> fused
         residual + loss kernel.  Returns (loss, data_loss, mean|r|, 0., 0.)."""
         dd = self.diff_dict
@@ -233,7 +247,7 @@ class DenoisingDiffusion(nn.Module):
         x0_hat, model_out = residual_func.predict_x0((image_to_b_xy_c(x), t), ddim_func=self.ddim_sample_x0)
         loss, sums = ops.darcy_pidm_loss(x0_hat, model_out, x_0, t, residual_func.f_s_flat, dd['p2_loss_weight'],
                                          dd['posterior_variance_clipped'], c_data, c_residual, *residual_func.geometry)
-        if self.sync_scalars:
+        if self.sync_scalars if sync_scalars is None else sync_scalars:
             s = sums.tolist()                   # one host sync (the reference does two .item() calls here)
             return loss, s[0], s[2], 0., 0.
         return loss, sums[0], sums[2], 0., 0.

@@ -92,11 +92,20 @@ def _unet_grad_group(name):
 
 class TrainEngine:
     def __init__(self, model, diffusion, residuals, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, ema_mu=0.99,
-                 c_data=1.0, c_residual=1e-3, use_graph=True, world=1, bucketed_allreduce=None):
+                 c_data=1.0, c_residual=1e-3, use_graph=True, world=1, bucketed_allreduce=None, ema_start=-1,
+                 c_ineq=0., lambda_opt=0., rank=0, global_draws=False, snapshot_grad=False):
+        """ema_start: the EMA shadow is updated when the 0-based iteration index exceeds it (reference main.py:52,178
+        uses 1000); -1 = from the first step on.  The comparison runs on the device against the step counter, so it is
+        CUDA-graph safe.  global_draws (world > 1): t and eps are drawn for the GLOBAL batch from a generator that is
+        identical on every rank and sliced to this rank's rows (seed parity with the one-process run).
+        snapshot_grad: keep a copy of the (all-reduced, unclipped) flat gradient of the last step in `grad_snapshot`
+        (parity tests; the Adam kernel zeroes the live buffer)."""
         self.model, self.diffusion, self.residuals = model, diffusion, residuals
         self.lr, self.betas, self.eps, self.max_norm, self.ema_mu = lr, betas, eps, max_norm, ema_mu
-        self.c_data, self.c_residual = c_data, c_residual
-        self.world = world
+        self.c_data, self.c_residual, self.c_ineq, self.lambda_opt = c_data, c_residual, c_ineq, lambda_opt
+        self.world, self.rank = world, rank
+        self.ema_first_step = int(ema_start) + 2
+        self.global_draws = bool(global_draws) and world > 1
         # Overlap of the gradient exchange with backward (OPT-IN: PIDM_BUCKET_AR=1 or bucketed_allreduce=True): the flat
         # gradient is laid out in three readiness groups and a group is all-reduced on its own stream as soon as backward
         # has crossed the matching boundary of the U-Net.  Checked on 2 GPUs (scripts/check_bucket_ar.py: ranks stay
@@ -110,7 +119,7 @@ class TrainEngine:
         self._reduced = set()
         if self.bucketed:
             model._boundary_cb = self._on_boundary
-        self.diffusion.sync_scalars = False
+        self.grad_snapshot = torch.empty_like(self.fp.grad) if snapshot_grad else None
         self.use_graph = use_graph
         self._graph = None
         self._static_x0 = None
@@ -120,8 +129,10 @@ class TrainEngine:
     # ---- one step, eager (also the body that gets captured) -------------------------------------------------
     def _step_body(self, x0):
         fp = self.fp
+        shard = (self.rank, self.world) if self.global_draws else None
         loss, data_l, rabs, _, _ = self.diffusion.model_estimation_loss(
-            x0, residual_func=self.residuals, c_data=self.c_data, c_residual=self.c_residual, c_ineq=0., lambda_opt=0.)
+            x0, residual_func=self.residuals, c_data=self.c_data, c_residual=self.c_residual, c_ineq=self.c_ineq,
+            lambda_opt=self.lambda_opt, sync_scalars=False, draw_shard=shard)
         ops.side_stream_begin()                 # weight-gradient kernels overlap the dgrad chain (joined below)
         self._reduced = set()
         try:
@@ -137,11 +148,13 @@ class TrainEngine:
                 torch.cuda.current_stream().wait_stream(self._ar_stream)
         else:
             allreduce_flat_grad(fp.grad, self.world)
+        if self.grad_snapshot is not None:
+            self.grad_snapshot.copy_(fp.grad)
         fp.gnorm_sq.zero_()
         call('pidm_sumsq', fp.grad, fp.total, fp.gnorm_sq, stream())
         call('pidm_adam_ema_step', fp.flat, fp.grad, fp.exp_avg, fp.exp_avg_sq, fp.ema, fp.total, self.lr,
              self.betas[0], self.betas[1], self.eps, 0, fp.step_dev, fp.gnorm_sq, 1.0 / self.world, self.max_norm,
-             self.ema_mu, 1, 1, stream())
+             self.ema_mu, self.ema_first_step, 1, stream())
         return loss.detach(), data_l, rabs
 
     def _on_boundary(self, group):
@@ -162,27 +175,44 @@ class TrainEngine:
 
     def step(self, x0):
         """x0: [B, 2, 64, 64] fp32 on the device.  Returns (loss, data_loss, mean|r|) as device tensors."""
-        if not self.use_graph:
-            out = self._step_body(x0)
+        try:
+            if not self.use_graph:
+                out = self._step_body(x0)
+                self.steps_done += 1
+                return out
+            if self._graph is None:
+                self._capture(x0)
+            if x0.shape != self._static_x0.shape:
+                raise ValueError(f'TrainEngine was captured for batches of shape {tuple(self._static_x0.shape)}, got '
+                                 f'{tuple(x0.shape)}: build a second engine (or use_graph=False) for another batch size')
+            self._static_x0.copy_(x0, non_blocking=True)
+            self._graph.replay()
             self.steps_done += 1
-            return out
-        if self._graph is None:
-            self._capture(x0)
-        self._static_x0.copy_(x0, non_blocking=True)
-        self._graph.replay()
-        self.steps_done += 1
-        return self._static_out
+            return self._static_out
+        finally:
+            packer = getattr(self.model, '_packer', None)
+            if packer is not None:
+                packer.invalidate()              # the optimizer kernel rewrote the weights behind autograd's back
 
     def _capture(self, x0):
         self._static_x0 = x0.clone()
-        # warm-up on a side stream (allocator, lazy module state, table uploads), as CUDA-graph capture requires
+        fp = self.fp
+        # The warm-up below (allocator, lazy module state, table uploads; on a side stream as capture requires) runs real
+        # steps: snapshot every piece of training state first and put it back afterwards, so that the first batch gets
+        # exactly ONE optimizer update and the RNG stream continues where the caller left it.
+        keep = [t.clone() for t in (fp.flat, fp.exp_avg, fp.exp_avg_sq, fp.ema, fp.step_dev)]
+        rng = torch.cuda.get_rng_state(fp.flat.device)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
                 self._step_body(self._static_x0)
-                self.steps_done += 1
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for t, k in zip((fp.flat, fp.exp_avg, fp.exp_avg_sq, fp.ema, fp.step_dev), keep):
+            t.copy_(k)
+        fp.grad.zero_()
+        torch.cuda.set_rng_state(rng, fp.flat.device)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
@@ -201,11 +231,17 @@ class SampleEngine:
     """B200-native ancestral sampling loop (reference denoising_utils.py:388-545 p_sample / p_sample_loop, called from
     sample.py:145): the same per-step work as DenoisingDiffusion.p_sample -- x0 estimate through the residual object
     (network call, or the DDIM walk when use_ddim_x0), Darcy residual, posterior step with sigma_t = sqrt(beta_t) --
-    but with the time index and the posterior coefficients living on the DEVICE, so that ONE captured CUDA graph is
-    replayed n_steps times and nothing is decided on the host inside the loop.  `DenoisingDiffusion.p_sample_loop`
-    remains the drop-in API (host-side step index, CPU trajectory); this is the throughput path."""
+    but with the time index and the posterior coefficients living on the DEVICE, so that a captured CUDA graph of
+    `steps_per_graph` consecutive steps is replayed n_steps / steps_per_graph times and nothing is decided on the host
+    inside the loop.  The packed bf16 weights are produced once per loop, not once per step (they only change when an
+    optimizer has run).  `DenoisingDiffusion.p_sample_loop` remains the drop-in API (host-side step index, CPU
+    trajectory); this is the throughput path.
 
-    def __init__(self, model, diffusion, residuals, batch, image_shape=(2, 64, 64), surpress_noise=True, use_graph=True):
+    external_noise=True: the per-step noise z is read from a static buffer that `sample(noises=...)` refreshes before
+    every replay (parity tests inject the reference's draws); otherwise z is drawn by torch's Philox inside the graph."""
+
+    def __init__(self, model, diffusion, residuals, batch, image_shape=(2, 64, 64), surpress_noise=True, use_graph=True,
+                 steps_per_graph=None, external_noise=False):
         from .denoising_utils import _axpby, image_to_b_xy_c, generalized_b_xy_c_to_image
         self._axpby, self._to_rows, self._to_img = _axpby, image_to_b_xy_c, generalized_b_xy_c_to_image
         self.model, self.diffusion, self.residuals = model, diffusion, residuals
@@ -213,7 +249,13 @@ class SampleEngine:
         dd = diffusion.diff_dict
         dev = dd['alphas'].device
         self.n_steps = diffusion.n_steps
+        if steps_per_graph is None:
+            steps_per_graph = next(k for k in (10, 5, 4, 2, 1) if self.n_steps % k == 0)
+        assert self.n_steps % steps_per_graph == 0, 'steps_per_graph must divide n_steps'
+        self.k = steps_per_graph if use_graph else 1
+        self.external_noise = external_noise
         self.x = torch.zeros(batch, *image_shape, device=dev)
+        self.z = torch.zeros(self.k, batch, *image_shape, device=dev) if external_noise else None
         self.t = torch.zeros(batch, device=dev, dtype=torch.long)
         self.residual = None
         self.c1 = dd['posterior_mean_coef1'].float().contiguous()
@@ -225,7 +267,7 @@ class SampleEngine:
         self.sigma = sig
         self._graph = None
 
-    def _step_body(self):
+    def _step_body(self, j=0):
         with torch.no_grad():
             x, t = self.x, self.t
             out = self.residuals.compute_residual(((self._to_rows(x), t),), reduce='per-batch', return_model_out=True,
@@ -233,7 +275,7 @@ class SampleEngine:
             model_out = out['model_out']
             if model_out.dim() == 3:
                 model_out = self._to_img(model_out)
-            z = torch.randn_like(x)                                     # drawn at every step, t == 0 included
+            z = self.z[j] if self.external_noise else torch.randn_like(x)   # drawn at every step, t == 0 included
             new_x = self._axpby(self.c1[t].contiguous(), model_out.float(), self.c2[t].contiguous(), x,
                                 self.sigma[t].contiguous(), z)
             if self.residual is None:
@@ -254,11 +296,18 @@ class SampleEngine:
         self.t.fill_(self.n_steps - 1)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._step_body()
+            for j in range(self.k):
+                self._step_body(j)
 
-    def sample(self, x_init=None, trajectory=False):
+    def sample(self, x_init=None, trajectory=False, noises=None):
         """Runs the whole loop; returns (x_0 [B,C,P,P], residual of the last step [B,P*P,3]) as device tensors and,
-        if asked, the trajectory [n_steps+1,B,C,P,P] (device)."""
+        if asked, the trajectory [n_steps+1,B,C,P,P] (device; recorded per replay, so it needs steps_per_graph=1).
+        noises [n_steps,B,C,P,P]: the z of every step (external_noise engines only)."""
+        assert (noises is not None) == self.external_noise, 'noises= goes with external_noise=True'
+        assert not (trajectory and self.k != 1), 'trajectory=True needs steps_per_graph=1'
+        packer = getattr(self.model, '_packer', None)
+        if packer is not None:
+            packer.refresh_if_stale(ops.act_dtype())       # the captured steps do not re-pack the weights
         if self.use_graph and self._graph is None:
             self._capture()
         if x_init is None:
@@ -266,7 +315,9 @@ class SampleEngine:
         self.x.copy_(x_init)
         self.t.fill_(self.n_steps - 1)
         traj = [self.x.clone()] if trajectory else None
-        for _ in range(self.n_steps):
+        for it in range(self.n_steps // self.k):
+            if self.external_noise:
+                self.z.copy_(noises[it * self.k:(it + 1) * self.k])
             if self.use_graph:
                 self._graph.replay()
             else:

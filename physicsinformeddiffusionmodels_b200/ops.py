@@ -53,6 +53,18 @@ def _need_cuda(*ts):
                                'There is no CPU fallback on the product path.')
 
 
+def _need_f32(**named):
+    """Raw device pointers cross the C ABI: a table / field of the wrong dtype or with strides would be read as garbage,
+    so the public wrappers check what they hand over (fp32, contiguous, CUDA)."""
+    for k, t in named.items():
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f'{k}: expected a CUDA tensor (no CPU fallback on the product path)')
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f'{k}: expected a contiguous float32 tensor, got {t.dtype}, strides {t.stride()}')
+
+
 # ----------------------------------------------------------------------------------------------
 # layout
 # ----------------------------------------------------------------------------------------------
@@ -600,6 +612,7 @@ def head(x, w, b, sigmoid_last=False):
 # ----------------------------------------------------------------------------------------------
 def q_sample(x0, noise, t, sqrt_ab, sqrt_1mab):
     _need_cuda(x0, noise, t)
+    _need_f32(sqrt_ab=sqrt_ab, sqrt_1mab=sqrt_1mab)
     x0 = x0.contiguous().float()
     xt = torch.empty_like(x0)
     call('pidm_qsample', x0, noise.contiguous().float(), t.to(torch.int64).contiguous(), sqrt_ab, sqrt_1mab, xt,
@@ -635,6 +648,7 @@ class _DarcyResidual(torch.autograd.Function):
 
 def darcy_residual(x0hat, f_s, domain_length=1.0, reverse_d1=True, pixels_at_boundary=True):
     _need_cuda(x0hat)
+    _need_f32(f_s=f_s)
     assert x0hat.shape[1] == 2, 'Darcy fields are (p, K)'
     return _DarcyResidual.apply(x0hat.contiguous().float(), f_s,
                                 (float(domain_length), int(reverse_d1), int(pixels_at_boundary)))
@@ -663,19 +677,25 @@ class _DarcyPidmLoss(torch.autograd.Function):
     def backward(ctx, g, _unused):
         gx, gm = ctx.saved_tensors
         g = g.contiguous().float()
-        call('pidm_scale_inplace', gx, g, gx.numel(), stream())
+        # out of place: the saved gradients stay intact, so a second backward (retain_graph) scales the originals again
+        ox = torch.empty_like(gx)
+        call('pidm_scale', gx, g, ox, gx.numel(), stream())
+        om = None
         if gm is not None:
-            call('pidm_scale_inplace', gm, g, gm.numel(), stream())
-        return gx, gm, None, None, None, None, None, None, None, None
+            om = torch.empty_like(gm)
+            call('pidm_scale', gm, g, om, gm.numel(), stream())
+        return ox, om, None, None, None, None, None, None, None, None
 
 
 def darcy_pidm_loss(x0hat, model_out, target, t, f_s, p2w, pvar, c_data, c_res, domain_length=1.0, reverse_d1=True,
                     pixels_at_boundary=True):
     """Returns (loss, sums) with sums = [data_loss, residual_loss, mean|r|] on the device."""
     _need_cuda(x0hat, target)
+    _need_f32(f_s=f_s, p2w=p2w, pvar=pvar)
     geom = (float(domain_length), int(reverse_d1), int(pixels_at_boundary))
     if model_out is not None and model_out is x0hat:
         model_out = None
-    return _DarcyPidmLoss.apply(x0hat.contiguous(), None if model_out is None else model_out.contiguous(),
+    return _DarcyPidmLoss.apply(x0hat.contiguous().float(),
+                                None if model_out is None else model_out.contiguous().float(),
                                 target.contiguous().float(), t.to(torch.int64).contiguous(), f_s, p2w, pvar, c_data, c_res,
                                 geom)

@@ -68,6 +68,7 @@ class WeightPacker:
         self._table = None
         self._buf = None
         self._n = 0
+        self._packed_for = None
 
     def add(self, spec):
         self.specs.append(spec)
@@ -99,6 +100,20 @@ class WeightPacker:
         self._table, self._host = _to_device_bytes(arr, device)
         self._n = len(rows)
 
+    def _versions(self, dtype):
+        return (tuple(s.weight.data_ptr() for s in self.specs), tuple(s.weight._version for s in self.specs), dtype)
+
+    def invalidate(self):
+        """Parameters were changed behind autograd's back (flat-buffer optimizer kernel): the packed copy is stale."""
+        self._packed_for = None
+
+    def stale(self, dtype):
+        return self._packed_for != self._versions(dtype)
+
+    def refresh_if_stale(self, dtype):
+        if self.specs and self.stale(dtype):
+            self.refresh(dtype)
+
     def refresh(self, dtype):
         """Re-pack all weights (one launch).  Rebuilds the table if parameters moved (e.g. .to(device))."""
         if not self.specs:
@@ -109,6 +124,7 @@ class WeightPacker:
             self._build(w0.device, dtype)
             self._key = key
         call('pidm_pack_weights', self._table, self._n, _lib.DTYPE_CODE[dtype], stream())
+        self._packed_for = self._versions(dtype)
 
 
 class MlpTable:

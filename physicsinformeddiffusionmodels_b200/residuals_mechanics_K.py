@@ -143,14 +143,20 @@ class ResidualsMechanics:
         raise ValueError('Unknown reduction method.')
 
     # ---- hooks used by DenoisingDiffusion (mechanics branch of the reference's loss / sampler) ------------------
-    def training_loss(self, diffusion, input, t, c_data, c_residual, c_ineq, lambda_opt):
+    def training_loss(self, diffusion, input, t, c_data, c_residual, c_ineq, lambda_opt, sync_scalars=True,
+                      draw_shard=None):
         """model_estimation_loss for gov_eqs='mechanics' (reference denoising_utils.py:629-710)."""
         from . import ops
         from .denoising_utils import image_to_b_xy_c
         dd = diffusion.diff_dict
         conditioning, x_0, bcs = torch.tensor_split(input, (3, 6), dim=1)
         x_0 = x_0.contiguous()
-        e = torch.randn_like(x_0)
+        if draw_shard is None or draw_shard[1] == 1:
+            e = torch.randn_like(x_0)
+        else:
+            rank, world = draw_shard
+            B = x_0.shape[0]
+            e = torch.randn((B * world,) + tuple(x_0.shape[1:]), device=x_0.device, dtype=x_0.dtype)[rank * B:(rank + 1) * B]
         x = ops.q_sample(x_0, e, t, dd['alphas_bar_sqrt'], dd['one_minus_alphas_bar_sqrt'])
         x = torch.cat((x, conditioning), dim=1)
         vf = conditioning[:, 0, 0, 0]
@@ -165,10 +171,15 @@ class ResidualsMechanics:
         loss = data_loss + (c_residual * 0.5 * residual ** 2 / var[:, None]).mean()
         ineq_track = 0.
         if c_ineq > 0.:
-            loss = loss + (c_ineq * 0.5 * out['inequality'] ** 2 / var).mean()
-            ineq_track = out['inequality'].mean().item()
+            # reference quirk kept (:679,:694): `var` is extracted with the residual's rank ([B,1]) while the inequality
+            # is [B], so the quotient broadcasts to [B,B]: mean_i(1/var_i) * mean_j(ineq_j^2) * c_ineq / 2
+            loss = loss + (c_ineq * 0.5 * out['inequality'][None, :] ** 2 / var[:, None]).mean()
+            ineq_track = out['inequality'].mean()
         loss = loss + (lambda_opt * out['optimizer']).mean()
-        return loss, data_loss.item(), residual.abs().mean().item(), ineq_track, out['optimizer'].mean().item()
+        tracked = (data_loss.detach(), residual.detach().abs().mean(), ineq_track, out['optimizer'].detach().mean())
+        if sync_scalars:
+            tracked = tuple(float(v) for v in tracked)
+        return (loss,) + tracked
 
     def sampling_residual(self, diffusion, x, conditioning_input, t_vec, return_optimizer, return_inequality, sample):
         from .denoising_utils import image_to_b_xy_c

@@ -334,9 +334,13 @@ class Unet3D(nn.Module):
         dt = ops.act_dtype()
         # the weight re-packing (one launch over all layers) runs on a forked stream and overlaps the input layout
         # change and the time-conditioning MLPs; it is joined before the first convolution
+        # Inference (no_grad): the packed copy is reused as long as no parameter changed (tensor version counters;
+        # engine.TrainEngine invalidates explicitly because its optimizer kernel writes the flat buffer directly), so a
+        # 250-step sampling loop packs once instead of 250 times.
         pack_stream = ops.fork_stream()
-        with torch.cuda.stream(pack_stream):
-            self._packer.refresh(dt)
+        if torch.is_grad_enabled() or self._packer.stale(dt):
+            with torch.cuda.stream(pack_stream):
+                self._packer.refresh(dt)
         # pre-zeroed scratch for the GroupNorm statistics that the conv epilogues accumulate (<= 64 norms)
         ops.zero_pool_begin(64 * (x.shape[0] * self.groups * 2 + 32), x.device)
         h = ops.nchw_to_nhwc(x.float(), self._cin_pad, dt)

@@ -124,6 +124,29 @@ def test_sampling_loop_matches_reference(golden):
     assert rel(r, gd['residual']) < 2e-3          # residual amplifies x0 differences by 1/h^2
 
 
+def replay_draws_100(gd):
+    """the 101 draws of the 100-step reference run (x_T, then one z per step), regenerated from the stored seed"""
+    torch.manual_seed(int(gd['seed']))
+    draws = torch.stack([torch.randn(1, 2, 64, 64) for _ in range(101)])
+    assert torch.equal(draws.double().sum(dim=(1, 2, 3, 4)), gd['noise_checksum']), \
+        'CPU generator does not reproduce the draws of the golden run (torch version mismatch?)'
+    return draws
+
+
+def test_sampling_loop_100_steps_matches_reference(golden):
+    """The reference's default 100-step ancestral loop at B=1 (denoising_utils.py:494-545): errors of the x0
+    estimate are re-injected at every step, so this is the long-horizon check of the sampler algebra."""
+    gd = golden('sample_loop_100.pt')
+    cfg = O.unet_config(dim=32, channels=2)
+    sd = O.make_test_state_dict(cfg, 0)
+    tables = O.diffusion_tables(100)
+    draws = replay_draws_100(gd)
+    with torch.no_grad():
+        x, r = O.p_sample_loop(sd, cfg, draws[0], list(draws[1:]), tables, 100)
+    assert rel(x, gd['x_final']) < 1e-3, rel(x, gd['x_final'])
+    assert abs(r.abs().mean().item() / gd['residual_abs_mean'].item() - 1) < 1e-2
+
+
 def test_q4_stiffness_known_answer(golden):
     """Closed-form 99-line-topopt KE (E=1, nu=0.3) == the Gauss-integrated Q4 used by the reference run."""
     KE = O.q4_plane_stress_stiffness()
