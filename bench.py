@@ -17,7 +17,16 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+_IMPL = next((sys.argv[i + 1] for i, a in enumerate(sys.argv[:-1]) if a == '--impl'), 'b200')
+if _IMPL in ('reference', 'cpu_extras'):
+    # CPU legs: hide the GPU before torch initialises (the reference picks `cuda` whenever it is available)
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''
+if _IMPL == 'b200':
+    sys.path.insert(0, ROOT)
+else:
+    # reference legs import the UNMODIFIED reference `src` package (oracle/ref_arm.py): the repo root, whose `src/`
+    # drop-in package would shadow it, must not be importable in this process
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or '.') != ROOT]
 
 import torch  # noqa: E402
 
@@ -87,71 +96,23 @@ def log(msg):
     print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
 
 
-def usable_cores():
-    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota (a shared GPU box reports
-    every host core in os.cpu_count(); spawning that many threads inside a small quota is pathologically slow)."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    try:
-        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
-        if q != 'max':
-            n = min(n, max(1, int(float(q) / float(per))))
-    except Exception:
-        try:
-            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
-            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
-            if q > 0:
-                n = min(n, max(1, q // per))
-        except Exception:
-            pass
-    return max(1, n)
-
-
-def cpu_reference_steps(steps, warmup, batch=PER_GPU_BATCH, budget_s=150.0):
-    from oracle import pidm_oracle as O
-    ncores = usable_cores()
-    torch.set_num_threads(ncores)
-    log(f'cpu reference: {ncores} usable cores (os.cpu_count()={os.cpu_count()}), batch {batch}')
-    t_begin = time.perf_counter()
-    cfg = O.unet_config(dim=32, channels=2)
-    sd = O.make_test_state_dict(cfg, 0)
-    sdr = {k: v.clone().requires_grad_('freqs' not in k) for k, v in sd.items()}
-    train = [v for v in sdr.values() if v.requires_grad]
-    m = [torch.zeros_like(p) for p in train]
-    v = [torch.zeros_like(p) for p in train]
-    ema = [p.detach().clone() for p in train]
-    tables = O.diffusion_tables(100)
-    torch.manual_seed(0)
-    x0 = torch.randn(batch, 2, 64, 64)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        t = torch.randint(0, 100, (batch,))
-        e = torch.randn_like(x0)
-        for p in train:
-            p.grad = None
-        loss, _ = O.darcy_training_loss(sdr, cfg, x0, t, e, tables, 1.0, 1e-3)
-        loss.backward()
-        with torch.no_grad():
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in train]
-            O.adam_ema_step(train, grads, m, v, ema, it + 1)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-        log(f'cpu reference: iteration {it} took {time.perf_counter() - t0:.2f} s')
-        if times and time.perf_counter() - t_begin > budget_s:
-            break                                  # bounded sample
-    steps = len(times)
-    sec = sum(times) / len(times)
-    return dict(value=batch / sec, unit='samples/s', cores=ncores, kind='port', ms_per_step=sec * 1e3,
-                sample=f'{steps} training iterations at batch {batch} after {warmup} warm-up, torch {torch.__version__} '
-                       f'CPU, {ncores} threads (oracle/pidm_oracle.py restatement of main.py:157-183)')
+def _ref_arm():
+    """oracle/ref_arm.py, loaded by file path (the repo root is not importable in the reference legs)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('pidm_ref_arm', os.path.join(ROOT, 'oracle', 'ref_arm.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the reference's own training iteration on the host cores (unmodified modules from
+    baseline/_ref/reference when present, else the oracle port), bounded sample."""
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    r = cpu_reference_steps(steps, warmup)
-    out = {'metric': METRIC, 'value': r['value'], 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': steps,
+    r = _ref_arm().cpu_train_baseline(steps, warmup, PER_GPU_BATCH)
+    out = {'metric': METRIC, 'value': r['value'], 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': r['steps'],
            'warmup': warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
            'config': {'workload': 'Darcy 64x64 PIDM train step (mean-mode x0), Unet3D dim=32, batch 32, host CPU',
@@ -160,6 +121,33 @@ def run_reference(args, rank):
            'e2e': {'value': r['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0}
     print(json.dumps(out), flush=True)
+
+
+def run_side_leg(args):
+    """internal legs spawned by the b200 arm: `--impl cpu_extras` (BASELINE.md 3.5 CPU timings) and `--impl torch_cuda`
+    (the reference on the same B200 through stock PyTorch-CUDA)."""
+    ra = _ref_arm()
+    out = ra.cpu_extras() if args.impl == 'cpu_extras' else ra.torch_cuda_baselines(PER_GPU_BATCH)
+    print(json.dumps(out), flush=True)
+
+
+def spawn_leg(impl, timeout_s, *extra):
+    """run `bench.py --impl <impl>` in a fresh process (own sys.path, own CUDA context) and parse its JSON line"""
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', impl, *extra]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT')}
+    try:
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s, env=env,
+                           cwd=ROOT)
+        for line in p.stderr.splitlines():
+            if line.startswith('[ref_arm'):
+                print(line, file=sys.stderr, flush=True)
+        lines = [l for l in p.stdout.splitlines() if l.startswith('{')]
+        if p.returncode != 0 or not lines:
+            return {'error': f'leg {impl} rc={p.returncode}: {p.stderr.strip().splitlines()[-1][:300] if p.stderr.strip() else ""}'}
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return {'error': f'leg {impl} exceeded {timeout_s} s'}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -344,7 +332,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'cpu_extras', 'torch_cuda'])
+    ap.add_argument('--no-torch-cuda-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sampling', action='store_true')
@@ -354,6 +343,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
         return run_reference(args, rank)
+    if args.impl in ('cpu_extras', 'torch_cuda'):
+        return run_side_leg(args)
     assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
     import torch.distributed as dist
     from physicsinformeddiffusionmodels_b200 import _lib, ops
@@ -478,9 +469,15 @@ def main():
         if not args.no_sampling:
             log('sampling loop (configs[3]): 250 ancestral steps, batch 16')
             extra['sampling'] = sampling_bench(model, res, dev)
+        if not args.no_torch_cuda_baseline:
+            log('torch_cuda_baseline: the reference on this GPU through stock PyTorch-CUDA (subprocess)')
+            extra['torch_cuda_baseline'] = spawn_leg('torch_cuda', 240)
         if not args.no_cpu_baseline:
-            cb = cpu_reference_steps(3, 1)
-            extra['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            log('cpu_baseline: the reference training iteration on the host cores (subprocess)')
+            cb = spawn_leg('reference', 300, '--steps', '3', '--warmup', '1')
+            extra['cpu_baseline'] = cb.get('cpu_baseline', cb)
+            log('cpu extras: residual operator and p_sample_loop of the reference on the host cores (subprocess)')
+            extra['cpu_baseline_extras'] = spawn_leg('cpu_extras', 300)
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -159,16 +159,20 @@ int pidm_attn_bwd(const void* qkv, const void* dout, void* dqkv, int B, int n_to
 /* SinusoidalPosEmb + time_mlp (src/unet_model.py:147-159,464-469); also returns SiLU(temb) for the block MLPs */
 int pidm_time_embed_fwd(const long long* t, const float* W1, const float* b1, const float* W2, const float* b2,
                         float* emb, float* h1, float* temb, float* silu_t, int B, int dim, int td, void* stream);
+/* workspace float[2*B*td]; parts: bit 1 = activation gradients into the workspace, bit 0 = weight / bias gradients from
+ * it (ACCUMULATED) -- the second half only feeds the optimizer and may be issued on another stream after the first. */
 int pidm_time_embed_bwd(const float* d_silu_t, const float* emb, const float* h1, const float* temb, const float* W2,
-                        float* dW1, float* db1, float* dW2, float* db2, int B, int dim, int td, void* stream);
+                        float* dW1, float* db1, float* dW2, float* db2, float* workspace, int B, int dim, int td,
+                        int parts, void* stream);
 /* every ResnetBlock.mlp Linear in one launch (src/unet_model.py:246-249,258-262).  MlpEntry (56 bytes):
  *   { const float* W; const float* b; float* dW; float* db; float* out; const float* dout; int n, pad_; }
  *   out_e[b, j] = b_e[j] + W_e[j,:] . silu_t[b,:] ;  backward accumulates dW_e, db_e and overwrites d_silu_t. */
 int pidm_mlp_entry_size(void);
 int pidm_block_mlps_fwd(const void* table_dev, int n_entries, int max_rows, const float* silu_t, int B, int td,
                         void* stream);
+/* parts: bit 0 = weight / bias gradients, bit 1 = input gradient d_silu_t (independent halves) */
 int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max_rows, const float* silu_t, float* d_silu_t, int B,
-                        int td, void* stream);
+                        int td, int parts, void* stream);
 
 /* ---- output head: final 1x1 conv to NCHW fp32 (+ sigmoid on the last channel) src/unet_model.py:517,619-621 */
 int pidm_head_fwd(const void* x, const float* w, const float* bias, float* y, int B, int HW, int C, int O,

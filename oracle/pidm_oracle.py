@@ -261,7 +261,7 @@ def _mid_attention(sd, p, x, heads, dim_head):
 def time_embedding(sd, time, dim):
     # SinusoidalPosEmb + time_mlp, unet_model.py:147-159,464-469  (nn.GELU() = exact erf form)
     half = dim // 2
-    f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    f = torch.exp(torch.arange(half, dtype=torch.float32, device=time.device) * -(math.log(10000) / (half - 1)))
     e = time.to(torch.float32)[:, None] * f[None, :]
     e = torch.cat((e.sin(), e.cos()), dim=-1).to(sd['time_mlp.1.weight'].dtype)
     e = F.linear(e, sd['time_mlp.1.weight'], sd['time_mlp.1.bias'])
@@ -369,7 +369,7 @@ def darcy_residual(x0_pred, domain_length=1.0, reverse_d1=True, pixels_at_bounda
     p0, p1 = fd_first(p, -2, d0), fd_first(p, -1, d1)
     p00, p11 = fd_second(p, -2, d0), fd_second(p, -1, d1)
     K0, K1 = fd_first(K, -2, d0), fd_first(K, -1, d1)
-    fs = darcy_source(P, dtype=x0_pred.dtype)
+    fs = darcy_source(P, dtype=x0_pred.dtype).to(x0_pred.device)     # (device-aware: bench's torch-CUDA leg runs this on the GPU)
     eq0 = (-K * p00 - K0 * p0) + (-K * p11 - K1 * p1) - fs
     bc0 = torch.zeros_like(p)
     bc1 = torch.zeros_like(p)

@@ -58,10 +58,10 @@ _SIGS = {
     'pidm_attn_fwd': [P, P, I, I, I, I, P],
     'pidm_attn_bwd': [P, P, P, I, I, I, I, P],
     'pidm_time_embed_fwd': [P, P, P, P, P, P, P, P, P, I, I, I, P],
-    'pidm_time_embed_bwd': [P, P, P, P, P, P, P, P, P, I, I, I, P],
+    'pidm_time_embed_bwd': [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     'pidm_mlp_entry_size': [],
     'pidm_block_mlps_fwd': [P, I, I, P, I, I, P],
-    'pidm_block_mlps_bwd': [P, I, I, P, P, I, I, P],
+    'pidm_block_mlps_bwd': [P, I, I, P, P, I, I, I, P],
     'pidm_head_fwd': [P, P, P, P, I, I, I, I, I, I, P],
     'pidm_head_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     'pidm_sumsq': [P, L, P, P],

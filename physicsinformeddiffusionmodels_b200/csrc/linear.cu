@@ -47,33 +47,48 @@ __global__ void time_embed_fwd_kernel(const long long* __restrict__ t, const flo
     silu_t[(size_t)b * td + j] = silu_f(o);
 }
 
-// backward: given d_silu_t; gradients of W1,b1,W2,b2 are ACCUMULATED with atomics (B CTAs).
-__global__ void time_embed_bwd_kernel(const float* __restrict__ d_silu, const float* __restrict__ emb,
-                                      const float* __restrict__ h1, const float* __restrict__ temb,
-                                      const float* __restrict__ W2, float* __restrict__ dW1, float* __restrict__ db1,
-                                      float* __restrict__ dW2, float* __restrict__ db2, int dim, int td) {
+// backward, stage 1 (one CTA per sample, blockDim = td): dt = d_silu * silu'(temb), dh = (W2^T dt) * gelu'(h1); both
+// are written to the workspace [2, B, td] for stage 2.
+__global__ void time_embed_bwd_act_kernel(const float* __restrict__ d_silu, const float* __restrict__ h1,
+                                          const float* __restrict__ temb, const float* __restrict__ W2,
+                                          float* __restrict__ dt_out, float* __restrict__ dh_out, int td) {
     pdl_trigger();
     pdl_wait();
-    extern __shared__ float sm[];   // e[dim] | a1[td] | dt[td] | dh[td]
-    float* e = sm;
-    float* a1 = e + dim;
-    float* dt = a1 + td;
-    float* dh = dt + td;
+    extern __shared__ float sm[];   // dt[td]
+    float* dt = sm;
     const int b = blockIdx.x, j = threadIdx.x;
-    if (j < dim) e[j] = emb[(size_t)b * dim + j];
-    a1[j] = gelu_erf(h1[(size_t)b * td + j]);
-    float dtj = d_silu[(size_t)b * td + j] * silu_grad_f(temb[(size_t)b * td + j]);
+    const float dtj = d_silu[(size_t)b * td + j] * silu_grad_f(temb[(size_t)b * td + j]);
     dt[j] = dtj;
+    dt_out[(size_t)b * td + j] = dtj;
     __syncthreads();
-    atomicAdd(&db2[j], dtj);
-    for (int k = 0; k < td; ++k) atomicAdd(&dW2[(size_t)j * td + k], dtj * a1[k]);
     // da1[j] = sum_i dt[i] W2[i][j]  (column read: coalesced across threads j)
     float da = 0.f;
+#pragma unroll 8
     for (int i = 0; i < td; ++i) da += dt[i] * W2[(size_t)i * td + j];
-    float dhj = da * gelu_erf_grad(h1[(size_t)b * td + j]);
-    dh[j] = dhj;
-    atomicAdd(&db1[j], dhj);
-    for (int k = 0; k < dim; ++k) atomicAdd(&dW1[(size_t)j * dim + k], dhj * e[k]);
+    dh_out[(size_t)b * td + j] = da * gelu_erf_grad(h1[(size_t)b * td + j]);
+}
+
+// backward, stage 2 (one CTA per output row j, blockDim = td = columns k): the weight gradients are small
+// [td x B] x [B x td] products -- every element is owned by exactly one thread, so they are accumulated with plain
+// read-modify-writes (the first version issued td + dim contended atomics per thread from B CTAs: 26 us).
+//   dW2[j,k] += sum_b dt[b,j] gelu(h1[b,k]);  db2[j] += sum_b dt[b,j];  dW1[j,k<dim] += sum_b dh[b,j] emb[b,k];  db1[j] += ...
+__global__ void time_embed_bwd_wgrad_kernel(const float* __restrict__ dt, const float* __restrict__ dh,
+                                            const float* __restrict__ emb, const float* __restrict__ h1,
+                                            float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                            float* __restrict__ db2, int B, int dim, int td) {
+    pdl_trigger();
+    pdl_wait();
+    const int j = blockIdx.x, k = threadIdx.x;
+    float w2 = 0.f, w1 = 0.f, s2 = 0.f, s1 = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float dtj = dt[(size_t)b * td + j], dhj = dh[(size_t)b * td + j];      // broadcast loads
+        w2 += dtj * gelu_erf(h1[(size_t)b * td + k]);
+        if (k < dim) w1 += dhj * emb[(size_t)b * dim + k];
+        s2 += dtj; s1 += dhj;
+    }
+    dW2[(size_t)j * td + k] += w2;
+    if (k < dim) dW1[(size_t)j * dim + k] += w1;
+    if (k == 0) { db2[j] += s2; db1[j] += s1; }
 }
 
 struct MlpEntry {
@@ -238,11 +253,23 @@ extern "C" int pidm_time_embed_fwd(const long long* t, const float* W1, const fl
     return 0;
 }
 
+// workspace: float[2 * B * td] (dt | dh), written by stage 1 and read by stage 2.
+// parts: bit 1 = stage 1 (activation gradients into the workspace), bit 0 = stage 2 (weight / bias gradients from the
+// workspace, ACCUMULATED).  Stage 2 only feeds the optimizer: a caller may issue it on the stream of its other
+// weight-gradient kernels, ordered after stage 1.
 extern "C" int pidm_time_embed_bwd(const float* d_silu_t, const float* emb, const float* h1, const float* temb,
-                                   const float* W2, float* dW1, float* db1, float* dW2, float* db2, int B, int dim,
-                                   int td, void* stream) {
+                                   const float* W2, float* dW1, float* db1, float* dW2, float* db2, float* workspace,
+                                   int B, int dim, int td, int parts, void* stream) {
     PIDM_REQUIRE(td <= 1024 && dim <= td, "time_embed_bwd: need dim<=td<=1024");
-    PIDM_CUDA(launch_pdl(time_embed_bwd_kernel, dim3(B), dim3(td), (size_t)((dim + 3 * td) * sizeof(float)), (cudaStream_t)stream, d_silu_t, emb, h1, temb, W2, dW1, db1, dW2, db2, dim, td));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dt = workspace;
+    float* dh = workspace + (size_t)B * td;
+    if (parts & 2)
+        PIDM_CUDA(launch_pdl(time_embed_bwd_act_kernel, dim3(B), dim3(td), (size_t)(td * sizeof(float)), st, d_silu_t, h1, temb,
+                             W2, dt, dh, td));
+    if (parts & 1)
+        PIDM_CUDA(launch_pdl(time_embed_bwd_wgrad_kernel, dim3(td), dim3(td), (size_t)0, st, (const float*)dt,
+                             (const float*)dh, emb, h1, dW1, db1, dW2, db2, B, dim, td));
     PIDM_LAUNCH_CHECK("time_embed_bwd");
     return 0;
 }
@@ -271,17 +298,23 @@ extern "C" int pidm_block_mlps_fwd(const void* table_dev, int n_entries, int max
 }
 
 // weight/bias grads accumulate into the table's dW/db pointers; d_silu_t is overwritten.
+// parts: bit 0 = weight / bias gradients, bit 1 = input gradient (d_silu_t) -- the two halves are independent, so a
+// caller can put the weight-gradient half on the stream of its other weight-gradient kernels.
 extern "C" int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max_rows, const float* silu_t,
-                                   float* d_silu_t, int B, int td, void* stream) {
+                                   float* d_silu_t, int B, int td, int parts, void* stream) {
     PIDM_REQUIRE(td <= 704 && td % 32 == 0, "block_mlps: td must be a multiple of 32, <= 704");
     cudaStream_t st = (cudaStream_t)stream;
     size_t smem = (size_t)MLP_BCHUNK * (td + 1) * sizeof(float);
     if (int e = mlp_smem_attr(smem)) return e;
-    dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
-    PIDM_CUDA(launch_pdl(block_mlps_wgrad_kernel, dim3(grid), dim3(256), (size_t)(smem), st, (const MlpEntry*)table_dev, silu_t, B, td));
-    PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
-    dim3 dgrid(MLP_DG_GROUPS, ceil_div(B, MLP_BCHUNK));
-    PIDM_CUDA(launch_pdl(block_mlps_dgrad_kernel, dim3(dgrid), dim3(td), (size_t)(0), st, (const MlpEntry*)table_dev, n_entries, d_silu_t, B, td));
+    if (parts & 1) {
+        dim3 grid(n_entries, ceil_div(max_rows, MLP_ROWS));
+        PIDM_CUDA(launch_pdl(block_mlps_wgrad_kernel, dim3(grid), dim3(256), (size_t)(smem), st, (const MlpEntry*)table_dev, silu_t, B, td));
+    }
+    if (parts & 2) {
+        PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
+        dim3 dgrid(MLP_DG_GROUPS, ceil_div(B, MLP_BCHUNK));
+        PIDM_CUDA(launch_pdl(block_mlps_dgrad_kernel, dim3(dgrid), dim3(td), (size_t)(0), st, (const MlpEntry*)table_dev, n_entries, d_silu_t, B, td));
+    }
     PIDM_LAUNCH_CHECK("block_mlps_bwd");
     return 0;
 }

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "pidm.h"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace pidm {
 
@@ -57,43 +58,76 @@ __device__ __forceinline__ void gn_mean_rstd(const float* sums, int b, int g, in
     rstd = rsqrtf(var + eps);
 }
 
-// y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift )
+// 16-byte vector of activations: 8 bf16 or 4 fp32 channels
+template <typename T> struct Vec { static constexpr int N = 16 / (int)sizeof(T); };
+template <typename T> __device__ __forceinline__ void ldv(const T* p, float* v);
+template <> __device__ __forceinline__ void ldv<float>(const float* p, float* v) { ld4(p, v); }
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16>(const __nv_bfloat16* p, float* v) { ld8(p, v); }
+template <typename T> __device__ __forceinline__ void stv(T* p, const float* v);
+template <> __device__ __forceinline__ void stv<float>(float* p, const float* v) { st4(p, v); }
+template <> __device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, const float* v) { st8(p, v); }
+
+// y = silu( ((x-mean)*rstd*gamma + beta) * (scale+1) + shift ) (+ res)
+// grid (chunks, B).  A thread owns ONE 16-byte channel vector position (o) and walks pixels: its per-channel constants
+// (group mean, rstd*gamma, beta, 1+scale, shift) are loaded once into registers, the pixel loop is 3 FMAs + SiLU per
+// element with GN_APPLY_UNR independent 16-byte loads in flight.  (The first version re-derived mean/rstd and re-read
+// gamma/beta/scale/shift from global memory for every vector: ~30 loads per 8 outputs, 2.2 TB/s at 64x64x32.)
+constexpr int GN_APPLY_UNR = 4;
 template <typename T>
-__global__ void gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ ss /*[B,2C] or null*/,
-                                const T* __restrict__ res /*added after the SiLU, or null*/, T* __restrict__ y, int HW,
-                                int C, int G, float eps, long long total8) {
-    const int oct = C / 8, cpg = C / G;
+__global__ void __launch_bounds__(NORM_THREADS) gn_apply_kernel(
+        const T* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+        const float* __restrict__ beta, const float* __restrict__ ss /*[B,2C] or null*/,
+        const T* __restrict__ res /*added after the SiLU, or null*/, T* __restrict__ y, int HW, int C, int G, float eps) {
+    constexpr int VE = Vec<T>::N;
+    const int ov = C / VE, cpg = C / G;
+    const int b = blockIdx.y;
+    const int o = threadIdx.x % ov, r0 = threadIdx.x / ov;
+    const int rpp = blockDim.x / ov;
     const float inv_n = 1.f / ((float)cpg * (float)HW);
     pdl_trigger();
+    // parameters do not depend on the predecessor kernel: load them before the grid dependency resolves
+    float a[VE], bt[VE], s1p[VE], sh[VE], mean[VE];
+#pragma unroll
+    for (int k = 0; k < VE; ++k) { a[k] = gamma[o * VE + k]; bt[k] = beta[o * VE + k]; }
     pdl_wait();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
-         i += (long long)gridDim.x * blockDim.x) {
-        int o = (int)(i % oct);
-        long long pix = i / oct;
-        int b = (int)(pix / HW);
-        float v[8];
-        ld8(x + i * 8, v);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int c0 = o * 8 + h * 4;
-            float mean, rstd;
-            gn_mean_rstd(sums, b, c0 / cpg, G, inv_n, eps, mean, rstd);
+    for (int k = 0; k < VE; k += 4) {          // cpg is 4 or a multiple of 8: 4 consecutive channels share a group
+        float m, r;
+        gn_mean_rstd(sums, b, (o * VE + k) / cpg, G, inv_n, eps, m, r);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int c = c0 + k;
-                float a = (v[h * 4 + k] - mean) * rstd * gamma[c] + beta[c];
-                if (ss) a = a * (ss[(size_t)b * 2 * C + c] + 1.f) + ss[(size_t)b * 2 * C + C + c];
-                v[h * 4 + k] = silu_f(a);
+        for (int j = 0; j < 4; ++j) { mean[k + j] = m; a[k + j] *= r; }
+    }
+#pragma unroll
+    for (int k = 0; k < VE; ++k) {
+        const int c = o * VE + k;
+        s1p[k] = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        sh[k] = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
+    }
+    const size_t base = (size_t)b * HW * C + (size_t)o * VE;
+    const int stride = gridDim.x * rpp;
+    for (int p0 = blockIdx.x * rpp + r0; p0 < HW; p0 += stride * GN_APPLY_UNR) {
+        float v[GN_APPLY_UNR][VE], rr[GN_APPLY_UNR][VE];
+#pragma unroll
+        for (int u = 0; u < GN_APPLY_UNR; ++u) {
+            const int p = p0 + u * stride;
+            if (p < HW) {
+                ldv<T>(x + base + (size_t)p * C, v[u]);
+                if (res) ldv<T>(res + base + (size_t)p * C, rr[u]);
             }
         }
-        if (res) {
-            float r[8];
-            ld8(res + i * 8, r);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += r[k];
+        for (int u = 0; u < GN_APPLY_UNR; ++u) {
+            const int p = p0 + u * stride;
+            if (p < HW) {
+#pragma unroll
+                for (int k = 0; k < VE; ++k) {
+                    const float z = ((v[u][k] - mean[k]) * a[k] + bt[k]) * s1p[k] + sh[k];
+                    v[u][k] = silu_f(z);
+                    if (res) v[u][k] += rr[u][k];
+                }
+                stv<T>(y + base + (size_t)p * C, v[u]);
+            }
         }
-        st8(y + i * 8, v);
     }
 }
 
@@ -224,96 +258,131 @@ __global__ void gn_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ 
     }
 }
 
-// Single-pass backward for tensors whose per-sample (x, dy) pair fits the shared memory of one thread-block cluster:
-// one cluster of CL CTAs per sample.  Every CTA copies its slice of x and dy into shared memory once (cp.async, all
-// loads in flight together), reduces (dz, dz*xhat) per channel over its rows, the CL partial vectors are combined
-// through distributed shared memory, and dx is computed from the resident slice: x and dy are read from HBM exactly
-// once and no workspace / memset / second launch is needed.  Arithmetic order per element is the same as in the
-// two-kernel path (gn_bwd_reduce_kernel + gn_bwd_dx_kernel).
-template <typename T>
-__global__ void __launch_bounds__(NORM_THREADS) gn_bwd_cluster_kernel(
+// Single-launch backward.  GroupNorm couples only the channels of one group, so the work is cut into (sample, channel
+// slab) pieces -- a slab is one or more whole groups and at least 32 bytes of channels per pixel -- and a piece is owned by
+// a cluster of CL CTAs that split its pixels (CL = 1 at the low-resolution levels: no cluster launch at all).
+//   phase 1: per-channel sums of dz and dz*xhat over the thread's pixels -> warp shuffles -> shared memory
+//            (-> distributed shared memory across the CL CTAs of the cluster)
+//   phase 2: dx = rstd * (gamma*(1+scale)*dz - m1 - xhat*m2), FiLM / affine / bias gradients
+// KEEP = true (<= 2 vectors per thread): xhat and dz stay in REGISTERS between the phases, x and dy are read once.
+// KEEP = false: phase 2 re-reads the thread's own vectors (L1 / L2 hits: the CTA touched them a few microseconds
+// earlier), two vectors at a time -- holding 4 x 8 x 2 fp32 values per thread cost 156 registers = one CTA per SM and
+// 35 us at 64x64x32.
+// Either way the grid has 256..512 CTAs at every level of the U-Net (the first version ran one CTA or one 8-CTA cluster
+// per SAMPLE: 32 CTAs on 148 SMs at the 8x8 level, 14 us for 1 MB; ncu: warps_active 12 %, waves_per_multiprocessor 0.05).
+// Element-wise arithmetic is the same, in the same order, as in gn_bwd_reduce_kernel + gn_bwd_dx_kernel.
+template <typename T, int V, bool KEEP>
+__global__ void __launch_bounds__(NORM_THREADS, 2) gn_bwd_piece_kernel(
         const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums, const float* __restrict__ gamma,
         const float* __restrict__ beta, const float* __restrict__ ss, T* __restrict__ dx, float* __restrict__ dss,
         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int HW, int C, int G, float eps,
-        int rows_per_cta) {
+        int S /*channels per slab*/, int CL /*CTAs per (sample, slab)*/, int rows_per_cta, int nchunks) {
     namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    pdl_trigger();
-    pdl_wait();
-    extern __shared__ __align__(16) unsigned char gsm[];
-    float* part = reinterpret_cast<float*>(gsm);           // [C][2] partial sums of this CTA
-    float* Sf = part + 2 * C;                              // [C][2] sums over the whole sample
-    float* gm = Sf + 2 * C;                                // [G][2]
-    float* cs = gm + 2 * G;                                // [C] column sums of dx
-    T* xs = reinterpret_cast<T*>(cs + C);                  // [rows][C]
-    T* ds = xs + (size_t)rows_per_cta * C;
-    const int oct = C / 8, cpg = C / G;
-    const int b = blockIdx.x / CL;
-    const int o = threadIdx.x % oct, r0 = threadIdx.x / oct;
-    const int rows_per_pass = blockDim.x / oct;
-    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    constexpr int VE = Vec<T>::N;
+    extern __shared__ float rsm[];
+    float* part = rsm;                 // [S][2] partial sums of this CTA
+    float* Sf = part + 2 * S;          // [S][2] sums over the whole (sample, slab)
+    float* gm = Sf + 2 * S;            // [S / cpg][2]
+    float* cs = gm + 2 * (S / (C / G));// [S] column sums of dx
+    const int cpg = C / G, so = S / VE, nslab = C / S;
+    const int piece = blockIdx.x / CL, rank = blockIdx.x - piece * CL;
+    const int b = piece / nslab, slab = piece - b * nslab;
+    const int c0 = slab * S;                                   // first channel of the slab
+    const int o = threadIdx.x % so, r0 = threadIdx.x / so;
+    const int rpp = blockDim.x / so;
     const int row_begin = rank * rows_per_cta;
-    const int rows = min(rows_per_cta, HW - row_begin);
-    const size_t base = ((size_t)b * HW + row_begin) * C;
-    {   // bulk copy of the slice: 16-byte cp.async, everything in flight at once
-        const int vec = 16 / (int)sizeof(T);
-        const int n16 = rows * C / vec;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
-            const uint32_t dxs = (uint32_t)__cvta_generic_to_shared(xs + (size_t)i * vec);
-            const uint32_t dds = (uint32_t)__cvta_generic_to_shared(ds + (size_t)i * vec);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dxs), "l"(x + base + (size_t)i * vec) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dds), "l"(dy + base + (size_t)i * vec) : "memory");
+    const int row_end = min(HW, row_begin + rows_per_cta);
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    pdl_trigger();
+    float gmv[VE], bt[VE];
+#pragma unroll
+    for (int k = 0; k < VE; ++k) { gmv[k] = gamma[c0 + o * VE + k]; bt[k] = beta[c0 + o * VE + k]; }
+    for (int i = threadIdx.x; i < 5 * S + 2 * (S / cpg); i += blockDim.x) rsm[i] = 0.f;
+    pdl_wait();
+    const size_t base = (size_t)b * HW * C + c0 + (size_t)o * VE;
+    float xv[V][VE], dv[V][VE];
+    bool ok[V];
+    // the first chunk's loads are issued before the parameter loads they do not depend on
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        const int p = row_begin + r0 + u * rpp;
+        ok[u] = p < row_end;
+        if (ok[u]) {
+            ldv<T>(x + base + (size_t)p * C, xv[u]);
+            ldv<T>(dy + base + (size_t)p * C, dv[u]);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) part[i] = 0.f;
-    for (int i = threadIdx.x; i < 2 * G + C; i += blockDim.x) gm[i] = 0.f;       // gm and cs are adjacent
-    float mean[2], rstd[2], gmv[8], bt[8], s1p[8], sh[8];
+    float mean[VE], rstd[VE], s1p[VE], sh[VE];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) gn_mean_rstd(sums, b, (o * 8 + h * 4) / cpg, G, inv_n, eps, mean[h], rstd[h]);
+    for (int k = 0; k < VE; k += 4) {
+        float m, r;
+        gn_mean_rstd(sums, b, (c0 + o * VE + k) / cpg, G, inv_n, eps, m, r);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = o * 8 + k;
-        gmv[k] = gamma[c]; bt[k] = beta[c];
+        for (int j = 0; j < 4; ++j) { mean[k + j] = m; rstd[k + j] = r; }
+    }
+#pragma unroll
+    for (int k = 0; k < VE; ++k) {
+        const int c = c0 + o * VE + k;
         s1p[k] = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
         sh[k] = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    float a1[8], a2[8];
+    // ---- phase 1
+    float a1[VE], a2[VE];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
-    for (int p = r0; p < rows; p += rows_per_pass) {
-        float v[8], d[8];
-        ld8(xs + (size_t)p * C + o * 8, v);
-        ld8(ds + (size_t)p * C + o * 8, d);
+    for (int k = 0; k < VE; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+    for (int it = 0; it < nchunks; ++it) {
+        if (it > 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float xh = (v[k] - mean[k >> 2]) * rstd[k >> 2];
-            float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
-            float dz = d[k] * silu_grad_f(z);
-            a1[k] += dz; a2[k] += dz * xh;
+            for (int u = 0; u < V; ++u) {
+                const int p = row_begin + r0 + (it * V + u) * rpp;
+                ok[u] = p < row_end;
+                if (ok[u]) {
+                    ldv<T>(x + base + (size_t)p * C, xv[u]);
+                    ldv<T>(dy + base + (size_t)p * C, dv[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            if (ok[u]) {
+#pragma unroll
+                for (int k = 0; k < VE; ++k) {
+                    const float xh = (xv[u][k] - mean[k]) * rstd[k];
+                    const float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
+                    const float dz = dv[u][k] * silu_grad_f(z);
+                    a1[k] += dz; a2[k] += dz * xh;
+                    if (KEEP) { xv[u][k] = xh; dv[u][k] = dz; }       // keep xhat / dz for phase 2
+                }
+            }
         }
     }
-    const bool pub1 = reduce_same_octet(a1, oct);
-    reduce_same_octet(a2, oct);
+    __syncthreads();                                           // zero-fill of the shared sums is complete
+    const bool pub1 = reduce_same_octet(a1, so);
+    reduce_same_octet(a2, so);
     if (pub1) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { atomicAdd(&part[(o * 8 + k) * 2], a1[k]); atomicAdd(&part[(o * 8 + k) * 2 + 1], a2[k]); }
+        for (int k = 0; k < VE; ++k) { atomicAdd(&part[(o * VE + k) * 2], a1[k]); atomicAdd(&part[(o * VE + k) * 2 + 1], a2[k]); }
     }
-    cluster.sync();                                        // all partial vectors of the sample are complete
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-        float t = 0.f;
-        for (int r = 0; r < CL; ++r) t += cluster.map_shared_rank(part, r)[i];
-        Sf[i] = t;
+    if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();                                        // all partial vectors of the piece are complete
+        for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) {
+            float t = 0.f;
+            for (int r = 0; r < CL; ++r) t += cluster.map_shared_rank(part, r)[i];
+            Sf[i] = t;
+        }
+        cluster.sync();                                        // nobody reads a peer's `part` after this point
+    } else {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) Sf[i] = part[i];
+        __syncthreads();
     }
-    cluster.sync();                                        // nobody reads a peer's `part` after this point
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float s1 = Sf[c * 2], s2 = Sf[c * 2 + 1];
+    for (int cl = threadIdx.x; cl < S; cl += blockDim.x) {
+        const int c = c0 + cl;
+        const float s1 = Sf[cl * 2], s2 = Sf[cl * 2 + 1];
         const float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
-        atomicAdd(&gm[(c / cpg) * 2], gamma[c] * f * s1);
-        atomicAdd(&gm[(c / cpg) * 2 + 1], gamma[c] * f * s2);
+        atomicAdd(&gm[(cl / cpg) * 2], gamma[c] * f * s1);
+        atomicAdd(&gm[(cl / cpg) * 2 + 1], gamma[c] * f * s2);
         if (rank == 0) {
             if (dss) {
                 dss[(size_t)b * 2 * C + c] = gamma[c] * s2 + beta[c] * s1;   // d scale
@@ -324,36 +393,56 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_bwd_cluster_kernel(
         }
     }
     __syncthreads();
-    float m1[2], m2[2];
+    // ---- phase 2
+    float m1[VE], m2[VE];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int g = (o * 8 + h * 4) / cpg;
-        m1[h] = gm[g * 2] * inv_n;
-        m2[h] = gm[g * 2 + 1] * inv_n;
+    for (int k = 0; k < VE; k += 4) {
+        const int gl = (o * VE + k) / cpg;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m1[k + j] = gm[gl * 2] * inv_n; m2[k + j] = gm[gl * 2 + 1] * inv_n; }
     }
-    float colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = r0; p < rows; p += rows_per_pass) {
-        float v[8], d[8];
-        ld8(xs + (size_t)p * C + o * 8, v);
-        ld8(ds + (size_t)p * C + o * 8, d);
+    float colsum[VE];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float xh = (v[k] - mean[k >> 2]) * rstd[k >> 2];
-            float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
-            float dz = d[k] * silu_grad_f(z);
-            float g = rstd[k >> 2] * (gmv[k] * s1p[k] * dz - m1[k >> 2] - xh * m2[k >> 2]);
-            v[k] = g;
-            colsum[k] += g;
+    for (int k = 0; k < VE; ++k) colsum[k] = 0.f;
+    for (int it = 0; it < nchunks; ++it) {
+        if (!KEEP) {
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const int p = row_begin + r0 + (it * V + u) * rpp;
+                ok[u] = p < row_end;
+                if (ok[u]) {
+                    ldv<T>(x + base + (size_t)p * C, xv[u]);
+                    ldv<T>(dy + base + (size_t)p * C, dv[u]);
+                }
+            }
         }
-        st8(dx + base + (size_t)p * C + o * 8, v);
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            if (ok[u]) {
+                float g[VE];
+#pragma unroll
+                for (int k = 0; k < VE; ++k) {
+                    float xh, dz;
+                    if (KEEP) { xh = xv[u][k]; dz = dv[u][k]; }
+                    else {
+                        xh = (xv[u][k] - mean[k]) * rstd[k];
+                        const float z = (xh * gmv[k] + bt[k]) * s1p[k] + sh[k];
+                        dz = dv[u][k] * silu_grad_f(z);
+                    }
+                    g[k] = rstd[k] * (gmv[k] * s1p[k] * dz - m1[k] - xh * m2[k]);
+                    colsum[k] += g[k];
+                }
+                stv<T>(dx + base + (size_t)(row_begin + r0 + (it * V + u) * rpp) * C, g);
+            }
+        }
     }
     if (dbias) {
-        if (reduce_same_octet(colsum, oct)) {
+        if (reduce_same_octet(colsum, so)) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(&cs[o * 8 + k], colsum[k]);
+            for (int k = 0; k < VE; ++k) atomicAdd(&cs[o * VE + k], colsum[k]);
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], cs[i]);
+        for (int i = threadIdx.x; i < S; i += blockDim.x) atomicAdd(&dbias[c0 + i], cs[i]);
     }
 }
 
@@ -596,15 +685,19 @@ extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const 
     cudaStream_t st = (cudaStream_t)stream;
     int block, chunks;
     gn_launch_dims(HW, C, block, chunks);
-    long long total8 = (long long)B * HW * C / 8;
-    int g2 = ceil_div(total8, 256);
-    if (g2 > 148 * 16) g2 = 148 * 16;
     if (!stats_precomputed) PIDM_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * G * 2 * sizeof(float), st));
     PIDM_DISPATCH_DTYPE(dtype, {
         if (!stats_precomputed)
             gn_stats_kernel<T><<<dim3(chunks, B), block, 2 * G * sizeof(float), st>>>((const T*)x, sums, HW, C, G);
-        PIDM_CUDA(launch_pdl(gn_apply_kernel<T>, dim3(g2), dim3(256), 0, st, (const T*)x, (const float*)sums, gamma, beta,
-                             scale_shift, (const T*)residual, (T*)y, HW, C, G, eps, total8));
+        // apply: a thread owns one 16-byte channel vector position; ~GN_APPLY_UNR vectors per thread, >= 2 waves of CTAs
+        const int ov = C / Vec<T>::N;
+        PIDM_REQUIRE(ov <= NORM_THREADS && NORM_THREADS % ov == 0, "groupnorm: C=%d is not supported by the apply kernel", C);
+        const int rpp = NORM_THREADS / ov;
+        int ach = ceil_div(HW, rpp * GN_APPLY_UNR);
+        for (int u = GN_APPLY_UNR; u > 1 && (long long)B * ach < 148 * 2; u /= 2) ach = ceil_div(HW, rpp * (u / 2));
+        while (ach > 1 && (long long)B * ach > 148 * 8) ach = (ach + 1) / 2;
+        PIDM_CUDA(launch_pdl(gn_apply_kernel<T>, dim3(ach, B), dim3(NORM_THREADS), 0, st, (const T*)x, (const float*)sums,
+                             gamma, beta, scale_shift, (const T*)residual, (T*)y, HW, C, G, eps));
     });
     PIDM_LAUNCH_CHECK("groupnorm_silu_fwd");
     return 0;
@@ -620,43 +713,68 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
     cudaStream_t st = (cudaStream_t)stream;
     int block, chunks;
     gn_launch_dims(HW, C, block, chunks);
-    {   // single-pass cluster kernel when a sample's (x, dy) fits the shared memory of <= 8 CTAs
-        const size_t esz = dtype == PIDM_BF16 ? 2 : 4;
-        const size_t fixed = (size_t)(4 * C + 2 * G + C) * sizeof(float);
-        const int rows_gran = block / (C / 8);
-        int cl = 0, rows_per_cta = 0;
-        for (int c = 1; c <= 8; c *= 2) {
-            int r = (HW + c - 1) / c;
-            r = (r + rows_gran - 1) / rows_gran * rows_gran;
-            if ((size_t)r * C * esz * 2 + fixed <= 100 * 1024 && (size_t)r * (c - 1) < (size_t)HW) { cl = c; rows_per_cta = r; break; }
-            if (c == 1 && (size_t)r * C * esz * 2 + fixed <= 100 * 1024) { cl = 1; rows_per_cta = r; break; }
-        }
-        if (cl > 0 && (long long)B * cl >= 32 && (C * esz) % 16 == 0) {
-            const size_t smem = (size_t)rows_per_cta * C * esz * 2 + fixed;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(B * cl));
-            cfg.blockDim = dim3((unsigned)block);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[2];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[1].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr; cfg.numAttrs = pdl_enabled(0) ? 2 : 1;
-            static bool attr_done[2] = {false, false};
-            PIDM_DISPATCH_DTYPE(dtype, {
-                const int di = dtype == PIDM_BF16 ? 1 : 0;
-                if (!attr_done[di]) {
-                    PIDM_CUDA(cudaFuncSetAttribute(gn_bwd_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    attr_done[di] = true;
+    {   // single-launch piece kernel (see gn_bwd_piece_kernel): plan (slab, cluster size, vectors per thread)
+        const int esz = dtype == PIDM_BF16 ? 2 : 4, ve = 16 / esz, cpg = C / G;
+        int S = cpg;
+        while (S * esz < 32 && S * 2 <= C && C % (S * 2) == 0) S *= 2;    // >= 32 bytes of channels per pixel row
+        const int so = S / ve;
+        const bool shape_ok = S % ve == 0 && so >= 1 && so <= 32 && (so & (so - 1)) == 0 && C % S == 0 && (C * esz) % 16 == 0;
+        if (shape_ok) {
+            const int nslab = C / S;
+            const long long nv = (long long)HW * so;            // 16-byte vectors per (sample, slab)
+            int threads = NORM_THREADS;
+            while (threads > 32 && threads / 2 >= nv && (threads / 2) % so == 0) threads /= 2;
+            // CTAs per piece.  Measured (B200, B = 32): a CTA of this kernel is a ~4 us latency chain whatever its size, a
+            // second wave of CTAs doubles the launch and a cluster costs ~1 us extra -- so: no cluster unless a piece
+            // has more than 8 vectors per thread, never more CTAs than are resident at once (2 per SM), and otherwise
+            // as many CTAs as that allows.
+            const int resident = 148 * 2;
+            int cl = 1;
+            while (cl < 8 && nv > (long long)cl * threads * 8) cl *= 2;
+            while (cl < 8 && (long long)B * nslab * cl * 2 <= resident && nv > (long long)cl * threads) cl *= 2;
+            {   // tuning aid: PIDM_GN_CL pins the number of CTAs per piece
+                static int force_cl = -1;
+                if (force_cl < 0) { const char* ev = getenv("PIDM_GN_CL"); force_cl = ev ? atoi(ev) : 0; }
+                if (force_cl > 0) cl = force_cl;
+            }
+            const int rpp = threads / so;
+            int rows_per_cta = ceil_div(HW, cl);
+            rows_per_cta = ceil_div(rows_per_cta, rpp) * rpp;
+            const int v = rows_per_cta / rpp;                   // vectors per thread
+            if ((long long)rows_per_cta * (cl - 1) < HW) {
+                const int vt = v <= 1 ? 1 : 2;                  // vectors per chunk
+                const bool keep = v <= 2;                       // register-resident between the phases
+                const int nchunks = ceil_div(v, vt);
+                const size_t smem = (size_t)(5 * S + 2 * (S / cpg)) * sizeof(float);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(B * nslab * cl));
+                cfg.blockDim = dim3((unsigned)threads);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[2];
+                int na = 0;
+                if (pdl_enabled(0)) {
+                    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[na].val.programmaticStreamSerializationAllowed = 1;
+                    ++na;
                 }
-                PIDM_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel<T>, (const T*)x, (const T*)dy, sums, gamma, beta,
-                                             scale_shift, (T*)dx, d_scale_shift, dgamma, dbeta, dbias_of_producer, HW, C, G,
-                                             eps, rows_per_cta));
-            });
-            PIDM_LAUNCH_CHECK("groupnorm_silu_bwd(cluster)");
-            return 0;
+                if (cl > 1) {
+                    attr[na].id = cudaLaunchAttributeClusterDimension;
+                    attr[na].val.clusterDim.x = (unsigned)cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+                    ++na;
+                }
+                cfg.attrs = attr; cfg.numAttrs = na;
+#define GN_PIECE_CASE(VV, KK)                                                                                            \
+    if (vt == VV && keep == KK) {                                                                                                   \
+        PIDM_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_piece_kernel<T, VV, KK>, (const T*)x, (const T*)dy, sums, gamma, beta, \
+                                     scale_shift, (T*)dx, d_scale_shift, dgamma, dbeta, dbias_of_producer, HW, C, G, eps, \
+                                     S, cl, rows_per_cta, nchunks));                                                     \
+    }
+                PIDM_DISPATCH_DTYPE(dtype, { GN_PIECE_CASE(1, true) else GN_PIECE_CASE(2, true) else GN_PIECE_CASE(2, false) });
+#undef GN_PIECE_CASE
+                PIDM_LAUNCH_CHECK("groupnorm_silu_bwd(piece)");
+                return 0;
+            }
         }
     }
     float* S = workspace;

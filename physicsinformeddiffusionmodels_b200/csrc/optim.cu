@@ -80,7 +80,30 @@ __global__ void adam_ema_kernel(float* __restrict__ p, float* __restrict__ g, fl
     }
     const float step = s_step, rs = s_rs;
     const bool ema_on = s_ema != 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // 128-bit accesses: the pass moves 40 bytes per parameter (5 buffers read, 5 written), nothing else matters
+    const long long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* e4 = reinterpret_cast<float4*>(ema);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 gv = g4[i], mv = m4[i], vv = v4[i], pv = p4[i], ev;
+        if (ema_on) ev = e4[i];
+        float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x; float* pp = &pv.x; float* ep = &ev.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gi = gp[k] * coef;
+            mp[k] = b1 * mp[k] + (1.f - b1) * gi;
+            vp[k] = b2 * vp[k] + (1.f - b2) * gi * gi;
+            pp[k] = pp[k] - step * mp[k] / (sqrtf(vp[k]) * rs + eps);
+            if (ema_on) ep[k] = ema_mu * ep[k] + (1.f - ema_mu) * pp[k];
+        }
+        m4[i] = mv; v4[i] = vv; p4[i] = pv;
+        if (ema_on) e4[i] = ev;
+        if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i] * coef;
         float mi = b1 * m[i] + (1.f - b1) * gi;
         float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -119,9 +142,12 @@ extern "C" int pidm_adam_ema_step(float* param, float* grad, float* exp_avg, flo
                                   int* step_counter_dev, const float* grad_norm_sq_dev, float grad_scale, float max_norm, float ema_mu,
                                   int ema_first_step, int zero_grad, void* stream) {
     PIDM_REQUIRE(step >= 1 || step_counter_dev, "adam: step is 1-based");
+    PIDM_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq |
+                   (uintptr_t)(ema_first_step > 0 ? ema_shadow : param)) & 15) == 0, "adam: buffers must be 16-byte aligned");
     if (step_counter_dev) PIDM_CUDA(launch_pdl(incr_kernel, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)stream, step_counter_dev));   // counter holds steps done so far
-    int grid = (int)((n + 255) / 256);
+    int grid = (int)((n / 4 + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
     PIDM_CUDA(launch_pdl(adam_ema_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, ema_shadow, n, lr, beta1,
                                                            beta2, eps, step, step_counter_dev, grad_norm_sq_dev, grad_scale,
                                                            max_norm, ema_mu, ema_first_step, zero_grad));

@@ -255,6 +255,8 @@ _SIDE = {'stream': None, 'keep': [], 'active': False}
 
 
 def side_stream_begin():
+    if os.environ.get('PIDM_NO_SIDE_STREAM') == '1':      # debugging aid: everything on one stream
+        return
     if _SIDE['stream'] is None:
         _SIDE['stream'] = torch.cuda.Stream()
     _SIDE['active'] = True
@@ -533,8 +535,14 @@ class _TimeEmbed(torch.autograd.Function):
         gb1, rb1 = _grad_buffer(b1)
         gW2, rW2 = _grad_buffer(W2)
         gb2, rb2 = _grad_buffer(b2)
-        call('pidm_time_embed_bwd', d_silu.contiguous(), emb, h1, temb, W2, gW1, gb1, gW2, gb2, B, emb.shape[1], td,
-             stream())
+        d_silu = d_silu.contiguous()
+        ws = torch.empty(2 * B * td, device=h1.device, dtype=torch.float32)
+        args = (d_silu, emb, h1, temb, W2, gW1, gb1, gW2, gb2, ws, B, emb.shape[1], td)
+        call('pidm_time_embed_bwd', *args, 2, stream())                      # activation gradients (critical path)
+        # weight gradients feed the optimizer only.  EVERY tensor the side-stream kernel reads must be kept alive until
+        # the join: autograd releases this node's saved tensors (emb, h1) as soon as backward returns, and the caching
+        # allocator would hand their memory to the next main-stream allocation while the kernel is still reading it
+        call('pidm_time_embed_bwd', *args, 1, _wgrad_stream(ws, emb, h1))
         return None, rW1, rb1, rW2, rb2
 
 
@@ -567,8 +575,12 @@ class _BlockMlps(torch.autograd.Function):
             rets.append(r_)
         d_outs = [d.contiguous() for d in d_outs]
         d_silu = torch.empty_like(silu_t)
-        call('pidm_block_mlps_bwd', table.device_table(None, d_outs, bufs), table.n, table.max_rows, silu_t, d_silu, B, td,
-             stream())
+        tab = table.device_table(None, d_outs, bufs)
+        # (side stream: keep silu_t -- a saved tensor, released when this backward returns -- the incoming gradients
+        #  and the device table alive until the join, see _TimeEmbed.backward)
+        call('pidm_block_mlps_bwd', tab, table.n, table.max_rows, silu_t, d_silu, B, td, 1,
+             _wgrad_stream(silu_t, tab, *d_outs))
+        call('pidm_block_mlps_bwd', tab, table.n, table.max_rows, silu_t, d_silu, B, td, 2, stream())
         return (d_silu, None, *rets)
 
 

@@ -207,6 +207,45 @@ def test_groupnorm_silu(pk, C, H, with_ss, dtype, tol):
         assert rel(sd.grad, sr.grad) < 2 * tol
 
 
+@pytest.mark.parametrize('C,H,dtype,tol', [(32, 64, torch.bfloat16, 2e-2), (64, 32, torch.bfloat16, 2e-2),
+                                           (128, 16, torch.bfloat16, 2e-2), (256, 8, torch.bfloat16, 2e-2),
+                                           (32, 32, torch.bfloat16, 2e-2), (64, 16, torch.bfloat16, 2e-2),
+                                           (128, 8, torch.bfloat16, 2e-2), (32, 64, torch.float32, 2e-5),
+                                           (256, 8, torch.float32, 2e-5), (128, 64, torch.bfloat16, 2e-2),
+                                           (1024, 8, torch.bfloat16, 2e-2)])
+def test_groupnorm_silu_at_benchmarked_shapes(pk, C, H, dtype, tol):
+    """Every GroupNorm geometry of the B=32 training step (and two of the dim=128 mechanics model): the backward
+    planner picks (channel slab, cluster size 1..8, vectors per thread) from the shape, so each level of the U-Net runs
+    a different instantiation.  Also checks the producer-bias gradient that rides on the backward (column sums of dx)."""
+    ops, _ = pk
+    g = torch.Generator().manual_seed(40 + C + H)
+    B, G = (32 if C * H * H <= 32 * 64 * 64 * 2 else 4), 8
+    x = torch.randn(B, C, H, H, generator=g) * 1.5 + 0.3
+    cot = torch.randn(B, C, H, H, generator=g)
+    if dtype == torch.bfloat16:
+        x, cot = x.bfloat16().float(), cot.bfloat16().float()
+    gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ss = 0.3 * torch.randn(B, 2 * C, generator=g)
+    xr, gr, br, sr = (t.clone().requires_grad_(True) for t in (x, gamma, beta, ss))
+    h = F.group_norm(xr, G, gr, br, eps=1e-5) * (sr[:, :C, None, None] + 1) + sr[:, C:, None, None]
+    yr = F.silu(h)
+    (yr * cot).sum().backward()
+    xd = nhwc(x, dtype).to(DEV).requires_grad_(True)
+    gd, bd = torch.nn.Parameter(gamma.to(DEV)), torch.nn.Parameter(beta.to(DEV))
+    sd = ss.to(DEV).requires_grad_(True)
+    link = {'groups': G, 'sums': None, 'bias': torch.nn.Parameter(torch.zeros(C, device=DEV))}
+    y = ops.groupnorm_silu(xd, gd, bd, sd, G, gn_link=link)
+    assert rel(nchw(y), yr) < tol
+    y.backward(nhwc(cot, dtype).to(DEV))
+    assert rel(nchw(xd.grad), xr.grad) < 2 * tol
+    assert rel(gd.grad, gr.grad) < 2 * tol and rel(bd.grad, br.grad) < 2 * tol
+    assert rel(sd.grad, sr.grad) < 2 * tol
+    # column sums of a mean-free-per-group quantity: compare on the scale of |dx| summed, not of the (tiny) result
+    dbias_ref = xr.grad.sum(dim=(0, 2, 3))
+    scale = xr.grad.abs().sum(dim=(0, 2, 3)).max()
+    assert ((link['dbias'].cpu() - dbias_ref).abs().max() / scale).item() < (2e-3 if dtype == torch.bfloat16 else 1e-5)
+
+
 @pytest.mark.parametrize('dtype,tol', DTYPES)
 @pytest.mark.parametrize('C', [32, 64, 256, 512])
 def test_layernorm_c(pk, C, dtype, tol):
@@ -244,7 +283,7 @@ def _linattn_ref(qkv, heads):      # qkv [B, 3*hid, H, W]
 
 
 @pytest.mark.parametrize('dtype,tol', DTYPES)
-@pytest.mark.parametrize('H', [8, 16, 64])
+@pytest.mark.parametrize('H', [8, 16, 32, 64])      # 8, 16: one-CTA-per-head kernel (bf16); 32, 64: streaming kernels
 def test_linear_attention(pk, H, dtype, tol):
     ops, _ = pk
     g = torch.Generator().manual_seed(6)

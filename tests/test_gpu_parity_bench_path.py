@@ -140,22 +140,29 @@ def test_device_step_counter_bias_correction(env):
     g = torch.Generator().manual_seed(15)
     n = 65536 + 3
     for step in (1, 2, 1000):
-        p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 0.01
-        m, v = torch.randn(n, generator=g) * 0.01, torch.rand(n, generator=g) * 1e-4
-        ema = p + 0.01 * torch.randn(n, generator=g)
-        pr, mr, vr, er = p.clone(), m.clone(), v.clone(), ema.clone()
-        O.adam_ema_step([pr], [gr], [mr], [vr], [er], step)
-        pd, gd, md, vd, ed = (a.to(DEV) for a in (p, gr, m, v, ema))
-        counter = torch.full((1,), step - 1, device=DEV, dtype=torch.int32)     # steps done so far
-        nsq = torch.zeros(1, device=DEV)
-        call('pidm_sumsq', gd, n, nsq, stream())
-        call('pidm_adam_ema_step', pd, gd, md, vd, ed, n, 1e-4, 0.9, 0.999, 1e-8, 0, counter, nsq, 1.0, 1.0, 0.99, 1, 0,
-             stream())
-        assert int(counter.item()) == step
-        # compare the UPDATE (p is O(1), the update O(1e-4)): 1e-6 relative on the update itself
-        assert rel(pd.cpu() - p, pr - p) < 2e-6, (step, rel(pd.cpu() - p, pr - p))
-        assert rel(ed.cpu() - ema, er - ema) < 2e-5, step
-        assert torch.allclose(md.cpu(), mr, rtol=1e-5, atol=1e-9) and torch.allclose(vd.cpu(), vr, rtol=1e-5, atol=1e-12)
+        for zero_p in (True, False):
+            # zero_p: parameters start at 0, so the new parameter IS the (negated) update and can be compared to 1e-6
+            # relative; with p = O(1) the update (1e-4) sits 3 decimal digits below one ulp of p, so that case is held
+            # to "within one ulp of the fp32 parameter" instead
+            p = torch.zeros(n) if zero_p else torch.randn(n, generator=g)
+            gr = torch.randn(n, generator=g) * 0.01
+            m, v = torch.randn(n, generator=g) * 0.01, torch.rand(n, generator=g) * 1e-4
+            ema = p + 0.01 * torch.randn(n, generator=g)
+            pr, mr, vr, er = p.clone(), m.clone(), v.clone(), ema.clone()
+            O.adam_ema_step([pr], [gr], [mr], [vr], [er], step)
+            pd, gd, md, vd, ed = (a.to(DEV) for a in (p, gr, m, v, ema))
+            counter = torch.full((1,), step - 1, device=DEV, dtype=torch.int32)     # steps done so far
+            nsq = torch.zeros(1, device=DEV)
+            call('pidm_sumsq', gd, n, nsq, stream())
+            call('pidm_adam_ema_step', pd, gd, md, vd, ed, n, 1e-4, 0.9, 0.999, 1e-8, 0, counter, nsq, 1.0, 1.0, 0.99, 1,
+                 0, stream())
+            assert int(counter.item()) == step
+            if zero_p:
+                assert rel(pd.cpu(), pr) < 2e-6, (step, rel(pd.cpu(), pr))
+            else:
+                assert ((pd.cpu() - pr).abs() <= 1.2e-7 * pr.abs().clamp_min(1.0)).all(), step
+            assert torch.allclose(ed.cpu(), er, rtol=1e-6, atol=2e-7), step
+            assert torch.allclose(md.cpu(), mr, rtol=1e-5, atol=1e-9) and torch.allclose(vd.cpu(), vr, rtol=1e-5, atol=1e-12)
 
 
 def test_ema_start_is_honoured_on_the_device(env):
