@@ -285,6 +285,77 @@ def sampling_bench(model, res, dev, n_steps=250, batch=16):
             'final_abs_residual_mean': float(r.abs().mean().item()), 'finite': bool(torch.isfinite(x).all().item())}
 
 
+def mechanics_bench(dev, pk, batch=32, steps=10, warmup=4):
+    """BASELINE.json configs[2]: topology-optimisation (mechanics) 64x64, PIDM loss, batch 32, one B200 -- the model the
+    reference trains for this study, Unet3D(dim=128, channels=10, out_dim=3, sigmoid_last_channel=True) (main.py:102-109,
+    126), through TrainEngine (CUDA graph), device-timed; plus the matrix-free residual kernel against the HBM roofline
+    on a working set larger than L2."""
+    from physicsinformeddiffusionmodels_b200 import ops
+    from physicsinformeddiffusionmodels_b200._lib import call, stream
+    from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
+    from physicsinformeddiffusionmodels_b200.engine import TrainEngine
+    from physicsinformeddiffusionmodels_b200.residuals_mechanics_K import ResidualsMechanics
+    from physicsinformeddiffusionmodels_b200.unet_model import Unet3D
+    torch.manual_seed(0)
+    model = Unet3D(dim=128, channels=10, out_dim=3, sigmoid_last_channel=True).to(dev)
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    diff = DenoisingDiffusion(100, dev)
+    res = ResidualsMechanics(model=model, pixels_per_dim=64, pixels_at_boundary=True, no_BC_folder='', device=dev)
+    eng = TrainEngine(model, diff, res, lr=1e-4, max_norm=1.0, ema_mu=0.99, c_data=1.0, c_residual=1e-2, c_ineq=0.,
+                      lambda_opt=1e-3, use_graph=True)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    cond = torch.rand(batch, 3, 65, 65, generator=g)
+    cond[:, 0] = (0.3 + 0.4 * torch.rand(batch, generator=g))[:, None, None]
+    x0 = torch.cat((0.2 * torch.randn(batch, 2, 65, 65, generator=g), torch.rand(batch, 1, 65, 65, generator=g).clamp(1e-3, 1.)), 1)
+    bcs = torch.zeros(batch, 4, 65, 65)
+    bcs[:, 0, :, 0] = 1.; bcs[:, 1, :, 0] = 1.; bcs[:, 3, 32, 64] = -1.
+    inp = torch.cat((cond, x0, bcs), dim=1).to(dev)
+    for _ in range(warmup):
+        out = eng.step(inp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = eng.step(inp)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gf_sample = 47.3 * 3                       # SURVEY 8d: 47.3 GFLOP/sample forward, x3 for fwd + bwd
+    r = {'workload': f'mechanics (topology optimisation) 64x64 PIDM train step, Unet3D(dim=128, ch=10, out=3), batch {batch}, '
+                     'bf16 activations, CUDA graph, c_residual=1e-2, lambda_opt=1e-3 (configs[2])',
+         'trainable_parameters': n_params, 'ms_per_step': ms, 'samples_per_s': batch / (ms * 1e-3),
+         'model_tflops_at_value': gf_sample * batch / (ms * 1e-3) / 1e3, 'last_loss': float(out[0].item()),
+         'finite': bool(torch.isfinite(out[0]).item())}
+    del eng, model
+    torch.cuda.empty_cache()
+    # ---- residual kernel alone, B = 8192 (1.24 GB working set >> 126 MB L2)
+    Bs = 8192
+    u = torch.randn(Bs, 2, 65, 65, device=dev) * 0.1
+    rho = torch.rand(Bs, 64, 64, device=dev)
+    bc = torch.zeros(Bs, 4, 65, 65, device=dev)
+    bc[:, 0, :, 0] = 1.; bc[:, 1, :, 0] = 1.; bc[:, 3, 32, 64] = -1.
+    rr = torch.empty(Bs, 8450, device=dev)
+    cc = torch.empty(Bs, device=dev)
+    fn = lambda: call('pidm_mechanics_residual_fwd', u, rho, bc, res.KE, rr, cc, Bs, 64, stream())
+    for _ in range(3):
+        fn()
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_k = e0.elapsed_time(e1) / 10
+    alg = Bs * (2 * 4225 + 4096 + 4 * 4225 + 8450) * 4          # read u, rho, bcs; write residual (SURVEY 8d: ~152 KB/sample)
+    gbs = alg / ms_k / 1e6
+    r['roofline_mechanics'] = {'bound': 'hbm', 'kernel': 'mech_node_kernel<0> (pidm_mechanics_residual_fwd), B=8192 standalone sweep',
+                               'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
+                               'traffic': None, 'ms_per_launch': ms_k, 'algorithmic_bytes': alg,
+                               'reference_path_bytes_per_sample': 285.6e6 * 4,
+                               'note': 'matrix-free K(rho)u - f; the reference assembles a dense 8450 x 8450 stiffness matrix '
+                                       '(285.6 MB per sample, written >= 4 times)'}
+    return r
+
+
 def residual_kernel_sweep(pk):
     """Standalone HBM sweep of the Darcy residual kernel at B = 32768 (2.7 GB working set >> 126 MB L2)."""
     from physicsinformeddiffusionmodels_b200 import ops
@@ -337,6 +408,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sampling', action='store_true')
+    ap.add_argument('--no-mechanics', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -469,6 +541,12 @@ def main():
         if not args.no_sampling:
             log('sampling loop (configs[3]): 250 ancestral steps, batch 16')
             extra['sampling'] = sampling_bench(model, res, dev)
+        if not args.no_mechanics:
+            log('mechanics workload (configs[2]): Unet3D(dim=128), batch 32')
+            try:
+                extra['mechanics'] = mechanics_bench(dev, pk)
+            except Exception as ex:                      # a secondary workload must not take the headline line down
+                extra['mechanics'] = {'error': repr(ex)[:400]}
         if not args.no_torch_cuda_baseline:
             log('torch_cuda_baseline: the reference on this GPU through stock PyTorch-CUDA (subprocess)')
             extra['torch_cuda_baseline'] = spawn_leg('torch_cuda', 240)

@@ -198,6 +198,15 @@ int pidm_mechanics_residual_fwd(const float* u, const float* rho, const float* b
 int pidm_mechanics_residual_bwd(const float* u, const float* rho, const float* bcs, const float* KE,
                                 const float* grad_residual, const float* grad_compliance, float* grad_u, float* grad_rho,
                                 float* workspace /* float[B*2*(nel+1)^2] */, int B, int nel, void* stream);
+/* Fused PIDM loss of the mechanics branch + its gradients (src/denoising_utils.py:669-710), one launch:
+ * u [B,2,n] displacements on the (nel+1)^2 node grid, rho [B,nel,nel], x0 [B,3,n] = (disp_x, disp_y, E) data target,
+ * residual [B,2n], compliance [B], vf [B].  sums6 (zeroed here) = data, residual, inequality, optimisation loss terms,
+ * mean|r|, mean_b(mean(rho_b) - vf_b).  grad_u / grad_rho / grad_residual / grad_compliance are overwritten. */
+int pidm_mech_pidm_loss(const float* u, const float* rho, const float* x0, const float* residual, const float* compliance,
+                        const float* vf, const long long* t, const float* p2_loss_weight,
+                        const float* posterior_var_clipped, float c_data, float c_residual, float c_ineq,
+                        float lambda_opt, float* sums6, float* grad_u, float* grad_rho, float* grad_residual,
+                        float* grad_compliance, int B, int nel, void* stream);
 /* bilinear resize, align_corners=False, antialias=False (resize_image, src/residuals_mechanics_K.py:10-21) */
 int pidm_bilinear_resize_fwd(const float* x, float* y, int planes, int in, int out, void* stream);
 int pidm_bilinear_resize_bwd(const float* dy, float* dx, int planes, int in, int out, void* stream);

@@ -227,6 +227,41 @@ def main():
                                            compliance=out['optimizer'].detach(), inequality=out['inequality'].detach(),
                                            KE=KE_ref, cotangent=wr, grad_x0_pred=xmg.grad.clone()))
 
+        # ---- mechanics training loss through the reference's model_estimation_loss (A3 + A13, configs[2] glue) ------
+        # B = 2 with all four terms switched on (c_ineq > 0 pins the [B,1] x [B] broadcast of :679,:694)
+        cfg_m = O.unet_config(dim=32, channels=10, out_dim=3, sigmoid_last_channel=True)
+        sd_m = O.make_test_state_dict(cfg_m, seed=3)
+        model_m = Unet3D(dim=32, channels=10, out_dim=3, sigmoid_last_channel=True)
+        model_m.load_state_dict(sd_m, strict=True)
+        model_m.train()
+        mres_t = ResidualsMechanics(model=model_m, pixels_per_dim=64, pixels_at_boundary=True, no_BC_folder=td + '/',
+                                    device='cpu', topopt_eval=False)
+        gt = torch.Generator().manual_seed(77)
+        B = 2
+        cond = torch.rand(B, 3, 65, 65, generator=gt)
+        cond[:, 0] = torch.tensor([0.4, 0.55])[:, None, None]
+        x0m = torch.cat((0.2 * torch.randn(B, 2, 65, 65, generator=gt), torch.rand(B, 1, 65, 65, generator=gt)), dim=1)
+        bcm = torch.zeros(B, 4, 65, 65)
+        bcm[:, 0, :, 0] = 1.
+        bcm[:, 1, :, 0] = 1.
+        bcm[:, 3, 32, 64] = -1.
+        inp = torch.cat((cond, x0m, bcm), dim=1)
+        coefs = dict(c_data=1.0, c_residual=1e-2, c_ineq=0.5, lambda_opt=1e-3)
+        torch.manual_seed(99)
+        loss_m, data_m, res_m, ineq_m, opt_m = diff.model_estimation_loss(inp, residual_func=mres_t, **coefs)
+        model_m.zero_grad()
+        loss_m.backward()
+        torch.manual_seed(99)
+        t_m = torch.randint(0, 100, size=(B,))
+        e_m = torch.randn_like(x0m)
+        named_m = dict(model_m.named_parameters())
+        save('mechanics_loss.pt', dict(input=inp, t=t_m, noise=e_m, loss=loss_m.detach(), data_loss=torch.tensor(data_m),
+                                       residual_abs=torch.tensor(res_m), inequality=torch.tensor(ineq_m),
+                                       compliance=torch.tensor(opt_m), coefs=torch.tensor(list(coefs.values())),
+                                       grad_final_w=named_m['final_conv.1.weight'].grad.clone(),
+                                       grad_init_w=named_m['init_conv.weight'].grad.clone(),
+                                       grad_mid_w=named_m['downs.1.0.block1.proj.weight'].grad.clone()))
+
 
 if __name__ == '__main__':
     main()

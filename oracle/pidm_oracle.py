@@ -530,6 +530,31 @@ def mechanics_residual(x0_pred, bcs, vf, KE=None):
     return residual, compliance, ineq
 
 
+def mechanics_training_loss(sd, cfg, inp, t, noise, tables, c_data=1.0, c_residual=1e-2, c_ineq=0.0, lambda_opt=0.0):
+    """model_estimation_loss for gov_eqs='mechanics', mean-mode x0, with t and eps supplied (denoising_utils.py:616-710,
+    residuals_mechanics_K.py:166-274).  inp [B,10,65,65] = (vf, strain energy, von Mises | disp_x, disp_y, E | bc_x,
+    bc_y, load_x, load_y).  Returns (loss, dict of the tracked scalars and intermediates)."""
+    B = inp.shape[0]
+    cond, x0, bcs = torch.tensor_split(inp, (3, 6), dim=1)
+    xt = q_sample(x0, t, noise, tables)
+    net_in = torch.cat((bilinear_resize(torch.cat((xt, cond), dim=1), 64), bilinear_resize(bcs, 64)), dim=1)
+    y = unet_forward(sd, cfg, net_in, t)
+    vf = cond[:, 0, 0, 0]
+    r, comp, ineq = mechanics_residual(y, bcs, vf)
+    out = torch.cat((bilinear_resize(y[:, :2], 65), F.pad(y[:, 2], (0, 1, 0, 1)).unsqueeze(1)), dim=1)
+    mse = ((x0 - out) ** 2).reshape(B, -1).mean(dim=1)
+    data = c_data * (mse * tables['p2_loss_weight'].to(mse.dtype)[t]).mean()
+    var = tables['posterior_variance_clipped'].to(mse.dtype)[t]
+    loss = data + (c_residual * 0.5 * r ** 2 / var[:, None]).mean()
+    if c_ineq > 0:
+        # reference :679,:694: var is extracted with the residual's rank ([B,1]) while the inequality is [B]: the
+        # quotient broadcasts to [B,B]
+        loss = loss + (c_ineq * 0.5 * ineq[None, :] ** 2 / var[:, None]).mean()
+    loss = loss + (lambda_opt * comp).mean()
+    return loss, dict(data=data, residual_abs=r.abs().mean(), inequality=ineq.mean(), compliance=comp.mean(), model_out=out,
+                      residual=r)
+
+
 # --------------------------------------------------------------------------------------------
 # A14  step glue: clip + Adam + EMA     (main.py:163-166,178-183,316 ; denoising_utils.py:163-205)
 # --------------------------------------------------------------------------------------------

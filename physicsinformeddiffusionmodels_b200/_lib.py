@@ -68,6 +68,7 @@ _SIGS = {
     'pidm_adam_ema_step': [P, P, P, P, P, L, F, D, D, F, I, P, P, F, F, F, I, I, P],
     'pidm_mechanics_residual_fwd': [P, P, P, P, P, P, I, I, P],
     'pidm_mechanics_residual_bwd': [P, P, P, P, P, P, P, P, P, I, I, P],
+    'pidm_mech_pidm_loss': [P, P, P, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, I, I, P],
     'pidm_bilinear_resize_fwd': [P, P, I, I, I, P],
     'pidm_bilinear_resize_bwd': [P, P, I, I, I, P],
     'pidm_version': [],

@@ -435,7 +435,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
 bool la_small_supported(int N, int dtype);
 int la_small_fwd(const void* qkv, void* out, float* ctx, float* kmax, float* kzinv, int B, int N, int heads, float scale,
                  cudaStream_t st);
-int la_small_bwd(const void* qkv, const void* dout, void* dqkv, int B, int N, int heads, float scale, cudaStream_t st);
 int la_mma_ctx(int mode, const void* qkv, const void* dout, const float* part, int n_stat_chunks, float* kmax,
                float* kzinv, float* ctx, int B, int N, float scale, cudaStream_t st);
 int la_mma_out(const void* qkv, const float* ctx, void* out, int B, int N, float scale, cudaStream_t st);
@@ -470,7 +469,7 @@ extern "C" int pidm_linattn_fwd(const void* qkv, void* out, float* ctx, float* k
     const int chunks = la_chunks(N);
     const int rpc = (N + chunks - 1) / chunks;
     const float scale = 0.17677669529663687f;   // 32^-0.5
-    if (la_small_supported(N, dtype))     // 16x16 / 8x8 levels: the whole (sample, head) problem in one CTA, one launch
+    if (la_small_supported(N, dtype))     // 8x8 level: the whole (sample, head) problem in one CTA, one launch
         return la_small_fwd(qkv, out, ctx, kmax, kzinv, B, N, heads, scale, st);
     PIDM_CUDA(cudaMemsetAsync(ctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
     if (dtype == PIDM_BF16 && heads == 8 && N % 64 == 0) {
@@ -502,8 +501,6 @@ extern "C" int pidm_linattn_bwd(const void* qkv, const void* dout, const float* 
     PIDM_REQUIRE(N % 32 == 0 && heads % LA_HB == 0, "linattn_bwd: N%%32==0 and heads%%4==0 required");
     cudaStream_t st = (cudaStream_t)stream;
     const float scale = 0.17677669529663687f;
-    if (la_small_supported(N, dtype))     // recomputes k~, p, ctx from qkv: needs none of the saved statistics
-        return la_small_bwd(qkv, dout, dqkv, B, N, heads, scale, st);
     PIDM_CUDA(cudaMemsetAsync(dctx, 0, (size_t)B * heads * DH * DH * sizeof(float), st));
     if (dtype == PIDM_BF16 && heads == 8 && N % 64 == 0) {
         if (int e = la_mma_ctx(1, qkv, dout, nullptr, 0, nullptr, nullptr, dctx, B, N, scale, st)) return e;

@@ -11,7 +11,7 @@
 // dependent kernels plus two memsets, each a grid-wide pass) was pure launch / dependency latency: 16.6-18.7 us
 // forward and 20.1-20.7 us backward per layer for 6..25 MB of traffic.  Here the whole chain runs inside one CTA on
 // CUDA cores (the products are 32-wide: 2 MFLOP per CTA), 256 CTAs = one wave.
-// The backward recomputes k~, p and ctx from qkv (cheaper than reading them back), so it needs nothing saved but qkv.
+// (A one-CTA backward was built and measured too: no faster than the streaming backward at 64 tokens, slower at 256.)
 #define PIDM_PDL_GROUP 1
 #include "common.cuh"
 #include "pidm.h"
@@ -22,7 +22,7 @@ constexpr int LS_D = 32;            // dim_head
 constexpr int LS_PITCH = LS_D + 1;  // fp32 row pitch: a thread that owns a token walks its row without bank conflicts
 constexpr int LS_BPITCH = LS_D + 2;  // bf16 row pitch of the read-only planes (v, dout): 17 words, odd -> conflict-free rows
 constexpr int LS_THREADS = 256;
-constexpr int LS_MAXN = 256;
+constexpr int LS_MAXN = 256;       // kernels are written for N <= 256; the dispatcher only routes N <= 64 here (see below)
 
 // dynamic shared memory layout: fp32 planes [N][LS_PITCH] for the operands that are transformed in place (q -> p,
 // k -> k~), bf16 planes [N][LS_BPITCH] for the read-only ones (v, dout: they ARE bf16, nothing is lost), small vectors
@@ -171,134 +171,28 @@ __global__ void __launch_bounds__(LS_THREADS) la_small_fwd_kernel(const __nv_bfl
     }
 }
 
-// ---- backward ------------------------------------------------------------------------------------------------------
-//   dp[n,d] = sum_e dout[n,e] ctx[d][e];  dq = s p (dp - sum_d p dp)                       (p = softmax, unscaled)
-//   dctx[d][e] = s sum_n p[n,d] dout[n,e];  cd[d] = sum_e dctx[d][e] ctx[d][e]
-//   dk = k~ ((v/N) dctx^T - cd);  dv = (k~ dctx) / N
-__global__ void __launch_bounds__(LS_THREADS) la_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                  const __nv_bfloat16* __restrict__ dout,
-                                                                  __nv_bfloat16* __restrict__ dqkv, int N, int heads,
-                                                                  float scale) {
-    pdl_trigger();
-    pdl_wait();
-    extern __shared__ __align__(16) float sm[];
-    const LsLayout L(N);
-    float* Q = sm;
-    float* K = Q + L.plane;
-    float* ctx = K + L.plane;                  // [32][32]
-    float* dctx = ctx + LS_D * LS_D;           // [32][32]
-    float* red = dctx + LS_D * LS_D;           // [8][32]
-    float* colM = red + 8 * 32;
-    float* colZi = colM + 32;
-    float* cd = colZi + 32;
-    __nv_bfloat16* V = reinterpret_cast<__nv_bfloat16*>(cd + 32);
-    __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(cd + 32 + L.bplane);      // dout
-    const int h = blockIdx.x, b = blockIdx.y, HID = heads * LS_D;
-    const size_t stride = 3 * (size_t)HID;
-    const __nv_bfloat16* base = qkv + (size_t)b * N * stride + h * LS_D;
-    ls_load_plane(Q, base, stride, N);
-    ls_load_plane(K, base + HID, stride, N);
-    ls_load_bplane(V, base + 2 * HID, stride, N);
-    ls_load_bplane(G, dout + (size_t)b * N * HID + h * LS_D, HID, N);
-    __syncthreads();
-    ls_col_softmax(K, red, colM, colZi, N);                        // K <- k~
-    ls_row_softmax(Q, N);                                          // Q <- p (unscaled softmax)
-    __syncthreads();
-    const float invN = 1.f / (float)N;
-    ls_outer_sum(ctx, K, V, N, invN);
-    ls_outer_sum(dctx, Q, G, N, scale);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int e = 0; e < LS_D; ++e) s += dctx[threadIdx.x * LS_D + e] * ctx[threadIdx.x * LS_D + e];
-        cd[threadIdx.x] = s;
-    }
-    __syncthreads();
-    // work item = (part, token): part 0 -> dq, 1 -> dk, 2 -> dv; each writes one 64-byte row segment of dqkv
-    __nv_bfloat16* obase = dqkv + (size_t)b * N * stride + h * LS_D;
-    for (int w = threadIdx.x; w < 3 * N; w += blockDim.x) {
-        const int part = w / N, n = w - part * N;
-        float o[LS_D];
-        if (part == 0) {
-            float g[LS_D];
-#pragma unroll
-            for (int e = 0; e < LS_D; e += 2) { const float2 t = ls_b2(G + n * LS_BPITCH + e); g[e] = t.x; g[e + 1] = t.y; }
-            const float* p = Q + n * LS_PITCH;
-            float dot = 0.f;
-#pragma unroll
-            for (int d = 0; d < LS_D; ++d) {
-                float dp = 0.f;
-#pragma unroll
-                for (int e = 0; e < LS_D; ++e) dp += g[e] * ctx[d * LS_D + e];
-                o[d] = dp;
-                dot += p[d] * dp;
-            }
-#pragma unroll
-            for (int d = 0; d < LS_D; ++d) o[d] = scale * p[d] * (o[d] - dot);
-        } else if (part == 1) {
-            float v[LS_D];
-#pragma unroll
-            for (int e = 0; e < LS_D; e += 2) { const float2 t = ls_b2(V + n * LS_BPITCH + e); v[e] = t.x; v[e + 1] = t.y; }
-            const float* kt = K + n * LS_PITCH;
-#pragma unroll
-            for (int d = 0; d < LS_D; ++d) {
-                float dk = 0.f;
-#pragma unroll
-                for (int e = 0; e < LS_D; ++e) dk += v[e] * dctx[d * LS_D + e];
-                o[d] = kt[d] * (dk * invN - cd[d]);
-            }
-        } else {
-            const float* kt = K + n * LS_PITCH;
-#pragma unroll
-            for (int e = 0; e < LS_D; ++e) o[e] = 0.f;
-#pragma unroll
-            for (int d = 0; d < LS_D; ++d) {
-                const float kv = kt[d];
-#pragma unroll
-                for (int e = 0; e < LS_D; ++e) o[e] += kv * dctx[d * LS_D + e];
-            }
-#pragma unroll
-            for (int e = 0; e < LS_D; ++e) o[e] *= invN;
-        }
-        __nv_bfloat16* dst = obase + (size_t)n * stride + part * HID;
-#pragma unroll
-        for (int k = 0; k < LS_D; k += 8) st8(dst + k, o + k);
-    }
-}
-
 static size_t ls_smem(int N, bool bwd) {
     const LsLayout L(N);
     return (size_t)(2 * L.plane + (bwd ? 2 : 1) * LS_D * LS_D + 8 * 32 + 3 * 32 + (bwd ? 2 : 1) * L.bplane) * sizeof(float);
 }
 
 // entry points used by attention.cu
-bool la_small_supported(int N, int dtype) { return dtype == PIDM_BF16 && N >= 32 && N <= LS_MAXN; }
+// Measured at B = 32 (graph-replayed, us per layer, streaming kernels -> this file):
+//   N =  64: forward 16.3 -> 8.7, backward 20.0 -> 19.9        N = 256: forward 18.5 -> 26.9, backward 20.7 -> 48.3
+// At 256 tokens the 32-wide products (0.7 GFLOP per layer) are CUDA-core FLOP-bound here while the streaming kernels
+// run them on mma.sync, so only the 8x8 level takes this path, and only where it wins (forward).
+bool la_small_supported(int N, int dtype) { return dtype == PIDM_BF16 && N >= 32 && N <= 64; }
 
 int la_small_fwd(const void* qkv, void* out, float* ctx, float* kmax, float* kzinv, int B, int N, int heads, float scale,
                  cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         PIDM_CUDA(cudaFuncSetAttribute(la_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem(LS_MAXN, false)));
-        PIDM_CUDA(cudaFuncSetAttribute(la_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem(LS_MAXN, true)));
         attr = true;
     }
     PIDM_CUDA(launch_pdl(la_small_fwd_kernel, dim3(heads, B), dim3(LS_THREADS), ls_smem(N, false), st, (const __nv_bfloat16*)qkv,
                          (__nv_bfloat16*)out, ctx, kmax, kzinv, N, heads, scale));
     PIDM_LAUNCH_CHECK("la_small_fwd");
-    return 0;
-}
-
-int la_small_bwd(const void* qkv, const void* dout, void* dqkv, int B, int N, int heads, float scale, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        PIDM_CUDA(cudaFuncSetAttribute(la_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem(LS_MAXN, false)));
-        PIDM_CUDA(cudaFuncSetAttribute(la_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem(LS_MAXN, true)));
-        attr = true;
-    }
-    PIDM_CUDA(launch_pdl(la_small_bwd_kernel, dim3(heads, B), dim3(LS_THREADS), ls_smem(N, true), st, (const __nv_bfloat16*)qkv,
-                         (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, N, heads, scale));
-    PIDM_LAUNCH_CHECK("la_small_bwd");
     return 0;
 }
 

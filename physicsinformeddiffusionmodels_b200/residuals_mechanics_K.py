@@ -73,6 +73,34 @@ class _MechResidual(torch.autograd.Function):
         return gu, grho, None, None
 
 
+class _MechPidmLoss(torch.autograd.Function):
+    """Data + residual + inequality + optimisation terms of the mechanics PIDM loss and their gradients in ONE libpidm
+    launch (csrc/mechanics.cu mech_loss_kernel; reference denoising_utils.py:669-710).  Like the Darcy loss the gradients
+    are produced in forward and only scaled (out of place) in backward.  Returns (loss, sums6)."""
+
+    @staticmethod
+    def forward(ctx, u, rho, residual, compliance, x0, vf, t, p2w, pvar, coefs):
+        B, _, nn_, _ = u.shape
+        c_data, c_res, c_ineq, lam = coefs
+        sums = torch.empty(6, device=u.device, dtype=torch.float32)
+        gu, grho, gr, gc = torch.empty_like(u), torch.empty_like(rho), torch.empty_like(residual), torch.empty_like(compliance)
+        call('pidm_mech_pidm_loss', u, rho, x0, residual, compliance, vf, t, p2w, pvar, float(c_data), float(c_res),
+             float(c_ineq), float(lam), sums, gu, grho, gr, gc, B, nn_ - 1, stream())
+        ctx.save_for_backward(gu, grho, gr, gc)
+        ctx.mark_non_differentiable(sums)
+        return sums[0] + sums[1] + sums[2] + sums[3], sums
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        g = g.contiguous().float()
+        outs = []
+        for t_ in ctx.saved_tensors:
+            o = torch.empty_like(t_)
+            call('pidm_scale', t_, g, o, t_.numel(), stream())
+            outs.append(o)
+        return (*outs, None, None, None, None, None, None)
+
+
 class ResidualsMechanics:
     def __init__(self, model, pixels_per_dim, pixels_at_boundary, no_BC_folder, device='cpu', bcs='none', E=1.0,
                  nu=0.3, topopt_eval=False, use_ddim_x0=False, ddim_steps=0):
@@ -145,12 +173,15 @@ class ResidualsMechanics:
     # ---- hooks used by DenoisingDiffusion (mechanics branch of the reference's loss / sampler) ------------------
     def training_loss(self, diffusion, input, t, c_data, c_residual, c_ineq, lambda_opt, sync_scalars=True,
                       draw_shard=None):
-        """model_estimation_loss for gov_eqs='mechanics' (reference denoising_utils.py:629-710)."""
+        """model_estimation_loss for gov_eqs='mechanics' (reference denoising_utils.py:629-710).
+        input [B,10,65,65] = (vf, strain energy, von Mises | disp_x, disp_y, E | bc_x, bc_y, load_x, load_y).
+        Mean-mode x0 (the reference default): q_sample, the two resamplings, the matrix-free residual and ONE fused loss
+        kernel are libpidm launches; no host synchronisation unless sync_scalars (the reference reads four .item()s)."""
         from . import ops
         from .denoising_utils import image_to_b_xy_c
         dd = diffusion.diff_dict
         conditioning, x_0, bcs = torch.tensor_split(input, (3, 6), dim=1)
-        x_0 = x_0.contiguous()
+        x_0 = x_0.contiguous().float()
         if draw_shard is None or draw_shard[1] == 1:
             e = torch.randn_like(x_0)
         else:
@@ -159,24 +190,38 @@ class ResidualsMechanics:
             e = torch.randn((B * world,) + tuple(x_0.shape[1:]), device=x_0.device, dtype=x_0.dtype)[rank * B:(rank + 1) * B]
         x = ops.q_sample(x_0, e, t, dd['alphas_bar_sqrt'], dd['one_minus_alphas_bar_sqrt'])
         x = torch.cat((x, conditioning), dim=1)
-        vf = conditioning[:, 0, 0, 0]
-        out = self.compute_residual(((image_to_b_xy_c(x), t), bcs, vf, x_0), reduce='per-batch', return_model_out=True,
-                                    return_optimizer=True, return_inequality=c_ineq > 0.,
-                                    ddim_func=diffusion.ddim_sample_x0)
-        residual, output = out['residual'], out['model_out']
-        B = x_0.shape[0]
-        mse = ((x_0 - output) ** 2).reshape(B, -1).mean(dim=1)
-        data_loss = c_data * (mse * dd['p2_loss_weight'][t]).mean()
-        var = dd['posterior_variance_clipped'][t]
-        loss = data_loss + (c_residual * 0.5 * residual ** 2 / var[:, None]).mean()
-        ineq_track = 0.
-        if c_ineq > 0.:
-            # reference quirk kept (:679,:694): `var` is extracted with the residual's rank ([B,1]) while the inequality
-            # is [B], so the quotient broadcasts to [B,B]: mean_i(1/var_i) * mean_j(ineq_j^2) * c_ineq / 2
-            loss = loss + (c_ineq * 0.5 * out['inequality'][None, :] ** 2 / var[:, None]).mean()
-            ineq_track = out['inequality'].mean()
-        loss = loss + (lambda_opt * out['optimizer']).mean()
-        tracked = (data_loss.detach(), residual.detach().abs().mean(), ineq_track, out['optimizer'].detach().mean())
+        vf = conditioning[:, 0, 0, 0].contiguous().float()
+        if not self.use_ddim_x0:
+            bcs = bcs.contiguous().float()
+            net_in = torch.cat((resize_image(x, 64), resize_image(bcs, 64)), dim=1)
+            y = self.model(net_in, t)                                        # [B,3,64,64]: u_x, u_y, rho (sigmoid)
+            P = y.shape[-1]
+            u = resize_image(y[:, :-1], P + 1)
+            rho = y[:, -1].contiguous()
+            residual, compliance = _MechResidual.apply(u, rho, bcs, self.KE)
+            loss, sums = _MechPidmLoss.apply(u, rho, residual, compliance, x_0, vf, t.to(torch.int64).contiguous(),
+                                             dd['p2_loss_weight'], dd['posterior_variance_clipped'],
+                                             (c_data, c_residual, c_ineq, lambda_opt))
+            # tracked scalars of the reference: data loss, mean|r|, mean inequality (only if c_ineq > 0), mean compliance
+            tracked = (sums[0], sums[4], sums[5] if c_ineq > 0. else 0., compliance.detach().mean())
+        else:
+            out = self.compute_residual(((image_to_b_xy_c(x), t), bcs, vf, x_0), reduce='per-batch', return_model_out=True,
+                                        return_optimizer=True, return_inequality=c_ineq > 0.,
+                                        ddim_func=diffusion.ddim_sample_x0)
+            residual, output = out['residual'], out['model_out']
+            B = x_0.shape[0]
+            mse = ((x_0 - output) ** 2).reshape(B, -1).mean(dim=1)
+            data_loss = c_data * (mse * dd['p2_loss_weight'][t]).mean()
+            var = dd['posterior_variance_clipped'][t]
+            loss = data_loss + (c_residual * 0.5 * residual ** 2 / var[:, None]).mean()
+            ineq_track = 0.
+            if c_ineq > 0.:
+                # reference quirk kept (:679,:694): `var` is extracted with the residual's rank ([B,1]) while the
+                # inequality is [B], so the quotient broadcasts to [B,B]: mean_i(1/var_i) * mean_j(ineq_j^2) * c_ineq / 2
+                loss = loss + (c_ineq * 0.5 * out['inequality'][None, :] ** 2 / var[:, None]).mean()
+                ineq_track = out['inequality'].detach().mean()
+            loss = loss + (lambda_opt * out['optimizer']).mean()
+            tracked = (data_loss.detach(), residual.detach().abs().mean(), ineq_track, out['optimizer'].detach().mean())
         if sync_scalars:
             tracked = tuple(float(v) for v in tracked)
         return (loss,) + tracked

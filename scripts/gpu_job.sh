@@ -2,7 +2,7 @@
 # development job on one GPU: GPU test suite, per-layer timings, bench.  Usage: gpurun -- bash scripts/gpu_job.sh <tag> [pytest-filter]
 TAG=${1:-job}
 FILTER=${2:-}
-BENCH_FLAGS=${3:---no-cpu-baseline --no-sampling --no-torch-cuda-baseline}
+BENCH_FLAGS=${3:---no-cpu-baseline --no-sampling --no-torch-cuda-baseline --no-mechanics}
 mkdir -p gpurun_out
 PT="python -m pytest -q -p no:cacheprovider --timeout 600 --timeout-method=thread"
 if [ -n "$FILTER" ]; then

@@ -167,3 +167,24 @@ def test_mechanics_residual_matches_reference(golden):
     assert torch.allclose(q, gd['inequality'], atol=1e-6)
     ((r * gd['cotangent']).sum() + 0.3 * c.sum() + 2.0 * q.sum()).backward()
     assert rel(x.grad, gd['grad_x0_pred']) < 5e-5
+
+
+def test_mechanics_training_loss_matches_reference(golden):
+    """The reference's own model_estimation_loss for gov_eqs='mechanics' (dense 8450 x 8450 assembly, B = 2, all four loss
+    terms on; c_ineq > 0 pins the [B,1] x [B] broadcast of denoising_utils.py:679,694) vs the matrix-free oracle."""
+    gd = golden('mechanics_loss.pt')
+    cfg = O.unet_config(dim=32, channels=10, out_dim=3, sigmoid_last_channel=True)
+    sd = O.make_test_state_dict(cfg, 3)
+    sdr = {k: v.clone().requires_grad_(v.is_floating_point() and 'freqs' not in k) for k, v in sd.items()}
+    c_data, c_res, c_ineq, lam = gd['coefs'].tolist()
+    loss, aux = O.mechanics_training_loss(sdr, cfg, gd['input'], gd['t'], gd['noise'], O.diffusion_tables(100), c_data, c_res,
+                                          c_ineq, lam)
+    assert abs(loss.item() / gd['loss'].item() - 1) < 2e-5
+    assert abs(aux['data'].item() / gd['data_loss'].item() - 1) < 2e-5
+    assert abs(aux['residual_abs'].item() / gd['residual_abs'].item() - 1) < 2e-5
+    assert abs(aux['inequality'].item() - gd['inequality'].item()) < 1e-6
+    assert abs(aux['compliance'].item() / gd['compliance'].item() - 1) < 2e-5
+    loss.backward()
+    assert rel(sdr['final_conv.1.weight'].grad, gd['grad_final_w']) < 1e-4
+    assert rel(sdr['init_conv.weight'].grad, gd['grad_init_w']) < 1e-4
+    assert rel(sdr['downs.1.0.block1.proj.weight'].grad, gd['grad_mid_w']) < 1e-4
