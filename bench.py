@@ -436,12 +436,15 @@ def main():
     diff = DenoisingDiffusion(100, dev)
     res = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True, device=dev,
                          bcs='none', domain_length=1.)
+    # data parallel: t / eps are drawn for the GLOBAL batch from a generator that is identical on every rank and sliced
+    # to the rank's rows (the N-rank job consumes the random numbers of the one-process run on N*32 samples)
     eng = TrainEngine(model, diff, res, lr=1e-4, max_norm=1.0, ema_mu=0.99, c_data=1.0, c_residual=1e-3,
-                      use_graph=not args.no_graph, world=world)
-    torch.manual_seed(1234 + rank)                    # different data / noise per rank
+                      use_graph=not args.no_graph, world=world, rank=rank, global_draws=True)
     B = PER_GPU_BATCH
-    x0_dev = torch.randn(B, 2, 64, 64, device=dev)
-    x0_host = torch.randn(B, 2, 64, 64).pin_memory()
+    gdata = torch.Generator().manual_seed(1234 + rank)                     # different data per rank
+    x0_dev = torch.randn(B, 2, 64, 64, generator=gdata).to(dev)
+    x0_host = torch.randn(B, 2, 64, 64, generator=gdata).pin_memory()
+    torch.cuda.manual_seed(1234)                                          # identical noise stream on every rank
     loss_host = torch.zeros(1).pin_memory()
 
     def barrier():
@@ -580,15 +583,17 @@ def main():
         out.update(extra)
         print(json.dumps(out), flush=True)
     if world > 1:
-        # Leave without tearing the communicator down: ncclCommDestroy while CUDA graphs that captured NCCL kernels are
-        # still alive has been observed to hang; the result is printed, every rank is past the barrier, and the OS
-        # reclaims the rest.
+        # orderly teardown: the captured graphs hold NCCL kernels, so they go first, then the communicator
         faulthandler.cancel_dump_traceback_later()
-        torch.cuda.synchronize()
-        dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        watchdog = threading.Timer(60.0, lambda: os._exit(0))   # the result is printed: a stuck teardown must not stall the driver
+        watchdog.daemon = True
+        watchdog.start()
+        eng.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == '__main__':

@@ -165,6 +165,22 @@ def _axpby(a, x, b, y, c, z):
     return out
 
 
+def draw_t_and_noise(n_steps, x_0, draw_shard=None):
+    """The two RNG draws of the training loss in the reference's order (denoising_utils.py:625,636): t ~ U{0..n_steps-1}
+    per sample, then eps ~ N(0,1) of x_0's shape.  draw_shard=(rank, world): both are drawn for the GLOBAL batch
+    (world * len(x_0) rows) and this rank's rows are sliced out, so that ranks with identical generator states consume
+    exactly the random numbers of the one-process run on the concatenated batch."""
+    B = len(x_0)
+    rank, world = draw_shard if draw_shard is not None else (0, 1)
+    lo, hi = rank * B, (rank + 1) * B
+    t = torch.randint(0, n_steps, size=(B * world,), device=x_0.device)[lo:hi]
+    if world == 1:
+        e = torch.randn_like(x_0)
+    else:
+        e = torch.randn((B * world,) + tuple(x_0.shape[1:]), device=x_0.device, dtype=x_0.dtype)[lo:hi]
+    return t, e
+
+
 class DenoisingDiffusion(nn.Module):
     def __init__(self, n_steps, device, residual_grad_guidance=False):
         # like the reference, nn.Module.__init__ is deliberately not called (no parameters are owned)
@@ -222,20 +238,12 @@ class DenoisingDiffusion(nn.Module):
         draw_shard=(rank, world): t / eps are drawn for the GLOBAL batch (world * len(input) rows) and sliced to this
         rank's rows -- with identical generator states on all ranks the data-parallel job consumes the same random
         numbers as the one-process run on the concatenated batch."""
-        batch_size = len(input)
         sync = self.sync_scalars if sync_scalars is None else sync_scalars
-        rank, world = draw_shard if draw_shard is not None else (0, 1)
-        lo, hi = rank * batch_size, (rank + 1) * batch_size
-        t = torch.randint(0, self.n_steps, size=(batch_size * world,), device=input.device)[lo:hi]   # draw 1 (ref :625)
         if residual_func.gov_eqs == 'darcy':
-            if world == 1:
-                e = torch.randn_like(input)                                              # RNG draw 2 (reference :636)
-            else:
-                e = torch.randn((batch_size * world,) + tuple(input.shape[1:]), device=input.device,
-                                dtype=input.dtype)[lo:hi]
+            t, e = draw_t_and_noise(self.n_steps, input, draw_shard)
             return self.darcy_loss_from_draws(input, t, e, residual_func, c_data, c_residual, sync_scalars=sync)
         if residual_func.gov_eqs == 'mechanics':
-            return residual_func.training_loss(self, input, t, c_data, c_residual, c_ineq, lambda_opt,
+            return residual_func.training_loss(self, input, None, c_data, c_residual, c_ineq, lambda_opt,
                                                sync_scalars=sync, draw_shard=draw_shard)
         raise ValueError('Unknown governing equations.')
 

@@ -25,21 +25,30 @@ class FlatParams:
 
     def __init__(self, model, with_optimizer_state=True, group_of=None):
         """group_of(name) -> int (optional): parameters are laid out group by group (stable within a group), and
-        `group_bounds[g] = (lo, hi)` is the flat range of group g -- the engine all-reduces ranges separately."""
+        `group_bounds[g] = (lo, hi)` is the flat range of group g -- the engine all-reduces ranges separately.
+        Parameters the forward pass never uses (model.unused_parameter_names(), 1.46 M elements for the Darcy U-Net)
+        are laid out LAST: `live_total` is the length of the prefix that can carry a gradient, and only that prefix
+        is exchanged between the ranks (their gradient is identically zero on every rank)."""
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-        if group_of is not None:
-            named.sort(key=lambda np_: group_of(np_[0]))               # stable: model order inside a group
+        dead = set(model.unused_parameter_names()) if hasattr(model, 'unused_parameter_names') else set()
+        order = {n: i for i, (n, _) in enumerate(named)}
+        named.sort(key=lambda np_: (np_[0] in dead, group_of(np_[0]) if group_of is not None else 0, order[np_[0]]))
         params = [p for _, p in named]
         dev = params[0].device
         offs, total = [], 0
         self.group_bounds = {}
+        self.live_total = None
         for n, p in named:
+            if n in dead and self.live_total is None:
+                self.live_total = total
             offs.append(total)
-            if group_of is not None:
+            if group_of is not None and n not in dead:
                 g = group_of(n)
                 lo, _ = self.group_bounds.get(g, (total, total))
                 self.group_bounds[g] = (lo, total + (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN)
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        if self.live_total is None:
+            self.live_total = total
         self.total = total
         self.params, self.offsets = params, offs
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -69,10 +78,11 @@ def shard_rows(global_batch, rank, world):
     return rank * per, (rank + 1) * per
 
 
-def allreduce_flat_grad(flat_grad, world):
-    """The single exchange step of the data-parallel path: sum of the flat gradient over all ranks."""
+def allreduce_flat_grad(flat_grad, world, live=None):
+    """The single exchange step of the data-parallel path: sum of the flat gradient over all ranks.  `live`: length of
+    the prefix that can be non-zero (FlatParams.live_total); the tail belongs to parameters the forward never uses."""
     if world > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        dist.all_reduce(flat_grad if live is None else flat_grad[:live], op=dist.ReduceOp.SUM)
     return flat_grad
 
 
@@ -147,7 +157,7 @@ class TrainEngine:
             if self._ar_stream is not None:
                 torch.cuda.current_stream().wait_stream(self._ar_stream)
         else:
-            allreduce_flat_grad(fp.grad, self.world)
+            allreduce_flat_grad(fp.grad, self.world, fp.live_total)
         if self.grad_snapshot is not None:
             self.grad_snapshot.copy_(fp.grad)
         fp.gnorm_sq.zero_()
@@ -217,6 +227,21 @@ class TrainEngine:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_out = self._step_body(self._static_x0)
+
+    def close(self):
+        """Release everything that pins NCCL / CUDA-graph resources: the captured graph (it holds NCCL kernels when
+        world > 1, and ncclCommDestroy waits for it), the static tensors, and the model -> engine back reference of the
+        bucketed exchange (a reference cycle that would keep the graph alive past `del engine`).  Call before
+        torch.distributed.destroy_process_group()."""
+        import gc
+        torch.cuda.synchronize()
+        self._graph = None
+        self._static_x0 = None
+        self._static_out = None
+        if getattr(self.model, '_boundary_cb', None) is not None:
+            self.model._boundary_cb = None
+        gc.collect()
+        torch.cuda.synchronize()
 
     def ema_state_dict(self):
         """EMA weights keyed like model.state_dict() (what the reference checkpoints hold, main.py:314)."""

@@ -176,18 +176,17 @@ class ResidualsMechanics:
         """model_estimation_loss for gov_eqs='mechanics' (reference denoising_utils.py:629-710).
         input [B,10,65,65] = (vf, strain energy, von Mises | disp_x, disp_y, E | bc_x, bc_y, load_x, load_y).
         Mean-mode x0 (the reference default): q_sample, the two resamplings, the matrix-free residual and ONE fused loss
-        kernel are libpidm launches; no host synchronisation unless sync_scalars (the reference reads four .item()s)."""
+        kernel are libpidm launches; no host synchronisation unless sync_scalars (the reference reads four .item()s).
+        t=None: draw it here (the normal path); a given t is used as is (tests)."""
         from . import ops
         from .denoising_utils import image_to_b_xy_c
         dd = diffusion.diff_dict
         conditioning, x_0, bcs = torch.tensor_split(input, (3, 6), dim=1)
         x_0 = x_0.contiguous().float()
-        if draw_shard is None or draw_shard[1] == 1:
-            e = torch.randn_like(x_0)
-        else:
-            rank, world = draw_shard
-            B = x_0.shape[0]
-            e = torch.randn((B * world,) + tuple(x_0.shape[1:]), device=x_0.device, dtype=x_0.dtype)[rank * B:(rank + 1) * B]
+        from .denoising_utils import draw_t_and_noise
+        t_drawn, e = draw_t_and_noise(diffusion.n_steps, x_0, draw_shard)      # reference order: t, then eps (:625,:636)
+        if t is None:
+            t = t_drawn
         x = ops.q_sample(x_0, e, t, dd['alphas_bar_sqrt'], dd['one_minus_alphas_bar_sqrt'])
         x = torch.cat((x, conditioning), dim=1)
         vf = conditioning[:, 0, 0, 0].contiguous().float()

@@ -253,6 +253,22 @@ class Unet3D(nn.Module):
         plan_rb(self.final_conv[0])
         self._mlp_table = MlpTable(mlps)
 
+    def unused_parameter_names(self):
+        """Trainable parameters that Unet3D.forward never touches (they exist for state_dict parity with the reference:
+        temporal attentions, relative position bias, signal embedding, the to_q / to_k / to_v side projections, emb_conv,
+        combine_conv).  They never receive a gradient -- in the reference their .grad stays None (checked against the
+        reference-generated tests/golden/params_without_grad.txt) -- so a data-parallel step need not exchange them."""
+        dead = []
+        for name, p in self.named_parameters():
+            if not p.requires_grad:
+                continue
+            parts = name.split('.')
+            if (name.startswith(('time_rel_pos_bias.', 'sign_emb_CNN.', 'emb_conv.', 'combine_conv.', 'init_temporal_attn.',
+                                 'mid_temporal_attn.'))
+                    or parts[-2] in ('to_q', 'to_k', 'to_v')):
+                dead.append(name)
+        return dead
+
     # ---- kernels ----------------------------------------------------------------------------------------
     # set by engine.TrainEngine: called during backward when the gradients of a parameter group are complete
     _boundary_cb = None

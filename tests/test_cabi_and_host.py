@@ -125,8 +125,39 @@ allreduce_flat_grad(g, world)
 g /= world
 full = grad(slice(0, 8))
 assert torch.allclose(g, full, atol=1e-6), (g - full).abs().max()
+# only the live prefix of the flat gradient is exchanged: the tail (parameters the forward never uses) stays untouched
+h = torch.full((10,), float(rank + 1))
+allreduce_flat_grad(h, world, live=6)
+assert torch.equal(h[:6], torch.full((6,), 3.0)) and torch.equal(h[6:], torch.full((4,), float(rank + 1)))
+# global-batch draws (SURVEY 8e): with identical generator states the rank shards are the rows of the one-process draws
+from physicsinformeddiffusionmodels_b200.denoising_utils import draw_t_and_noise
+x_shard = torch.zeros(4, 2, 8, 8)
+torch.manual_seed(123)
+t_r, e_r = draw_t_and_noise(100, x_shard, (rank, world))
+torch.manual_seed(123)
+t_1, e_1 = draw_t_and_noise(100, torch.zeros(4 * world, 2, 8, 8), None)
+assert torch.equal(t_r, t_1[4 * rank:4 * rank + 4]) and torch.equal(e_r, e_1[4 * rank:4 * rank + 4])
 print('rank', rank, 'ok')
 '''
+
+
+def test_flat_layout_puts_unused_parameters_last():
+    """FlatParams: the 56 parameters forward never touches (the reference leaves their .grad at None) form the tail of
+    the flat buffers, so the data-parallel exchange covers only [0, live_total)."""
+    from physicsinformeddiffusionmodels_b200.engine import FlatParams
+    from physicsinformeddiffusionmodels_b200.unet_model import Unet3D
+    model = Unet3D(dim=32, channels=2)
+    dead = set(model.unused_parameter_names())
+    with open(os.path.join(ROOT, 'tests', 'golden', 'params_without_grad.txt')) as f:
+        ref_dead = {k for k in f.read().split() if not k.endswith('rotary_emb.freqs')}
+    assert dead == ref_dead
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    fp = FlatParams(model, with_optimizer_state=False)
+    names = {id(p): n for n, p in model.named_parameters()}
+    for p, o in zip(fp.params, fp.offsets):
+        assert (o >= fp.live_total) == (names[id(p)] in dead), names[id(p)]
+        assert torch.equal(p.detach(), before[names[id(p)]])          # re-homing keeps the values
+    assert 0 < fp.total - fp.live_total < 1.6e6 and fp.live_total % 64 == 0
 
 
 def test_data_parallel_gradient_is_full_batch_gradient_gloo(tmp_path):
