@@ -40,6 +40,16 @@ int pidm_axpby_per_sample(const float* a, const float* x, const float* b, const 
 /* out = x * *alpha_dev  (chain-rule scaling of a precomputed gradient by the upstream scalar; out may alias x) */
 int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream);
 
+/* ---- toy study (main_toy.py, src/denoising_toy_utils.py:436-511): PIDM loss algebra on [B,D] points ---------- */
+/* data term c_data*mean_b(w_b*mean_D(target-output)^2) with w_b = p2[t_b] (p2_loss_weight != NULL) or 1; Gaussian NLL of the
+ * residual / inequality values with the log-likelihood clamped at -27.631 (:381); lambda*mean(opt).  ineq / opt may be
+ * NULL.  sums7 = data, residual, inequality, optimisation terms, mean|r|, mean(ineq), mean(opt); gradients overwritten. */
+int pidm_toy_pidm_loss(const float* target, const float* output, const float* residual, const float* ineq,
+                       const float* opt, const long long* t, const float* p2_loss_weight,
+                       const float* posterior_var_clipped, float c_data, float c_residual, float c_ineq, float lambda_opt,
+                       float* sums7, float* grad_output, float* grad_residual, float* grad_ineq, float* grad_opt, int B,
+                       int D, void* stream);
+
 /* ---- Darcy residual (src/residuals_darcy.py:134-183 + src/grad_utils.py:64-146) ------------------------- */
 /* x0hat [B,2,P,P] fp32 NCHW (p, K); f_s [P*P]; residual [B,P*P,3] = (eq_0, bc_x0, bc_x1).  P must be 64. */
 int pidm_darcy_residual_fwd(const float* x0hat, const float* f_s, float* residual, int B, int pixels,
@@ -181,7 +191,8 @@ int pidm_head_bwd(const void* x, const float* w, const float* y, const float* dy
                   int HW, int C, int O, int sigmoid_last, int dtype, void* stream);
 
 /* ---- step glue on flat buffers (main.py:163-166,178-183; src/denoising_utils.py:163-205) ----------------- */
-int pidm_sumsq(const float* x, long long n, float* out, void* stream);
+/* out[0] += sum x^2, deterministic (fixed summation order).  workspace: float[1185] zero-initialised once by the caller. */
+int pidm_sumsq(const float* x, long long n, float* out, float* workspace, void* stream);
 /* Adam (torch.optim.Adam semantics, bias corrections evaluated in double) + global-norm clip + EMA shadow, one pass.
  * step: 1-based host step count, ignored when step_counter_dev != NULL (device counter, incremented by the call).
  * ema_first_step: 0 = no EMA update; k >= 1 = update the shadow from the k-th step on (main.py:178 => ema_start+2). */

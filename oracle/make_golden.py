@@ -263,5 +263,55 @@ def main():
                                        grad_mid_w=named_m['downs.1.0.block1.proj.weight'].grad.clone()))
 
 
+def toy_golden():
+    """configs[0]: the toy study's loss (src/denoising_toy_utils.py:436-511) through the unmodified reference module, with
+    the residual / inequality / optimisation callables of main_toy.py:48-79."""
+    import src.denoising_toy_utils as T
+    assert os.path.abspath(T.__file__).startswith(os.path.abspath(REF)), T.__file__
+    T.device = torch.device('cpu')
+
+    def residual_func(x):
+        return torch.sum(x ** 2, dim=1) - 1.0
+
+    def ineq_func(x):
+        density = torch.sum(torch.abs(x), dim=1)
+        return torch.relu(density - 1.0), density
+
+    def opt_func(x):
+        return x[:, 0]
+    torch.manual_seed(5)
+    np.random.seed(5)
+    model = T.ConditionalModel(2, 100)
+    dd = T.create_diff_dict(100, 'cpu')
+    x0 = torch.tensor(T.sample_hypersphere(128, 2)).float()
+    out = {'x0': x0, **{'sd_' + k: v.clone() for k, v in model.state_dict().items()}}
+    for tag, mode, ddim in (('x0_mean', 'x0', False), ('x0_sample', 'x0', True), ('eps_sample', 'eps', True)):
+        torch.manual_seed(17)
+        loss, data_l, res_l, ineq_l, opt_l = T.model_estimation_loss(
+            model, x0, 100, dd, model_pred_mode=mode, residual_func=residual_func, ineq_func=ineq_func, opt_func=opt_func,
+            c_data=1.0, c_residual=0.005, c_ineq=0.3, lambda_opt=0.01, use_ddim_x0=ddim, reduced_ddim_steps=0)
+        model.zero_grad()
+        loss.backward()
+        out[tag + '_loss'] = loss.detach().clone()
+        out[tag + '_tracked'] = torch.tensor([data_l, res_l, ineq_l, opt_l])
+        out[tag + '_grad_lin3'] = model.lin3.weight.grad.clone()
+        out[tag + '_grad_lin1'] = model.lin1.lin.weight.grad.clone()
+        out[tag + '_grad_embed2'] = model.lin2.embed.weight.grad.clone()
+    torch.manual_seed(17)                                  # replay the draws (:440-441, :447)
+    t = torch.randint(0, 100, size=(128 // 2 + 1,))
+    out['t'] = torch.cat([t, 100 - t - 1], dim=0)[:128].long()
+    out['noise'] = torch.randn_like(x0)
+    # short ancestral loop (x0 mode), draws replayed by the test: x_T then one z per step
+    model.eval()
+    d8 = T.create_diff_dict(8, 'cpu')
+    torch.manual_seed(23)
+    xs, _, _ = T.p_sample_loop(model, [64, 2], 8, d8, model_pred_mode='x0', save_output=False, surpress_noise=True)
+    torch.manual_seed(23)
+    out['loop_draws'] = torch.stack([torch.randn(64, 2) for _ in range(9)])
+    out['loop_final'] = xs[-1]
+    save('toy.pt', out)
+
+
 if __name__ == '__main__':
     main()
+    toy_golden()

@@ -556,6 +556,67 @@ def mechanics_training_loss(sd, cfg, inp, t, noise, tables, c_data=1.0, c_residu
 
 
 # --------------------------------------------------------------------------------------------
+# A15  toy study on [B, D] points   (main_toy.py:48-79, src/denoising_toy_utils.py:171-199, 267-333, 372-383, 436-511)
+# --------------------------------------------------------------------------------------------
+
+
+def toy_model_forward(sd, x, t):
+    """ConditionalModel: softplus(embed1[t] * lin1(x)) -> softplus(embed2[t] * lin2(.)) -> lin3 (:171-199)"""
+    h = F.softplus(sd['lin1.embed.weight'][t] * F.linear(x, sd['lin1.lin.weight'], sd['lin1.lin.bias']))
+    h = F.softplus(sd['lin2.embed.weight'][t] * F.linear(h, sd['lin2.lin.weight'], sd['lin2.lin.bias']))
+    return F.linear(h, sd['lin3.weight'], sd['lin3.bias'])
+
+
+def toy_ddim_x0(sd, xt, t, tables, mode):
+    """ddim_sample_x0 with reduced_n_steps = 0, eta = 0 (:267-333): grid (t, 0) then (0, -1); cur_x advances."""
+    tz = torch.zeros_like(t)
+    out = toy_model_forward(sd, xt, t)
+    ra, rm = tables['sqrt_recip_alphas_cumprod'][t, None], tables['sqrt_recipm1_alphas_cumprod'][t, None]
+    if mode == 'eps':
+        eps, x0p = out, ra * xt - rm * out
+    else:
+        x0p = out
+        mean = tables['posterior_mean_coef1'][t, None] * x0p + tables['posterior_mean_coef2'][t, None] * xt
+        eps = (tables['sqrt_recip_alphas'][t, None] * xt - mean) / tables['noise_mean_coeff'][t, None]
+    a_next = tables['alphas_prod'][tz, None]
+    cur = x0p * a_next.sqrt() + (1 - a_next).sqrt() * eps
+    mask = (t == tz).float()[:, None]
+    cur = mask * xt + (1 - mask) * cur
+    out = toy_model_forward(sd, cur, tz)
+    if mode == 'eps':
+        return tables['sqrt_recip_alphas_cumprod'][tz, None] * cur - tables['sqrt_recipm1_alphas_cumprod'][tz, None] * out
+    return out
+
+
+def toy_training_loss(sd, x0, t, noise, tables, mode='x0', use_ddim_x0=False, c_data=1.0, c_residual=0.005, c_ineq=0.0,
+                      lambda_opt=0.0):
+    """model_estimation_loss of the toy study (:436-511) with the callables of main_toy.py:48-79: residual
+    |x|^2 - 1, inequality relu(|x|_1 - 1), optimisation x[:, 0].  Returns (loss, ["data loss" as the reference reports it, mean|r|, mean ineq, mean opt])."""
+    tables = {k: v.to(x0.dtype) for k, v in tables.items()}
+    x = tables['alphas_bar_sqrt'][t, None] * x0 + tables['one_minus_alphas_bar_sqrt'][t, None] * noise
+    out = toy_model_forward(sd, x, t)
+    if mode == 'eps':
+        data = ((noise - out) ** 2).mean()
+        x0p = tables['sqrt_recip_alphas_cumprod'][t, None] * x - tables['sqrt_recipm1_alphas_cumprod'][t, None] * out
+    else:
+        data = (((x0 - out) ** 2).mean(dim=1) * tables['p2_loss_weight'][t]).mean()
+        x0p = out
+    data = c_data * data
+    ev = toy_ddim_x0(sd, x, t, tables, mode) if use_ddim_x0 else x0p
+    var = tables['posterior_variance_clipped'][t]
+
+    def nll(v):
+        return -torch.clamp(-0.5 * v ** 2 / var, min=-27.6310211159)
+    r = (ev ** 2).sum(dim=1) - 1.0
+    q = torch.relu(ev.abs().sum(dim=1) - 1.0)
+    o = ev[:, 0]
+    loss = data + c_residual * nll(r).mean() + c_ineq * nll(q).mean() + lambda_opt * o.mean()
+    # reference quirk (:477-478,:491): `data_loss = loss` aliases the tensor that `loss += ...` then updates in place, so
+    # the "data loss" it reports is the TOTAL loss
+    return loss, [loss.detach(), r.abs().mean(), q.mean(), o.mean()]
+
+
+# --------------------------------------------------------------------------------------------
 # A14  step glue: clip + Adam + EMA     (main.py:163-166,178-183,316 ; denoising_utils.py:163-205)
 # --------------------------------------------------------------------------------------------
 

@@ -23,6 +23,7 @@ _SIGS = {
     'pidm_posterior_step': [P, P, P, P, F, F, F, L, P],
     'pidm_scale': [P, P, P, L, P],
     'pidm_axpby_per_sample': [P, P, P, P, P, P, P, I, I, P],
+    'pidm_toy_pidm_loss': [P, P, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, I, I, P],
     'pidm_fd_stencil': [P, P, I, I, I, F, F, P],
     'pidm_darcy_residual_fwd': [P, P, P, I, I, F, I, I, P],
     'pidm_darcy_residual_bwd': [P, P, P, P, I, I, F, I, I, P],
@@ -64,7 +65,7 @@ _SIGS = {
     'pidm_block_mlps_bwd': [P, I, I, P, P, I, I, I, P],
     'pidm_head_fwd': [P, P, P, P, I, I, I, I, I, I, P],
     'pidm_head_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
-    'pidm_sumsq': [P, L, P, P],
+    'pidm_sumsq': [P, L, P, P, P],
     'pidm_adam_ema_step': [P, P, P, P, P, L, F, D, D, F, I, P, P, F, F, F, I, I, P],
     'pidm_mechanics_residual_fwd': [P, P, P, P, P, P, I, I, P],
     'pidm_mechanics_residual_bwd': [P, P, P, P, P, P, P, P, P, I, I, P],

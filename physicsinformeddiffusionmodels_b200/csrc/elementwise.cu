@@ -180,6 +180,63 @@ __global__ void scale_kernel(const float* x, const float* __restrict__ alpha, fl
         out[i] = x[i] * a;
 }
 
+// ---- toy study (main_toy.py / src/denoising_toy_utils.py:436-511): the PIDM loss algebra on [B, D] points ----------
+//   data = c_data * mean_b( w_b * mean_D (target - output)^2 ),  w_b = p2[t_b] (x0 mode) or 1 (eps mode)
+//   res  = c_res  * mean_b( min(0.5 r_b^2 / var_b, 27.631) )      (Gaussian NLL, log-likelihood clamped at -27.631, :381)
+//   ineq = c_ineq * mean_b( min(0.5 q_b^2 / var_b, 27.631) ),    opt = lambda * mean_b(o_b)
+// one CTA; sums[0..6] = data, res, ineq, opt, mean|r|, mean q, mean o; gradients w.r.t. output, r, q, o are written.
+constexpr float TOY_NLL_CLAMP = 27.6310211159f;
+__global__ void toy_loss_kernel(const float* __restrict__ target, const float* __restrict__ output,
+                                const float* __restrict__ r, const float* __restrict__ q, const float* __restrict__ o,
+                                const long long* __restrict__ t, const float* __restrict__ p2w,
+                                const float* __restrict__ pvar, float c_data, float c_res, float c_ineq, float lam,
+                                float* __restrict__ sums, float* __restrict__ g_out, float* __restrict__ g_r,
+                                float* __restrict__ g_q, float* __restrict__ g_o, int B, int D) {
+    pdl_trigger();
+    pdl_wait();
+    float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float invB = 1.f / (float)B;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float w = (p2w ? p2w[t[b]] : 1.f) * c_data * invB / (float)D;
+        for (int d = 0; d < D; ++d) {
+            const float e = output[(size_t)b * D + d] - target[(size_t)b * D + d];
+            a[0] += w * e * e;
+            g_out[(size_t)b * D + d] = 2.f * w * e;
+        }
+        const float iv = 1.f / pvar[t[b]];
+        {
+            const float rv = r[b], nll = 0.5f * rv * rv * iv;
+            const bool live = nll < TOY_NLL_CLAMP;
+            a[1] += c_res * invB * (live ? nll : TOY_NLL_CLAMP);
+            a[4] += fabsf(rv) * invB;
+            g_r[b] = live ? c_res * invB * rv * iv : 0.f;
+        }
+        if (q) {
+            const float qv = q[b], nll = 0.5f * qv * qv * iv;
+            const bool live = nll < TOY_NLL_CLAMP;
+            a[2] += c_ineq * invB * (live ? nll : TOY_NLL_CLAMP);
+            a[5] += qv * invB;
+            g_q[b] = live ? c_ineq * invB * qv * iv : 0.f;
+        }
+        if (o) {
+            a[3] += lam * invB * o[b];
+            a[6] += o[b] * invB;
+            g_o[b] = lam * invB;
+        }
+    }
+    __shared__ float red[8][7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a[k] = warp_sum(a[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 7; ++k) red[threadIdx.x >> 5][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        float s_ = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s_ += red[w][threadIdx.x];
+        sums[threadIdx.x] = s_;
+    }
+}
+
 // ---- output head: y[b,o,hw] = sum_c x[b,hw,c] w[o,c] + bias[o]; sigmoid on last channel if asked --------
 //      (final_conv.1 of the reference, unet_model.py:517 and :619-621).  O <= 4, C multiple of 8.
 template <typename T, int O>
@@ -376,6 +433,19 @@ extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float
 extern "C" int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream) {
     PIDM_CUDA(launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, alpha_dev, out, n));
     PIDM_LAUNCH_CHECK("scale");
+    return 0;
+}
+
+extern "C" int pidm_toy_pidm_loss(const float* target, const float* output, const float* residual, const float* ineq,
+                                  const float* opt, const long long* t, const float* p2_loss_weight,
+                                  const float* posterior_var_clipped, float c_data, float c_residual, float c_ineq,
+                                  float lambda_opt, float* sums7, float* grad_output, float* grad_residual, float* grad_ineq,
+                                  float* grad_opt, int B, int D, void* stream) {
+    PIDM_REQUIRE(B > 0 && D > 0, "toy_pidm_loss: bad sizes B=%d D=%d", B, D);
+    PIDM_CUDA(launch_pdl(toy_loss_kernel, dim3(1), dim3(256), (size_t)0, (cudaStream_t)stream, target, output, residual, ineq, opt,
+                         t, p2_loss_weight, posterior_var_clipped, c_data, c_residual, c_ineq, lambda_opt, sums7, grad_output,
+                         grad_residual, grad_ineq, grad_opt, B, D));
+    PIDM_LAUNCH_CHECK("toy_pidm_loss");
     return 0;
 }
 

@@ -28,8 +28,12 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+// Deterministic: every CTA writes its partial sum to workspace[1 + blockIdx.x]; the CTA that arrives last (ticket counter
+// in workspace[0]) adds the partials in index order.  The result does not depend on the arrival order, so every rank of a
+// data-parallel job computes bit-identical clip coefficients from its (bit-identical) all-reduced gradient -- with
+// atomicAdd the ranks' norms differed in the last bit and their weights drifted apart by ~1e-7 per step.
 __global__ void sumsq_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ tail, int ntail,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, float* __restrict__ workspace) {
     pdl_trigger();
     pdl_wait();
     float s = 0.f;
@@ -39,13 +43,34 @@ __global__ void sumsq_kernel(const float4* __restrict__ x, long long n4, const f
     }
     if (blockIdx.x == 0 && (int)threadIdx.x < ntail) s += tail[threadIdx.x] * tail[threadIdx.x];
     __shared__ float red[32];
+    __shared__ bool last;
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
         float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(out, v);
+        if (threadIdx.x == 0) {
+            workspace[1 + blockIdx.x] = v;
+            __threadfence();
+            unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
+            last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        float v = 0.f;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(&workspace[1 + i]);   // fixed assignment
+        v = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            *out += t;
+            *reinterpret_cast<unsigned int*>(workspace) = 0u;          // ready for the next launch / graph replay
+        }
     }
 }
 
@@ -125,14 +150,16 @@ extern "C" const char* pidm_last_error(void) { return g_last_error; }
 
 extern "C" int pidm_version(void) { return 100; }
 
-// out[0] += sum x^2   (caller zeroes out)
-extern "C" int pidm_sumsq(const float* x, long long n, float* out, void* stream) {
+// out[0] += sum x^2   (caller zeroes out).  workspace: float[PIDM_SUMSQ_WORKSPACE_FLOATS], zero-initialised ONCE by the
+// caller (element 0 is a ticket counter that every launch leaves at zero).
+extern "C" int pidm_sumsq(const float* x, long long n, float* out, float* workspace, void* stream) {
     PIDM_REQUIRE(((uintptr_t)x & 15) == 0, "sumsq: buffer must be 16-byte aligned");
+    PIDM_REQUIRE(workspace != nullptr, "sumsq: workspace of %d floats required", 1 + 148 * 8);
     long long n4 = n / 4;
     int grid = (int)((n4 + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    PIDM_CUDA(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x, n4, x + n4 * 4, (int)(n - n4 * 4), out));
+    PIDM_CUDA(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)x, n4, x + n4 * 4, (int)(n - n4 * 4), out, workspace));
     PIDM_LAUNCH_CHECK("sumsq");
     return 0;
 }

@@ -64,6 +64,7 @@ class FlatParams:
             self.ema = self.flat.clone()
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.gnorm_ws = torch.zeros(1 + 148 * 8, device=dev, dtype=torch.float32)      # pidm_sumsq partials + ticket
 
     def release(self):
         for p in self.params:
@@ -161,7 +162,7 @@ class TrainEngine:
         if self.grad_snapshot is not None:
             self.grad_snapshot.copy_(fp.grad)
         fp.gnorm_sq.zero_()
-        call('pidm_sumsq', fp.grad, fp.total, fp.gnorm_sq, stream())
+        call('pidm_sumsq', fp.grad, fp.total, fp.gnorm_sq, fp.gnorm_ws, stream())
         call('pidm_adam_ema_step', fp.flat, fp.grad, fp.exp_avg, fp.exp_avg_sq, fp.ema, fp.total, self.lr,
              self.betas[0], self.betas[1], self.eps, 0, fp.step_dev, fp.gnorm_sq, 1.0 / self.world, self.max_norm,
              self.ema_mu, self.ema_first_step, 1, stream())

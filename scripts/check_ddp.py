@@ -80,7 +80,9 @@ for use_graph in (False, True):
         flat = torch.cat([p.detach().reshape(-1) for _, p in sorted(model.named_parameters())])
         ref = flat.clone()
         dist.broadcast(ref, 0)
-        outs[bucketed] = (grads, (flat - ref).abs().max().item(), sorted(getattr(eng, '_reduced', [])))
+        dmax = torch.tensor([(flat - ref).abs().max().item()], device=dev)
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)                      # worst rank (rank 0 compares with itself)
+        outs[bucketed] = (grads, dmax.item(), sorted(getattr(eng, '_reduced', [])))
         eng.close()
         del eng, model
     worst = max(rel(outs[True][0][n], outs[False][0][n]) for n in outs[False][0] if outs[False][0][n].abs().max() > 0)

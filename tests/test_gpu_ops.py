@@ -515,7 +515,7 @@ def test_adam_ema_step(pk):
     for step in (1, 2, 3):
         O.adam_ema_step([pr], [gr], [mr], [vr], [er], step)
         nsq = torch.zeros(1, device=DEV)
-        call('pidm_sumsq', gd, n, nsq, stream())
+        call('pidm_sumsq', gd, n, nsq, torch.zeros(1 + 148 * 8, device=DEV), stream())
         call('pidm_adam_ema_step', pd, gd, md, vd, ed, n, 1e-4, 0.9, 0.999, 1e-8, step, None, nsq, 1.0, 1.0, 0.99, 1, 0,
              stream())
     assert abs(nsq.item() - (gr.double() ** 2).sum().item()) / nsq.item() < 1e-5

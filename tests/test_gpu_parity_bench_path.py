@@ -153,7 +153,7 @@ def test_device_step_counter_bias_correction(env):
             pd, gd, md, vd, ed = (a.to(DEV) for a in (p, gr, m, v, ema))
             counter = torch.full((1,), step - 1, device=DEV, dtype=torch.int32)     # steps done so far
             nsq = torch.zeros(1, device=DEV)
-            call('pidm_sumsq', gd, n, nsq, stream())
+            call('pidm_sumsq', gd, n, nsq, torch.zeros(1 + 148 * 8, device=DEV), stream())
             call('pidm_adam_ema_step', pd, gd, md, vd, ed, n, 1e-4, 0.9, 0.999, 1e-8, 0, counter, nsq, 1.0, 1.0, 0.99, 1,
                  0, stream())
             assert int(counter.item()) == step

@@ -188,3 +188,19 @@ def test_mechanics_training_loss_matches_reference(golden):
     assert rel(sdr['final_conv.1.weight'].grad, gd['grad_final_w']) < 1e-4
     assert rel(sdr['init_conv.weight'].grad, gd['grad_init_w']) < 1e-4
     assert rel(sdr['downs.1.0.block1.proj.weight'].grad, gd['grad_mid_w']) < 1e-4
+
+
+@pytest.mark.parametrize('tag,mode,ddim', [('x0_mean', 'x0', False), ('x0_sample', 'x0', True), ('eps_sample', 'eps', True)])
+def test_toy_loss_matches_reference(golden, tag, mode, ddim):
+    """configs[0] (main_toy.py): the toy study's PIDM loss through the unmodified reference module vs the oracle."""
+    gd = golden('toy.pt')
+    sd = {k[3:]: v.clone().requires_grad_(True) for k, v in gd.items() if k.startswith('sd_')}
+    tables = O.diffusion_tables(100)
+    loss, tracked = O.toy_training_loss(sd, gd['x0'], gd['t'], gd['noise'], tables, mode, ddim, 1.0, 0.005, 0.3, 0.01)
+    assert abs(loss.item() / gd[tag + '_loss'].item() - 1) < 1e-5
+    for a, b in zip(tracked, gd[tag + '_tracked'].tolist()):
+        assert abs(a.item() - b) < 1e-5 * max(1.0, abs(b))
+    loss.backward()
+    assert rel(sd['lin3.weight'].grad, gd[tag + '_grad_lin3']) < 1e-4
+    assert rel(sd['lin1.lin.weight'].grad, gd[tag + '_grad_lin1']) < 1e-4
+    assert rel(sd['lin2.embed.weight'].grad, gd[tag + '_grad_embed2']) < 1e-4
