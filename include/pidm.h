@@ -68,6 +68,11 @@ int pidm_darcy_pidm_loss(const float* x0hat, const float* model_out, const float
                          const long long* t, const float* p2_loss_weight, const float* posterior_var_clipped,
                          float c_data, float c_residual, float* sums3, float* grad_x0hat, float* grad_model_out, int B,
                          int pixels, float domain_length, int reverse_d1, int pixels_at_boundary, void* stream);
+/* CoCoGen step size (src/residuals_darcy.py:218-231): max_dr_dp[b] = largest entry (signed, as torch.max) of the Jacobian
+ * d residual / d p of sample b -- evaluated analytically from the stencil coefficients and K, the reference materialises
+ * the 12288 x 4096 Jacobian per sample with vmap(jacfwd). */
+int pidm_darcy_jacobian_max(const float* x0hat, float* max_dr_dp, int B, int pixels, float domain_length, int reverse_d1,
+                            int pixels_at_boundary, void* stream);
 
 /* ---- layout ------------------------------------------------------------------------------------------- */
 /* image_to_b_xy_c / b_xy_c_to_image (src/denoising_utils.py:36-55) fused with the dtype change + channel padding */

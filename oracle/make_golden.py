@@ -14,6 +14,7 @@ import warnings
 
 import numpy as np
 import torch
+from torch.nn.functional import pad as F_pad
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -135,6 +136,13 @@ def main():
     save('darcy_residual.pt', dict(x0_pred=x0p, residual=r.detach(), f_s=res.f_s.reshape(64, 64).clone(),
                                    cotangent=wgt, grad_x0_pred=xg.grad.clone()))
 
+    # ---- CoCoGen residual correction (8f.3), through the reference's vmap(jacfwd) Jacobian -------
+    xc = generalized_cocogen_input = x0p[:2].clone()
+    xin = xc.permute(0, 2, 3, 1).reshape(2, 4096, 2).clone()
+    x_corr, r_corr = res.residual_correction(xin)
+    save('cocogen.pt', dict(x0_pred=xc, corrected=x_corr.reshape(2, 64, 64, 2).permute(0, 3, 1, 2).contiguous().clone(),
+                            residual_corrected=r_corr.detach().clone()))
+
     # ---- full training loss + gradients, mean mode (A3) ---------------------------------------
     diff = DenoisingDiffusion(100, 'cpu')
     model.train()
@@ -226,6 +234,44 @@ def main():
         save('mechanics_residual.pt', dict(x0_pred=xm, bcs=bcs, vf=vf, residual=out['residual'].detach(),
                                            compliance=out['optimizer'].detach(), inequality=out['inequality'].detach(),
                                            KE=KE_ref, cotangent=wr, grad_x0_pred=xmg.grad.clone()))
+
+        # ---- evaluation metrics of the topology-optimisation study (8f.4; reference :276-354) -------------------------
+        # a consistent data sample: u_data solves K(rho_simp) u = f (dense assembly with the reference's own helper, fp64)
+        st = mres.stiffs
+        ge = torch.Generator().manual_seed(8)
+        i64 = torch.arange(64, dtype=torch.float32) / 63
+        Xe, Ye = torch.meshgrid(i64, i64, indexing='ij')
+        rho_simp = (0.55 + 0.45 * torch.sin(3.1 * Xe + 0.4) * torch.cos(2.3 * Ye)).clamp(0.05, 1.0)[None]
+        bce = torch.zeros(1, 4, 65, 65)
+        bce[:, 0, :, 0] = 1.
+        bce[:, 1, :, 0] = 1.
+        bce[:, 3, 30:34, 64] = -0.25
+        Kd = torch.zeros(st.neq, st.neq, dtype=torch.float64)
+        kl = (st.tot_local_stiffness.double() * rho_simp.reshape(-1).double()[:, None, None])
+        idx = st.glob_assembler_idcs
+        Kd.index_put_((idx[:, :, 0].reshape(-1), idx[:, :, 1].reshape(-1)),
+                      kl[:, st.indices_ext[:, 0], st.indices_ext[:, 1]].reshape(-1), accumulate=True)
+        bcx = st.image_to_stiffness_coord(bce[:, 0], 0) + st.image_to_stiffness_coord(bce[:, 1], 1)
+        fg = (st.image_to_stiffness_coord(bce[:, 2], 0) + st.image_to_stiffness_coord(bce[:, 3], 1))[0].double()
+        mk = bcx[0] != 0
+        Kd[mk] = 0
+        Kd[mk, mk] = 1
+        fg[mk] = 0
+        u_data = torch.linalg.solve(Kd, fg).float()[None]
+        sol = torch.stack((st.stiffness_to_image_coord(u_data, 0), st.stiffness_to_image_coord(u_data, 1)), dim=1)
+        sol = torch.cat((sol, F_pad(rho_simp, (0, 1, 0, 1)).unsqueeze(1)), dim=1)              # [1,3,65,65]
+        x_eval = torch.zeros(1, 3, 64, 64)
+        x_eval[:, :2] = 0.05 * torch.randn(1, 2, 64, 64, generator=ge)
+        x_eval[:, 2] = (rho_simp + 0.25 * torch.randn(1, 64, 64, generator=ge)).clamp(0, 1)
+        mres_e = ResidualsMechanics(model=None, pixels_per_dim=64, pixels_at_boundary=True, no_BC_folder=td + '/',
+                                    device='cpu', topopt_eval=True)
+        vfe = torch.tensor([0.5])
+        oe = mres_e.compute_residual((x_eval, bce, vfe, sol), reduce='per-batch', return_optimizer=True,
+                                     return_inequality=True, sample=True, pass_through=True)
+        save('mechanics_eval.pt', dict(x0_pred=x_eval, bcs=bce, vf=vfe, solution=sol,
+                                       rel_CE_error=oe['rel_CE_error_full_batch'].clone(),
+                                       vf_error=oe['vf_error_full_batch'].clone(),
+                                       fm_error=oe['fm_error_full_batch'].clone()))
 
         # ---- mechanics training loss through the reference's model_estimation_loss (A3 + A13, configs[2] glue) ------
         # B = 2 with all four terms switched on (c_ineq > 0 pins the [B,1] x [B] broadcast of :679,:694)

@@ -410,6 +410,28 @@ def darcy_training_loss(sd, cfg, x0, t, noise, tables, c_data=1.0, c_residual=1e
     return loss, dict(data=data, residual_abs=rabs, model_out=model_out, x0_hat=x0_hat, residual=r, x_t=xt)
 
 
+def cocogen_correction(x0_pred):
+    """ResidualsDarcy.residual_correction (residuals_darcy.py:209-240) on x0_pred [B,2,P,P]:
+    p <- p - (1e-6 / max(dr/dp)) * d(sum r^2)/dp, then the residual of the corrected field.  The reference obtains the
+    Jacobian dr/dp with vmap(jacfwd); the residual is affine in p, so here its columns are residual(e_j, K) - residual(0, K)
+    for the 4096 unit fields e_j (one batched call per sample)."""
+    B, _, P, _ = x0_pred.shape
+    x = x0_pred.detach().clone().requires_grad_(True)
+    r = darcy_residual(x)
+    dr_dp = torch.autograd.grad((r ** 2).sum(), x)[0][:, 0]
+    out = x0_pred.detach().clone()
+    for b in range(B):
+        K = x0_pred[b, 1].detach()
+        basis = torch.zeros(P * P + 1, 2, P, P, dtype=x0_pred.dtype)
+        basis[:, 1] = K
+        basis[torch.arange(P * P), 0, torch.arange(P * P) // P, torch.arange(P * P) % P] = 1.0
+        rr = darcy_residual(basis)
+        J = rr[:-1] - rr[-1:]                                    # [column j][row (pixel, channel)]
+        mx = torch.clamp(J.max(), max=1e12)
+        out[b, 0] = out[b, 0] - (1e-6 / mx) * dr_dp[b]
+    return out, darcy_residual(out)
+
+
 # --------------------------------------------------------------------------------------------
 # A11/A12  sampling   (src/denoising_utils.py:388-545, 571-574, 712-787)
 # --------------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ _SIGS = {
     'pidm_fd_stencil': [P, P, I, I, I, F, F, P],
     'pidm_darcy_residual_fwd': [P, P, P, I, I, F, I, I, P],
     'pidm_darcy_residual_bwd': [P, P, P, P, I, I, F, I, I, P],
+    'pidm_darcy_jacobian_max': [P, P, I, I, F, I, I, P],
     'pidm_darcy_pidm_loss': [P, P, P, P, P, P, P, F, F, P, P, P, I, I, F, I, I, P],
     'pidm_nchw_to_nhwc': [P, P, I, I, I, I, I, P],
     'pidm_nhwc_to_nchw': [P, P, I, I, I, I, I, P],

@@ -366,6 +366,83 @@ __global__ void __launch_bounds__(DARCY_THREADS) darcy_kernel(
     }
 }
 
+// ---- CoCoGen step size (reference residuals_darcy.py:209-240) -------------------------------------------------------
+// The reference builds, per sample, the dense Jacobian d r / d p (4096 x 3 rows, 4096 columns, via vmap(jacfwd)) only to
+// take its largest entry.  The residual is linear in p, so the Jacobian entries are stencil coefficients times fields of K:
+//   d r_eq[i] / d p[i + (dr, 0)] = -K c00_i(dr) - K_0 c0_i(dr),   d r_eq[i] / d p[i + (0, dc)] = -K c11_j(dc) - K_1 c1_j(dc)
+//   (the two centre entries add), d r_bc0 = -/+ c0_i(dr) on rows 0 / P-1, d r_bc1 = +/- s c1_j(dc) on columns 0 / P-1,
+// and every other entry is zero.  One CTA per sample evaluates them from the K plane in shared memory and reduces the
+// (signed, like torch.max) maximum.
+__device__ __forceinline__ int stencil1(int x, int off[4], float c[4]) {           // first derivative, index x of P
+    if (x == 0) { off[0] = 0; c[0] = -1.5f; off[1] = 1; c[1] = 2.f; off[2] = 2; c[2] = -0.5f; return 3; }
+    if (x == P - 1) { off[0] = 0; c[0] = 1.5f; off[1] = -1; c[1] = -2.f; off[2] = -2; c[2] = 0.5f; return 3; }
+    off[0] = -1; c[0] = -0.5f; off[1] = 1; c[1] = 0.5f; off[2] = 0; c[2] = 0.f;
+    return 3;
+}
+__device__ __forceinline__ int stencil2(int x, int off[4], float c[4]) {           // second derivative
+    if (x == 0) { off[0] = 0; c[0] = 2.f; off[1] = 1; c[1] = -5.f; off[2] = 2; c[2] = 4.f; off[3] = 3; c[3] = -1.f; return 4; }
+    if (x == P - 1) { off[0] = 0; c[0] = 2.f; off[1] = -1; c[1] = -5.f; off[2] = -2; c[2] = 4.f; off[3] = -3; c[3] = -1.f; return 4; }
+    off[0] = -1; c[0] = 1.f; off[1] = 0; c[1] = -2.f; off[2] = 1; c[2] = 1.f;
+    return 3;
+}
+// entries of one direction: e(d) = -K * c2(d) * inv_h2 - Kd * c1(d) * inv_h, merged over the offsets d in [-3, 3]
+__device__ __forceinline__ void dir_entries(int x, float kv, float kd, float inv_h, float inv_h2, float e[7], bool has[7]) {
+#pragma unroll
+    for (int d = 0; d < 7; ++d) { e[d] = 0.f; has[d] = false; }
+    int off[4]; float c[4];
+    int n = stencil2(x, off, c);
+    for (int k = 0; k < n; ++k) { e[off[k] + 3] += -kv * c[k] * inv_h2; has[off[k] + 3] = true; }
+    n = stencil1(x, off, c);
+    for (int k = 0; k < n; ++k) { e[off[k] + 3] += -kd * c[k] * inv_h; has[off[k] + 3] = true; }
+}
+__global__ void __launch_bounds__(DARCY_THREADS) darcy_jacobian_max_kernel(const float* __restrict__ x0hat,
+                                                                          float* __restrict__ out, DarcyGeom g) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sk[PP];
+    __shared__ float red[DARCY_THREADS / 32];
+    const int b = blockIdx.x;
+    const float* kp = x0hat + (size_t)b * 2 * PP + PP;
+    for (int i = threadIdx.x; i < PP; i += blockDim.x) sk[i] = kp[i];
+    __syncthreads();
+    float m = 0.f;                                       // the Jacobian is sparse: zero entries take part in the max
+    for (int q = threadIdx.x; q < PP; q += blockDim.x) {
+        const int i = q / P, j = q - i * P;
+        const float kv = sk[q];
+        const float k0 = d_row(sk, i, j, g.inv_h0), k1 = d_col(sk, i, j, g.inv_h1);
+        float er[7], ec[7];
+        bool hr[7], hc[7];
+        dir_entries(i, kv, k0, g.inv_h0, g.inv_h0sq, er, hr);
+        dir_entries(j, kv, k1, g.inv_h1, g.inv_h1sq, ec, hc);
+        m = fmaxf(m, er[3] + ec[3]);                     // both directions touch the pixel itself
+#pragma unroll
+        for (int d = 0; d < 7; ++d) {
+            if (d == 3) continue;
+            if (hr[d]) m = fmaxf(m, er[d]);
+            if (hc[d]) m = fmaxf(m, ec[d]);
+        }
+        int off[4]; float c[4];
+        if (i == 0 || i == P - 1) {                      // bc_x0 = -p_0 (row 0), +p_0 (row P-1)
+            const int n = stencil1(i, off, c);
+            const float sg = (i == 0) ? -g.inv_h0 : g.inv_h0;
+            for (int k = 0; k < n; ++k) m = fmaxf(m, sg * c[k]);
+        }
+        if (j == 0 || j == P - 1) {                      // bc_x1 = +s p_1 (column 0), -s p_1 (column P-1)
+            const int n = stencil1(j, off, c);
+            const float sg = ((j == 0) ? g.bc1_sign : -g.bc1_sign) * g.inv_h1;
+            for (int k = 0; k < n; ++k) m = fmaxf(m, sg * c[k]);
+        }
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = red[0];
+        for (int w = 1; w < DARCY_THREADS / 32; ++w) r = fmaxf(r, red[w]);
+        out[b] = r;
+    }
+}
+
 // single derivative field (StencilGradients.forward, grad_utils.py:161-175); global-memory version, forward only
 __global__ void fd_stencil_kernel(const float* __restrict__ u, float* __restrict__ out, int planes, int mode,
                                   float inv_h0, float inv_h1) {
@@ -473,4 +550,15 @@ extern "C" int pidm_darcy_pidm_loss(const float* x0hat, const float* model_out, 
     return launch_darcy<2>(x0hat, f_s, nullptr, nullptr, grad_x0hat, target, model_out, grad_model_out, t,
                            p2_loss_weight, posterior_var_clipped, c_data, c_residual, sums3, B, pixels, domain_length,
                            reverse_d1, pixels_at_boundary, (cudaStream_t)stream);
+}
+
+/* max_dr_dp[b] = largest entry of the Jacobian d residual / d p of sample b (CoCoGen step size, residuals_darcy.py:218-231) */
+extern "C" int pidm_darcy_jacobian_max(const float* x0hat, float* max_dr_dp, int B, int pixels, float domain_length,
+                                       int reverse_d1, int pixels_at_boundary, void* stream) {
+    PIDM_REQUIRE(pixels == P, "darcy kernels are built for %d x %d fields (got %d)", P, P, pixels);
+    PIDM_REQUIRE(B > 0, "empty batch");
+    PIDM_CUDA(launch_pdl(darcy_jacobian_max_kernel, dim3(B), dim3(DARCY_THREADS), (size_t)0, (cudaStream_t)stream, x0hat,
+                         max_dr_dp, make_geom(domain_length, reverse_d1, pixels_at_boundary)));
+    PIDM_LAUNCH_CHECK("darcy_jacobian_max");
+    return 0;
 }

@@ -264,8 +264,9 @@ class DenoisingDiffusion(nn.Module):
     def p_sample(self, x, conditioning_input, t, save_output=False, surpress_noise=False, use_dynamic_threshold=False,
                  residual_func=None, eval_residuals=False, return_optimizer=False, return_inequality=False,
                  residual_correction=False, correction_mode='none'):
-        if residual_correction:
-            raise NotImplementedError('CoCoGen residual correction is outside the built hot path (SURVEY.md 8f.3)')
+        assert correction_mode in ['x0', 'xt'] or not residual_correction, 'Correction mode unknown or not given.'
+        if residual_correction and residual_func.gov_eqs != 'darcy':
+            raise ValueError('CoCoGen correction is only implemented for the Darcy flow study (reference main.py:37-38).')
         if use_dynamic_threshold:
             raise NotImplementedError('dynamic thresholding is not used by the reference drivers')
         dd = self.diff_dict
@@ -284,6 +285,9 @@ class DenoisingDiffusion(nn.Module):
         model_out, residual = out_dict['model_out'], out_dict['residual']
         if len(model_out.shape) == 3:
             model_out = generalized_b_xy_c_to_image(model_out)
+        if residual_correction and correction_mode == 'x0':                   # CoCoGen on the x0 estimate (reference :433-435)
+            mo, residual = residual_func.residual_correction(generalized_image_to_b_xy_c(model_out.detach().clone()))
+            model_out = generalized_b_xy_c_to_image(mo)
         model_intermediate = model_out.detach() if save_output else None
         z = torch.randn_like(x_init)                                  # drawn even at t == 0 (reference :447)
         ht = self._host_tables
@@ -292,6 +296,9 @@ class DenoisingDiffusion(nn.Module):
             sigma = 0.
         sample = ops.posterior_step(x_init, model_out.detach(), z, float(ht['posterior_mean_coef1'][t]),
                                     float(ht['posterior_mean_coef2'][t]), sigma)
+        if residual_correction and correction_mode == 'xt':                   # CoCoGen on the new sample (reference :455-457)
+            sm, residual = residual_func.residual_correction(generalized_image_to_b_xy_c(sample))
+            sample = generalized_b_xy_c_to_image(sm).contiguous()
         if int(t) == 0 and eval_residuals:
             aux_out = {'residual': residual}
             if return_optimizer:
@@ -307,8 +314,6 @@ class DenoisingDiffusion(nn.Module):
     def p_sample_loop(self, conditioning_input, shape, save_output=False, surpress_noise=True,
                       use_dynamic_threshold=False, residual_func=None, eval_residuals=False, return_optimizer=False,
                       return_inequality=False, M_correction=0, N_correction=0, correction_mode='none'):
-        if M_correction or N_correction:
-            raise NotImplementedError('CoCoGen residual correction is outside the built hot path (SURVEY.md 8f.3)')
         dev = self.diff_dict['alphas'].device
         cur_x = torch.randn(shape, device=dev)
         # the trajectory stays on the device during the loop; ONE device->host transfer at the end
@@ -317,13 +322,25 @@ class DenoisingDiffusion(nn.Module):
         output = None
         with torch.no_grad():
             for i in reversed(range(self.n_steps)):
+                residual_correction = False
+                if i < N_correction:                                           # CoCoGen: correct during the last N steps
+                    residual_correction = True
+                    eval_residuals = True
                 output = self.p_sample(cur_x, conditioning_input, i, save_output, surpress_noise, use_dynamic_threshold,
                                        residual_func=residual_func, eval_residuals=eval_residuals,
-                                       return_optimizer=return_optimizer, return_inequality=return_inequality)
+                                       return_optimizer=return_optimizer, return_inequality=return_inequality,
+                                       residual_correction=residual_correction, correction_mode=correction_mode)
                 cur_x, interm_img = output[0]
                 dev_seq.append(cur_x)
                 if interm_img is not None:
                     dev_interm.append(interm_img)
+            for i in range(M_correction):                                      # CoCoGen: M extra corrections of x_0
+                # (the correction works in place: keep the trajectory entry recorded above intact)
+                cm, residual = residual_func.residual_correction(generalized_image_to_b_xy_c(cur_x.clone()))
+                cur_x = generalized_b_xy_c_to_image(cm).contiguous()
+                dev_seq.append(cur_x)
+                if eval_residuals and i == M_correction - 1:
+                    output[1]['residual'] = residual
         x_seq = list(torch.stack(dev_seq).cpu().unbind(0))
         interm_imgs = [torch.zeros(shape)] if save_output else []
         if dev_interm:

@@ -89,4 +89,25 @@ class ResidualsDarcy:
         raise ValueError('Unknown reduction method.')
 
     def residual_correction(self, x0_pred_in):
-        raise NotImplementedError('CoCoGen residual correction is outside the built hot path (SURVEY.md 8f.3)')
+        """CoCoGen correction step (reference :209-240): p <- p - (1e-6 / max|dr/dp|) * d(sum r^2)/dp, residual re-evaluated.
+        x0_pred_in [B, P*P, 2] is updated IN PLACE like the reference and returned with the corrected residual.
+        The reference materialises the per-sample Jacobian dr/dp (12288 x 4096, vmap(jacfwd)) to take its maximum; the
+        residual is linear in p, so the maximum is evaluated analytically from the stencil coefficients and K
+        (`pidm_darcy_jacobian_max`), and d(sum r^2)/dp is one adjoint-stencil launch (`pidm_darcy_residual_bwd`)."""
+        from ._lib import call, stream
+        assert len(x0_pred_in.shape) == 3, 'Model output must be a tensor shaped as b_xy_c.'
+        with torch.no_grad():
+            img = generalized_b_xy_c_to_image(x0_pred_in).contiguous().float()          # [B,2,P,P]
+            B, _, P, _ = img.shape
+            r = ops.darcy_residual(img, self.f_s_flat, *self.geometry)
+            gx = torch.empty_like(img)
+            call('pidm_darcy_residual_bwd', img, self.f_s_flat, (2.0 * r).contiguous(), gx, B, P, float(self.geometry[0]),
+                 int(self.geometry[1]), int(self.geometry[2]), stream())
+            mx = torch.empty(B, device=img.device, dtype=torch.float32)
+            call('pidm_darcy_jacobian_max', img, mx, B, P, float(self.geometry[0]), int(self.geometry[1]),
+                 int(self.geometry[2]), stream())
+            eps = 1.e-6 / torch.clamp(mx, max=1e12)
+            x0_pred_in[:, :, 0] -= eps.unsqueeze(1) * gx[:, 0].reshape(B, -1)
+            residual_corrected = ops.darcy_residual(generalized_b_xy_c_to_image(x0_pred_in).contiguous().float(),
+                                                    self.f_s_flat, *self.geometry)
+        return x0_pred_in, residual_corrected

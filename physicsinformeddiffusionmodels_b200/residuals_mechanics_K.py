@@ -7,8 +7,6 @@ unit-square mesh with node id = row*65 + col, dof = 2*node + d and counter-clock
 n1=(er+1,ec), n2=(er+1,ec+1), n3=(er,ec+1), n4=(er,ec); with it the element->dof map is implicit and
 `no_BC_folder` is not read.  Element stiffness: closed-form plane-stress Q4, E = 1, nu = 0.3 (the reference
 overrides the material file with exactly these values, residuals_mechanics_K.py:30-33)."""
-import warnings
-
 import torch
 import torch.nn.functional as F  # noqa: F401  (re-exported name of the reference module)
 
@@ -22,6 +20,26 @@ def q4_plane_stress_stiffness(E=1.0, nu=0.3):
     idx = [[0, 1, 2, 3, 4, 5, 6, 7], [1, 0, 7, 6, 5, 4, 3, 2], [2, 7, 0, 5, 6, 3, 4, 1], [3, 6, 5, 0, 7, 2, 1, 4],
            [4, 5, 6, 7, 0, 1, 2, 3], [5, 4, 3, 2, 1, 0, 7, 6], [6, 3, 4, 1, 2, 7, 0, 5], [7, 2, 1, 4, 3, 6, 5, 0]]
     return torch.tensor([[k[j] for j in row] for row in idx], dtype=torch.float64) * (E / (1 - nu ** 2))
+
+
+def check_floating_material(image):
+    """True if the binarised design is not exactly one connected piece of material (reference :376-380: cv2
+    connectedComponents, 8-connectivity, `labels != 2`)."""
+    import numpy as np
+    solid = np.asarray(image) > 0.5
+    try:
+        import cv2
+        n = cv2.connectedComponents(solid.astype(np.uint8))[0]
+    except ImportError:                                   # same labelling with scipy
+        from scipy import ndimage
+        n = ndimage.label(solid, structure=np.ones((3, 3)))[1] + 1
+    return n != 2
+
+
+def compute_fm(gen):
+    """floating-material flag per sample (host side, like the reference: evaluation only)"""
+    g = gen.detach().cpu().numpy()
+    return torch.tensor([int(check_floating_material(g[i])) for i in range(len(g))])
 
 
 class _Resize(torch.autograd.Function):
@@ -117,7 +135,6 @@ class ResidualsMechanics:
         self.topopt_eval = topopt_eval
         self.use_ddim_x0 = use_ddim_x0
         self.ddim_steps = ddim_steps
-        self._warned = False
 
     def compute_residual(self, input_tuple, reduce='none', return_model_out=False, return_optimizer=False,
                          return_inequality=False, sample=False, ddim_func=None, pass_through=False):
@@ -153,14 +170,8 @@ class ResidualsMechanics:
         if return_inequality:
             output['inequality'] = rho.reshape(rho.shape[0], -1).mean(1) - vf
         if self.topopt_eval and sample:
-            if not self._warned:
-                warnings.warn('topopt evaluation metrics (per-sample FEM solve, floating-material check; reference '
-                              ':276-354) are outside the built hot path and are reported as NaN')
-                self._warned = True
-            nan = torch.full((x0_pred.shape[0],), float('nan'), device=x0_pred.device)
-            output['rel_CE_error_full_batch'] = nan
-            output['vf_error_full_batch'] = nan.clone()
-            output['fm_error_full_batch'] = nan.clone()
+            with torch.no_grad():
+                output.update(self.topopt_metrics(rho.detach(), bcs, vf, input_tuple[3]))
         if reduce == 'full':
             return {k: v.mean() for k, v in output.items()}
         elif reduce == 'per-batch':
@@ -169,6 +180,71 @@ class ResidualsMechanics:
         elif reduce == 'none':
             return output
         raise ValueError('Unknown reduction method.')
+
+    # ---- evaluation metrics of the topology-optimisation study (reference :276-354) -----------------------------
+    def _apply_K(self, v, rho, masks):
+        """A v for nodal fields v [B,2,nn,nn]: (K(rho) v) on the free dofs, v itself on the Dirichlet dofs (the reference's
+        identity rows) -- one matrix-free libpidm launch; masks = bcs with the load planes zeroed."""
+        B, _, nn_, _ = v.shape
+        r = torch.empty(B, 2 * nn_ * nn_, device=v.device, dtype=torch.float32)
+        call('pidm_mechanics_residual_fwd', v, rho, masks, self.KE, r, None, B, nn_ - 1, stream())
+        return r.view(B, nn_ * nn_, 2).permute(0, 2, 1).reshape(B, 2, nn_, nn_)
+
+    def fem_solve(self, rho, bcs, tol=1e-6, max_iter=6000):
+        """u with K(rho) u = f on the free dofs, u = 0 on the Dirichlet dofs: Jacobi-preconditioned conjugate gradients on
+        the matrix-free operator, all samples at once (the reference assembles a dense 8450 x 8450 matrix per sample and
+        calls torch.linalg.solve in a Python loop, :322-325).  Returns u [B,2,nn,nn]."""
+        B, _, nn_, _ = bcs.shape
+        rho = rho.contiguous().float()
+        free = (bcs[:, :2] == 0).float()
+        f = (bcs[:, 2:4] * free).contiguous()
+        masks = torch.cat((bcs[:, :2], torch.zeros_like(bcs[:, 2:4])), dim=1).contiguous()
+        # diag K = KE[0,0] * (sum of the adjacent element densities): all eight diagonal entries of the Q4 matrix are equal
+        node_rho = F.conv2d(F.pad(rho[:, None], (1, 1, 1, 1)), torch.ones(1, 1, 2, 2, device=rho.device))
+        dinv = free / (self.KE[0, 0] * node_rho).clamp_min(1e-12)
+
+        def dot(a, b):
+            return (a.double() * b.double()).sum(dim=(1, 2, 3))
+        u = torch.zeros_like(f)
+        r = f.clone()
+        z = dinv * r
+        p = z.clone()
+        rz = dot(r, z)
+        f2 = dot(f, f).clamp_min(1e-300)
+        for it in range(max_iter):
+            Ap = self._apply_K(p.contiguous(), rho, masks) * free
+            alpha = (rz / dot(p, Ap).clamp_min(1e-300)).float().view(B, 1, 1, 1)
+            u = u + alpha * p
+            r = r - alpha * Ap
+            if it % 50 == 49 and bool(((dot(r, r) / f2).sqrt() < tol).all()):
+                break
+            z = dinv * r
+            rz_new = dot(r, z)
+            p = z + (rz_new / rz.clamp_min(1e-300)).float().view(B, 1, 1, 1) * p
+            rz = rz_new
+        return u
+
+    def topopt_metrics(self, rho, bcs, vf, solution):
+        """rel_CE_error (compliance of the binarised design, FEM-solved, vs the compliance of the data), vf_error and the
+        floating-material flag of reference :276-346, per sample."""
+        bcs = bcs.contiguous().float()
+        nn_ = bcs.shape[-1]
+        B = bcs.shape[0]
+        free = (bcs[:, :2] == 0).float()
+        f = bcs[:, 2:4] * free
+        opt_disp = solution[:, :2].contiguous().float()
+        rho_simp = solution[:, 2, :-1, :-1].contiguous().float()                 # remove the padding
+        r_data, _ = _MechResidual.apply(opt_disp, rho_simp, bcs, self.KE)
+        assert torch.isclose(r_data.abs().mean(), torch.zeros((), device=r_data.device), atol=1.e-5), \
+            'Residual of opt_disp is not zero.'
+        compliance_data = (opt_disp * f).sum(dim=(1, 2, 3))
+        rho_bin = torch.where(rho > 0.5, torch.ones_like(rho), torch.full_like(rho, 1.e-3)).contiguous()
+        u_sol = self.fem_solve(rho_bin, bcs)
+        compliance_true = (u_sol * f).sum(dim=(1, 2, 3))
+        out = {'rel_CE_error_full_batch': (compliance_true - compliance_data) / compliance_data,
+               'vf_error_full_batch': torch.abs(rho_bin.reshape(B, -1).mean(1) - vf) / vf,
+               'fm_error_full_batch': compute_fm(rho_bin)}
+        return out
 
     # ---- hooks used by DenoisingDiffusion (mechanics branch of the reference's loss / sampler) ------------------
     def training_loss(self, diffusion, input, t, c_data, c_residual, c_ineq, lambda_opt, sync_scalars=True,

@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import pytest
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -139,6 +140,41 @@ t_1, e_1 = draw_t_and_noise(100, torch.zeros(4 * world, 2, 8, 8), None)
 assert torch.equal(t_r, t_1[4 * rank:4 * rank + 4]) and torch.equal(e_r, e_1[4 * rank:4 * rank + 4])
 print('rank', rank, 'ok')
 '''
+
+
+def test_datasets_follow_the_reference_file_formats(tmp_path):
+    """reference data_utils.py:31-119: one CSV per channel with one flattened sample per row -> [C, P, P] (row-major
+    pixels); .npy samples stored channels-last, visited in NUMERIC file-name order, handed out channels-first."""
+    from physicsinformeddiffusionmodels_b200.data_utils import Dataset, Dataset_Paths
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal((5, 16)).astype(np.float32), rng.standard_normal((5, 16)).astype(np.float32)
+    np.savetxt(tmp_path / 'p.csv', a, delimiter=',')
+    np.savetxt(tmp_path / 'k.csv', b, delimiter=',')
+    ds = Dataset((str(tmp_path / 'p.csv'), str(tmp_path / 'k.csv')))
+    assert len(ds) == 5 and ds[3].shape == (2, 4, 4) and ds[3].dtype == torch.float32
+    assert np.allclose(ds[3][0].numpy(), a[3].reshape(4, 4), atol=1e-6) and np.allclose(ds[3][1].numpy(), b[3].reshape(4, 4), atol=1e-6)
+    assert Dataset((str(tmp_path / 'p.csv'), str(tmp_path / 'k.csv')), use_double=True)[0].dtype == torch.float64
+    with pytest.raises(IndexError):
+        ds[5]
+    os.makedirs(tmp_path / 'npy' / 'sub')
+    for i in (10, 2, 33):
+        np.save(tmp_path / 'npy' / ('sub' if i == 2 else '') / f'{i}.npy', np.full((6, 6, 10), float(i)) + np.arange(10))
+    dp = Dataset_Paths(str(tmp_path / 'npy'))
+    assert len(dp) == 3 and [int(dp[i][0, 0, 0]) for i in range(3)] == [2, 10, 33]
+    assert dp[1].shape == (10, 6, 6) and float(dp[1][7, 3, 3]) == 17.0
+
+
+def test_floating_material_check_matches_cv2_semantics():
+    """reference :376-380: exactly one 8-connected solid component <=> no floating material"""
+    from physicsinformeddiffusionmodels_b200.residuals_mechanics_K import check_floating_material
+    img = np.full((8, 8), 1e-3)
+    img[1:4, 1:4] = 1.0
+    assert not check_floating_material(img)
+    img[4, 4] = 1.0                                   # touches diagonally: still one piece (8-connectivity)
+    assert not check_floating_material(img)
+    img[6, 6] = 1.0                                   # detached island
+    assert check_floating_material(img)
+    assert check_floating_material(np.full((8, 8), 1e-3))     # no material at all
 
 
 def test_flat_layout_puts_unused_parameters_last():

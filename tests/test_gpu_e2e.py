@@ -149,6 +149,50 @@ def test_sample_engine_matches_reference_and_graph_replay(env, golden, monkeypat
     assert rel(xg, xe) < 1e-4, rel(xg, xe)
 
 
+def test_cocogen_correction_matches_reference(env, golden):
+    """SURVEY 8f.3 (residuals_darcy.py:209-240): the analytic Jacobian maximum + adjoint-stencil gradient against the
+    reference's vmap(jacfwd) path; the update is applied in place on the [B, P*P, 2] tensor like the reference."""
+    gd = golden('cocogen.pt')
+    _, _, res = env['build']()
+    xin = gd['x0_pred'].permute(0, 2, 3, 1).reshape(2, 4096, 2).clone().to(DEV)
+    x_corr, r_corr = res.residual_correction(xin)
+    assert x_corr is xin
+    img = xin.reshape(2, 64, 64, 2).permute(0, 3, 1, 2).cpu()
+    d_ref = gd['corrected'] - gd['x0_pred']
+    assert rel(img - gd['x0_pred'], d_ref) < 1e-3, rel(img - gd['x0_pred'], d_ref)
+    assert torch.equal(img[:, 1], gd['x0_pred'][:, 1])
+    assert rel(r_corr, gd['residual_corrected']) < 1e-5
+
+
+def test_sampling_loop_with_cocogen_corrections(env, golden, monkeypatch):
+    """p_sample_loop with N_correction / M_correction (reference :516-541): the corrected trajectory equals the plain
+    one followed by explicit corrections where the reference applies them (correction_mode 'xt')."""
+    env['ops'].set_precision('fp32')
+    gd = golden('sample_loop_6.pt')
+    model, diff, res = env['build'](n_steps=6)
+    model.eval()
+
+    def run(**kw):
+        it = iter([gd['x_T']] + list(gd['noises']))
+        monkeypatch.setattr(torch, 'randn', lambda *a, **k: next(it).to(DEV))
+        monkeypatch.setattr(torch, 'randn_like', lambda *a, **k: next(it).to(DEV))
+        out = diff.p_sample_loop(None, (1, 2, 64, 64), save_output=True, surpress_noise=True, residual_func=res,
+                                 eval_residuals=True, **kw)
+        monkeypatch.undo()
+        return out
+    (xs0, _), aux0 = run()
+    (xs1, _), aux1 = run(M_correction=2, N_correction=0, correction_mode='xt')
+    assert len(xs1) == len(xs0) + 2 and rel(xs1[6], xs0[6]) < 1e-5          # (run-to-run: fp32 atomics, ~1e-7)
+    manual = xs0[-1].clone().to(DEV)
+    for _ in range(2):
+        m, r = res.residual_correction(manual.permute(0, 2, 3, 1).reshape(1, 4096, 2).contiguous())
+        manual = m.reshape(1, 64, 64, 2).permute(0, 3, 1, 2).contiguous()
+    assert rel(xs1[-1], manual) < 1e-5 and rel(aux1['residual'], r) < 1e-4
+    (xs2, _), aux2 = run(M_correction=0, N_correction=2, correction_mode='xt')
+    assert len(xs2) == len(xs0) and rel(xs2[4], xs0[4]) < 1e-5 and rel(xs2[5], xs0[5]) > 1e-7
+    assert torch.isfinite(aux2['residual']).all()
+
+
 @pytest.mark.parametrize('B', [1, 3, 5, 16])
 def test_unet_tensor_core_path_at_odd_batch_sizes(env, B):
     """Tile / chunk / cluster planning depends on the batch size (TN samples per pixel tile, per-sample pixel chunks of

@@ -125,3 +125,25 @@ def test_mechanics_train_engine_graph_equals_eager(env):
     assert abs(lg / le - 1) < 1e-5, (lg, le)
     assert rel(gg, ge) < 1e-4, rel(gg, ge)
     assert de > 0 and dg > 0
+
+
+def test_topopt_evaluation_metrics_match_reference(env, golden):
+    """SURVEY 8f.4 (residuals_mechanics_K.py:276-354): compliance error of the binarised design (matrix-free PCG solve
+    here, dense 8450 x 8450 LU in the reference), volume-fraction error and the floating-material flag, vs the unmodified
+    reference (tests/golden/mechanics_eval.pt).  The design has 1e-3-stiffness voids: the system is ill-conditioned and
+    both solvers work in fp32, hence 5e-2 on the compliance ratio."""
+    from physicsinformeddiffusionmodels_b200.residuals_mechanics_K import ResidualsMechanics
+    gd = golden('mechanics_eval.pt')
+    res = ResidualsMechanics(model=None, pixels_per_dim=64, pixels_at_boundary=True, no_BC_folder='', device=DEV,
+                             topopt_eval=True)
+    out = res.compute_residual((gd['x0_pred'].to(DEV), gd['bcs'].to(DEV), gd['vf'].to(DEV), gd['solution'].to(DEV)),
+                               reduce='per-batch', return_optimizer=True, return_inequality=True, sample=True,
+                               pass_through=True)
+    ce, ce_ref = out['rel_CE_error_full_batch'].cpu(), gd['rel_CE_error']
+    assert torch.allclose(ce, ce_ref, rtol=5e-2), (ce, ce_ref)
+    assert torch.allclose(out['vf_error_full_batch'].cpu(), gd['vf_error'], atol=1e-6)
+    assert torch.equal(out['fm_error_full_batch'].cpu().long(), gd['fm_error'].long())
+    # the solver itself: K(rho) u = f to 1e-5 relative residual on a well-conditioned design
+    rho = gd['solution'][:, 2, :-1, :-1].contiguous().to(DEV)
+    u = res.fem_solve(rho, gd['bcs'].to(DEV))
+    assert rel(u, gd['solution'][:, :2]) < 2e-3, rel(u, gd['solution'][:, :2])

@@ -204,3 +204,15 @@ def test_toy_loss_matches_reference(golden, tag, mode, ddim):
     assert rel(sd['lin3.weight'].grad, gd[tag + '_grad_lin3']) < 1e-4
     assert rel(sd['lin1.lin.weight'].grad, gd[tag + '_grad_lin1']) < 1e-4
     assert rel(sd['lin2.embed.weight'].grad, gd[tag + '_grad_embed2']) < 1e-4
+
+
+def test_cocogen_correction_matches_reference(golden):
+    """ResidualsDarcy.residual_correction through the reference's vmap(jacfwd) Jacobian vs the oracle."""
+    gd = golden('cocogen.pt')
+    xc, rc = O.cocogen_correction(gd['x0_pred'])
+    # the correction itself is tiny (step 1e-6 / max|J|): compare the CHANGE, not the field
+    d_ref = gd['corrected'] - gd['x0_pred']
+    assert d_ref.abs().max() > 0
+    assert rel(xc - gd['x0_pred'], d_ref) < 1e-3
+    assert torch.equal(xc[:, 1], gd['x0_pred'][:, 1])                 # K is never touched
+    assert rel(rc, gd['residual_corrected']) < 1e-5
