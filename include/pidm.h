@@ -79,6 +79,9 @@ int pidm_darcy_jacobian_max(const float* x0hat, float* max_dr_dp, int B, int pix
 int pidm_nchw_to_nhwc(const float* src, void* dst, int B, int C, int HW, int Cpad, int dtype, void* stream);
 int pidm_nhwc_to_nchw(const void* src, float* dst, int B, int C, int HW, int Cpad, int dtype, void* stream);
 int pidm_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);
+/* exact (erf) GELU on activations, n % 8 == 0: emb_conv of the residual-gradient guidance branch (src/unet_model.py:520-524) */
+int pidm_gelu_fwd(const void* x, void* y, long long n, int dtype, void* stream);
+int pidm_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, void* stream);
 /* torch.cat((x, skip), dim=1) on NHWC rows and its backward (src/unet_model.py:606,612) */
 int pidm_concat_channels(const void* a, const void* b, void* out, long long rows, int Ca, int Cb, int dtype, void* stream);
 int pidm_split_channels(const void* g, void* ga, void* gb, long long rows, int Ca, int Cb, int dtype, void* stream);

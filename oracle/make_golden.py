@@ -184,6 +184,41 @@ def main():
                                       grad_final_w=named['final_conv.1.weight'].grad.clone(),
                                       grad_init_w=named['init_conv.weight'].grad.clone()))
 
+    # ---- residual-gradient guidance (8f.3: residuals_darcy.py:114-126, unet_model.py:530-540,585-603) -----------------
+    res_g = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True,
+                           device='cpu', bcs='none', domain_length=1., residual_grad_guidance=True)
+    x0g = smooth_fields(4, seed=19)
+    model.train()
+    torch.manual_seed(55)
+    loss_g, data_g, res_abs_g, _, _ = diff.model_estimation_loss(x0g, residual_func=res_g, c_data=1., c_residual=1e-3,
+                                                                 c_ineq=0., lambda_opt=0.)
+    model.zero_grad()
+    loss_g.backward()
+    torch.manual_seed(55)                                   # replay: t, eps, then the classifier-free mask (unet_model.py:69)
+    t_g = torch.randint(0, 100, size=(4,))
+    e_g = torch.randn_like(x0g)
+    mask_g = torch.zeros((4,)).float().uniform_(0, 1) < 0.1
+    mask_forced = torch.tensor([False, True, False, False])
+    # the draw above rarely drops a sample at B = 4: a second evaluation with a forced mask covers the null branch
+    import src.unet_model as _um
+    _orig_mask = _um.prob_mask_like
+    _um.prob_mask_like = lambda shape, prob, device: mask_forced.clone()
+    torch.manual_seed(55)
+    loss_f, _, _, _, _ = diff.model_estimation_loss(x0g, residual_func=res_g, c_data=1., c_residual=1e-3, c_ineq=0., lambda_opt=0.)
+    _um.prob_mask_like = _orig_mask
+    model.eval()
+    xs_in = (x0g * 0.6 + 0.3 * e_g)                        # (the reference needs autograd on here: no no_grad, :491-492)
+    og = res_g.compute_residual((((xs_in.permute(0, 2, 3, 1).reshape(4, 4096, 2)).clone(), t_g),), reduce='per-batch',
+                                return_model_out=True, sample=True)
+    og = {k: v.detach() for k, v in og.items()}
+    save('darcy_guidance.pt', dict(x0=x0g, t=t_g, noise=e_g, null_mask=mask_g, loss=loss_g.detach(),
+                                   grad_emb0=named['emb_conv.0.weight'].grad.clone(),
+                                   grad_combine=named['combine_conv.weight'].grad.clone(),
+                                   grad_final_w=named['final_conv.1.weight'].grad.clone(),
+                                   forced_mask=mask_forced, loss_forced=loss_f.detach(),
+                                   sample_in=xs_in, sample_x0=og['model_out'].clone()))
+    model.train()
+
     # ---- ancestral sampling loop (A11), 6 diffusion steps, B=1 --------------------------------
     model.eval()
     d6 = DenoisingDiffusion(6, 'cpu')

@@ -269,9 +269,11 @@ def time_embedding(sd, time, dim):
     return F.linear(e, sd['time_mlp.3.weight'], sd['time_mlp.3.bias'])
 
 
-def unet_forward(sd, cfg, x, time, return_taps=False):
-    """Unet3D.forward with F=1, cond=None, self_condition=False (unet_model.py:542-623).
-    x: [B,C,P,P] (or [B,P*P,C], converted as at :554-556).  Returns [B,out_dim,P,P]."""
+def unet_forward(sd, cfg, x, time, return_taps=False, cond=None, null_mask=None):
+    """Unet3D.forward with F=1, self_condition=False (unet_model.py:542-623).
+    x: [B,C,P,P] (or [B,P*P,C], converted as at :554-556).  Returns [B,out_dim,P,P].
+    cond [B,C,P,P] (optional, the residual gradient of the guidance branch, :585-603) with null_mask [B] bool = samples
+    whose conditioning is dropped (classifier-free guidance; the reference draws it with prob_mask_like)."""
     if x.ndim == 3:
         p = int(math.isqrt(x.shape[1]))
         x = x.reshape(x.shape[0], p, p, x.shape[2]).permute(0, 3, 1, 2)
@@ -279,6 +281,11 @@ def unet_forward(sd, cfg, x, time, return_taps=False):
     taps = OrderedDict()
     x = F.conv2d(x, sd['init_conv.weight'][:, :, 0], sd['init_conv.bias'], padding=3)
     taps['init_conv'] = x
+    if cond is not None:
+        c = torch.where(null_mask[:, None, None, None], torch.zeros_like(cond), cond)
+        e = F.conv2d(c, sd['emb_conv.0.weight'], sd['emb_conv.0.bias'])
+        e = F.conv2d(F.gelu(e), sd['emb_conv.2.weight'], sd['emb_conv.2.bias'], padding=1)
+        x = F.conv2d(torch.cat((x, e), dim=1), sd['combine_conv.weight'], sd['combine_conv.bias'])
     r = x
     t = time_embedding(sd, time, cfg['dim'])
     taps['time_emb'] = t
@@ -386,6 +393,13 @@ def darcy_residual(x0_pred, domain_length=1.0, reverse_d1=True, pixels_at_bounda
 # --------------------------------------------------------------------------------------------
 
 
+def darcy_residual_gradient(x_t):
+    """d mean|r(x_t)| / d x_t (residuals_darcy.py:117-120), [B,2,P,P]; a constant for the network (no graph kept)."""
+    with torch.enable_grad():
+        x = x_t.detach().clone().requires_grad_(True)
+        return torch.autograd.grad(darcy_residual(x).abs().mean(), x)[0]
+
+
 def pidm_loss_from_x0pred(x0, x0_pred, residual, t, tables, c_data=1.0, c_residual=1e-3):
     """loss = c_data * mean_b(p2[t] * mean_chw (x0 - x0_pred)^2) + mean(c_residual * 0.5 r^2 / var_t)."""
     B = x0.shape[0]
@@ -397,10 +411,15 @@ def pidm_loss_from_x0pred(x0, x0_pred, residual, t, tables, c_data=1.0, c_residu
     return data + res, data, residual.abs().mean()
 
 
-def darcy_training_loss(sd, cfg, x0, t, noise, tables, c_data=1.0, c_residual=1e-3, use_ddim_x0=False):
-    """model_estimation_loss for gov_eqs='darcy' with t and eps supplied (so it is RNG-free)."""
+def darcy_training_loss(sd, cfg, x0, t, noise, tables, c_data=1.0, c_residual=1e-3, use_ddim_x0=False,
+                        guidance_null_mask=None):
+    """model_estimation_loss for gov_eqs='darcy' with t and eps supplied (so it is RNG-free).
+    guidance_null_mask [B] bool: residual-gradient guidance on (residuals_darcy.py:114-126) with that classifier-free mask."""
     xt = q_sample(x0, t, noise, tables)
-    if use_ddim_x0:
+    if guidance_null_mask is not None:
+        model_out = unet_forward(sd, cfg, xt, t, cond=darcy_residual_gradient(xt), null_mask=guidance_null_mask)
+        x0_hat = model_out
+    elif use_ddim_x0:
         x0_hat, model_out = ddim_x0(sd, cfg, xt, t, tables)
     else:
         model_out = unet_forward(sd, cfg, xt, t)

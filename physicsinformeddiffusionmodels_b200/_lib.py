@@ -32,6 +32,8 @@ _SIGS = {
     'pidm_nchw_to_nhwc': [P, P, I, I, I, I, I, P],
     'pidm_nhwc_to_nchw': [P, P, I, I, I, I, I, P],
     'pidm_add': [P, P, P, L, I, P],
+    'pidm_gelu_fwd': [P, P, L, I, P],
+    'pidm_gelu_bwd': [P, P, P, L, I, P],
     'pidm_concat_channels': [P, P, P, L, I, I, I, P],
     'pidm_split_channels': [P, P, P, L, I, I, I, P],
     'pidm_pack_entry_size': [],

@@ -237,6 +237,26 @@ __global__ void toy_loss_kernel(const float* __restrict__ target, const float* _
     }
 }
 
+// ---- GELU (exact erf form, nn.GELU()) on activations: the residual-gradient embedding emb_conv of the guidance branch
+//      (reference unet_model.py:520-524).  n8 = number of 8-element vectors.
+template <typename T, bool BWD>
+__global__ void gelu_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, long long n8) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float v[8], d[8];
+        ld8(x + i * 8, v);
+        if (BWD) ld8(dy + i * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float cdf = 0.5f * (1.f + erff(v[k] * 0.70710678118654752f));
+            if (BWD) v[k] = d[k] * (cdf + v[k] * 0.3989422804014327f * expf(-0.5f * v[k] * v[k]));
+            else v[k] = v[k] * cdf;
+        }
+        st8(out + i * 8, v);
+    }
+}
+
 // ---- output head: y[b,o,hw] = sum_c x[b,hw,c] w[o,c] + bias[o]; sigmoid on last channel if asked --------
 //      (final_conv.1 of the reference, unet_model.py:517 and :619-621).  O <= 4, C multiple of 8.
 template <typename T, int O>
@@ -433,6 +453,22 @@ extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float
 extern "C" int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream) {
     PIDM_CUDA(launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, alpha_dev, out, n));
     PIDM_LAUNCH_CHECK("scale");
+    return 0;
+}
+
+extern "C" int pidm_gelu_fwd(const void* x, void* y, long long n, int dtype, void* stream) {
+    PIDM_REQUIRE(n % 8 == 0, "gelu: element count must be a multiple of 8");
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(gelu_kernel<T, false>, dim3(grid_for(n / 8, 256)), dim3(256), (size_t)0,
+                                                    (cudaStream_t)stream, (const T*)x, (const T*)nullptr, (T*)y, n / 8)));
+    PIDM_LAUNCH_CHECK("gelu_fwd");
+    return 0;
+}
+
+extern "C" int pidm_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, void* stream) {
+    PIDM_REQUIRE(n % 8 == 0, "gelu: element count must be a multiple of 8");
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(gelu_kernel<T, true>, dim3(grid_for(n / 8, 256)), dim3(256), (size_t)0,
+                                                    (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, n / 8)));
+    PIDM_LAUNCH_CHECK("gelu_bwd");
     return 0;
 }
 

@@ -188,8 +188,6 @@ class DenoisingDiffusion(nn.Module):
         self.device = device
         self.diff_dict = self.create_diff_dict()
         self.residual_grad_guidance = residual_grad_guidance
-        if residual_grad_guidance:
-            raise NotImplementedError('residual gradient guidance is outside the built hot path (SURVEY.md 8f.3)')
         self.sync_scalars = True     # False: tracked scalars are returned as device tensors (no host sync)
 
     # ---- A1: schedule tables (reference :315-370), computed once on the host in fp32, then moved -----------

@@ -111,6 +111,9 @@ class TrainEngine:
         identical on every rank and sliced to this rank's rows (seed parity with the one-process run).
         snapshot_grad: keep a copy of the (all-reduced, unclipped) flat gradient of the last step in `grad_snapshot`
         (parity tests; the Adam kernel zeroes the live buffer)."""
+        if getattr(residuals, 'residual_grad_guidance', False):
+            raise NotImplementedError('TrainEngine lays the guidance-only parameters (emb_conv, combine_conv) out as unused; '
+                                      'train residual-gradient guidance through the eager reference loop (main.py)')
         self.model, self.diffusion, self.residuals = model, diffusion, residuals
         self.lr, self.betas, self.eps, self.max_norm, self.ema_mu = lr, betas, eps, max_norm, ema_mu
         self.c_data, self.c_residual, self.c_ineq, self.lambda_opt = c_data, c_residual, c_ineq, lambda_opt

@@ -102,6 +102,26 @@ def add(a, b):
     return _Add.apply(a.contiguous(), b.contiguous())
 
 
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.empty_like(x)
+        call('pidm_gelu_fwd', x, y, x.numel(), _code(x), stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call('pidm_gelu_bwd', x, dy.contiguous(), dx, x.numel(), _code(x), stream())
+        return dx
+
+
+def gelu(x):
+    return _Gelu.apply(x.contiguous())
+
+
 class _Stash(torch.autograd.Function):
     """Identity whose backward parks the incoming gradient in `link['skip']` instead of returning it.  Used for the
     skip branch of y = f(x) + x: the backward of the FIRST op of f (a convolution dgrad or the LayerNorm backward, both

@@ -16,8 +16,6 @@ class ResidualsDarcy:
         self.input_dim = 2
         if self.periodic:
             raise NotImplementedError("bcs='periodic' is not used by the reference drivers")
-        if residual_grad_guidance:
-            raise NotImplementedError('residual gradient guidance is outside the built hot path (SURVEY.md 8f.3)')
         d0 = domain_length / (pixels_per_dim - 1) if pixels_at_boundary else domain_length / pixels_per_dim
         d1 = -d0 if reverse_d1 else d0
         self.reverse_d1 = reverse_d1
@@ -57,8 +55,32 @@ class ResidualsDarcy:
         return w.reshape(1, -1).to(self.device)
 
     # (x0_pred, model_out) for the residual / loss kernels
-    def predict_x0(self, model_input, ddim_func=None):
+    def residual_gradient(self, noisy_in):
+        """d mean|r(x_t)| / d x_t for x_t [B, P*P, 2] (reference :117-120): one residual launch, the cotangent sign(r) / N
+        and one adjoint-stencil launch.  Returned in the b_xy_c layout of the input; it is data for the network (no
+        graph is attached, as in the reference's torch.autograd.grad call)."""
+        from ._lib import call, stream
+        with torch.no_grad():
+            img = generalized_b_xy_c_to_image(noisy_in.detach()).contiguous().float()
+            B, _, P, _ = img.shape
+            r = ops.darcy_residual(img, self.f_s_flat, *self.geometry)
+            cot = (torch.sign(r) / r.numel()).contiguous()
+            gx = torch.empty_like(img)
+            call('pidm_darcy_residual_bwd', img, self.f_s_flat, cot, gx, B, P, float(self.geometry[0]), int(self.geometry[1]),
+                 int(self.geometry[2]), stream())
+        return generalized_image_to_b_xy_c(gx).contiguous()
+
+    def predict_x0(self, model_input, ddim_func=None, sample=False):
         noisy_in, time = model_input
+        if self.residual_grad_guidance:
+            assert not self.use_ddim_x0, 'Residual gradient guidance is not implemented with sample estimation for residual.'
+            dr_dx = self.residual_gradient(noisy_in)
+            if sample:
+                # NOTE (reference): "There is no mentioning of value for the guidance scale in the paper and repo"
+                out = self.model.forward_with_guidance_scale(noisy_in, time, cond=dr_dx, guidance_scale=3.)
+            else:
+                out = self.model(noisy_in, time, cond=dr_dx, null_cond_prob=0.1)
+            return out, out
         if self.use_ddim_x0:
             return ddim_func(noisy_in, time, self.model, noisy_in.shape, self.ddim_steps, 0.)
         out = self.model(noisy_in, time)
@@ -72,7 +94,7 @@ class ResidualsDarcy:
         else:
             assert len(input[0]) == 2 and isinstance(input[0], tuple), \
                 'Input[0] must be a tuple consisting of noisy signal and time.'
-            x0_pred, model_out = self.predict_x0(input[0], ddim_func)
+            x0_pred, model_out = self.predict_x0(input[0], ddim_func, sample=sample)
         assert len(x0_pred.shape) == 4, \
             'Model output must be a tensor shaped as an image (with explicit axes for the spatial dimensions).'
         residual = ops.darcy_residual(x0_pred, self.f_s_flat, *self.geometry)       # [B, P*P, 3]

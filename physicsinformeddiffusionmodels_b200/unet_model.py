@@ -251,10 +251,15 @@ class Unet3D(nn.Module):
             if not isinstance(up, nn.Identity):
                 conv(up, 4, 2, 1, kind='convT')
         plan_rb(self.final_conv[0])
+        # residual-gradient guidance branch (only executed when forward() is given cond=..., reference :585-603)
+        conv(self.emb_conv[0], 1, 1, 0, cin_pad=self._cin_pad, need_dgrad=False)
+        conv(self.emb_conv[2], 3, 1, 1)
+        conv(self.combine_conv, 1, 1, 0)
         self._mlp_table = MlpTable(mlps)
 
     def unused_parameter_names(self):
-        """Trainable parameters that Unet3D.forward never touches (they exist for state_dict parity with the reference:
+        """Trainable parameters that Unet3D.forward never touches WITHOUT residual-gradient guidance (cond=None: the
+        configuration of model.yaml; with cond=... emb_conv / combine_conv are live) (they exist for state_dict parity with the reference:
         temporal attentions, relative position bias, signal embedding, the to_q / to_k / to_v side projections, emb_conv,
         combine_conv).  They never receive a gradient -- in the reference their .grad stays None (checked against the
         reference-generated tests/golden/params_without_grad.txt) -- so a data-parallel step need not exchange them."""
@@ -325,13 +330,48 @@ class Unet3D(nn.Module):
         return self._conv(att.to_out, a, residual=ops.stash_grad(x, sk))
 
     def forward_with_guidance_scale(self, *args, **kwargs):
-        raise NotImplementedError('classifier-free residual-gradient guidance (cond=...) is outside the built hot path')
+        """classifier-free guidance at sampling time (reference :530-540): null + (cond - null) * scale"""
+        from .denoising_utils import _axpby
+        guidance_scale = kwargs.pop('guidance_scale', 3.)
+        logits = self.forward(*args, null_cond_prob=0., **kwargs)
+        if guidance_scale == 1:
+            return logits
+        null_logits = self.forward(*args, null_cond_prob=1., **kwargs)
+        B = logits.shape[0]
+        full = lambda v: torch.full((B,), float(v), device=logits.device, dtype=torch.float32)   # noqa: E731
+        return _axpby(full(guidance_scale), logits, full(1. - guidance_scale), null_logits, full(0.), null_logits)
+
+    def _cond_embedding(self, h, cond, null_cond_prob):
+        """x <- combine_conv(cat(x, emb_conv(cond))) with cond zeroed for the samples drawn as "unconditional"
+        (classifier-free guidance, reference :585-603).  cond [B, P*P, C] is data (the residual gradient): no gradient."""
+        from .denoising_utils import _axpby
+        if cond.dim() != 3:
+            raise ValueError('Input must be [BxP*PxC].')
+        B, N, C = cond.shape
+        P = int(math.isqrt(N))
+        mask = getattr(self, '_null_mask_override', None)          # tests inject the reference's draw
+        if mask is None:
+            if null_cond_prob == 1:
+                mask = torch.ones(B, device=cond.device, dtype=torch.bool)
+            elif null_cond_prob == 0:
+                mask = torch.zeros(B, device=cond.device, dtype=torch.bool)
+            else:                                                   # same draw as the reference's prob_mask_like (:63-69)
+                mask = torch.zeros(B, device=cond.device).float().uniform_(0, 1) < null_cond_prob
+        cimg = cond.detach().reshape(B, P, P, C).permute(0, 3, 1, 2).contiguous().float()
+        keep = (~mask).float().contiguous()
+        zero = torch.zeros_like(keep)
+        cimg = _axpby(keep, cimg, zero, cimg, zero, cimg)
+        e = ops.nchw_to_nhwc(cimg, self._cin_pad, ops.act_dtype())
+        e = self._conv(self.emb_conv[0], e)
+        e = ops.gelu(e)
+        e = self._conv(self.emb_conv[2], e)
+        return self._conv(self.combine_conv, ops.concat(h, e))
 
     def forward(self, x, time, x_self_cond=None, cond=None, null_cond_prob=0.):
         """x: [B, P*P, C] (as handed over by the residual operators), [B, C, P, P] or [B, C, 1, P, P].
         Returns fp32 [B, out_dim, P, P] ([B, out_dim, 1, P, P] for 5-D input), reference :542-623."""
-        if exists(cond) or exists(x_self_cond):
-            raise NotImplementedError('cond / self-conditioning inputs are outside the built hot path (SURVEY 8f.3)')
+        if exists(x_self_cond):
+            raise NotImplementedError('self-conditioning is not used by the reference drivers')
         video = False
         if x.dim() == 3:
             B, N, C = x.shape
@@ -367,6 +407,8 @@ class Unet3D(nn.Module):
         ss = ops.block_mlps(silu_t, self._mlp_table)
         torch.cuda.current_stream().wait_stream(pack_stream)
         h = self._conv(self.init_conv, h)
+        if exists(cond):
+            h = self._cond_embedding(h, cond, null_cond_prob)
         r = h
         skips = []
         for lvl, (b1, b2, la, down) in enumerate(self.downs):

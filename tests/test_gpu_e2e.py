@@ -164,6 +164,39 @@ def test_cocogen_correction_matches_reference(env, golden):
     assert rel(r_corr, gd['residual_corrected']) < 1e-5
 
 
+@pytest.mark.parametrize('mode,tol_loss,tol_grad', [('fp32', 5e-5, 2e-3), ('bf16', 3e-2, 1e-1)])
+def test_residual_gradient_guidance_matches_reference(env, golden, mode, tol_loss, tol_grad):
+    """SURVEY 8f.3 (residuals_darcy.py:114-126, unet_model.py:530-540,585-603): training loss and the gradients of the
+    guidance-only layers with the reference's classifier-free mask, the forced-null-mask variant, and sampling with
+    guidance scale 3, against the unmodified reference."""
+    env['ops'].set_precision(mode)
+    from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
+    from physicsinformeddiffusionmodels_b200.residuals_darcy import ResidualsDarcy
+    gd = golden('darcy_guidance.pt')
+    model, _, _ = env['build']()
+    diff = DenoisingDiffusion(100, DEV, residual_grad_guidance=True)
+    res = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True, device=DEV,
+                         bcs='none', domain_length=1., residual_grad_guidance=True)
+    x0, t, e = gd['x0'].to(DEV), gd['t'].to(DEV), gd['noise'].to(DEV)
+    model._null_mask_override = gd['null_mask'].to(DEV)
+    loss, _, _, _, _ = diff.darcy_loss_from_draws(x0, t, e, res, 1.0, 1e-3)
+    assert abs(loss.item() / gd['loss'].item() - 1) < tol_loss, (loss.item(), gd['loss'].item())
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, g in (('emb_conv.0.weight', 'grad_emb0'), ('combine_conv.weight', 'grad_combine'),
+                 ('final_conv.1.weight', 'grad_final_w')):
+        assert rel(named[k].grad, gd[g]) < tol_grad, (k, rel(named[k].grad, gd[g]))
+    model._null_mask_override = gd['forced_mask'].to(DEV)
+    loss_f, _, _, _, _ = diff.darcy_loss_from_draws(x0, t, e, res, 1.0, 1e-3)
+    assert abs(loss_f.item() / gd['loss_forced'].item() - 1) < tol_loss
+    model._null_mask_override = None
+    model.eval()
+    with torch.no_grad():
+        xin = gd['sample_in'].permute(0, 2, 3, 1).reshape(4, 4096, 2).to(DEV)
+        out = res.compute_residual(((xin, t),), reduce='per-batch', return_model_out=True, sample=True)
+    assert rel(out['model_out'], gd['sample_x0']) < (2e-4 if mode == 'fp32' else 5e-2)
+
+
 def test_sampling_loop_with_cocogen_corrections(env, golden, monkeypatch):
     """p_sample_loop with N_correction / M_correction (reference :516-541): the corrected trajectory equals the plain
     one followed by explicit corrections where the reference applies them (correction_mode 'xt')."""

@@ -216,3 +216,28 @@ def test_cocogen_correction_matches_reference(golden):
     assert rel(xc - gd['x0_pred'], d_ref) < 1e-3
     assert torch.equal(xc[:, 1], gd['x0_pred'][:, 1])                 # K is never touched
     assert rel(rc, gd['residual_corrected']) < 1e-5
+
+
+def test_residual_gradient_guidance_matches_reference(golden):
+    """SURVEY 8f.3: the guidance branch (cond = d mean|r(x_t)| / d x_t -> emb_conv -> combine_conv, classifier-free mask;
+    residuals_darcy.py:114-126, unet_model.py:530-540,585-603) through the unmodified reference vs the oracle: training
+    loss + gradients of the guidance-only layers, the forced-null-mask variant, and the guidance-scale-3 sample path."""
+    gd = golden('darcy_guidance.pt')
+    cfg = O.unet_config(dim=32, channels=2)
+    sd = O.make_test_state_dict(cfg, 0)
+    sdr = {k: v.clone().requires_grad_('freqs' not in k) for k, v in sd.items()}
+    tables = O.diffusion_tables(100)
+    loss, _ = O.darcy_training_loss(sdr, cfg, gd['x0'], gd['t'], gd['noise'], tables, guidance_null_mask=gd['null_mask'])
+    assert abs(loss.item() / gd['loss'].item() - 1) < 2e-5
+    loss.backward()
+    assert rel(sdr['emb_conv.0.weight'].grad, gd['grad_emb0']) < 1e-4
+    assert rel(sdr['combine_conv.weight'].grad, gd['grad_combine']) < 1e-4
+    assert rel(sdr['final_conv.1.weight'].grad, gd['grad_final_w']) < 1e-4
+    loss_f, _ = O.darcy_training_loss(sd, cfg, gd['x0'], gd['t'], gd['noise'], tables, guidance_null_mask=gd['forced_mask'])
+    assert abs(loss_f.item() / gd['loss_forced'].item() - 1) < 2e-5
+    with torch.no_grad():
+        c = O.darcy_residual_gradient(gd['sample_in'])
+        B = c.shape[0]
+        lo = O.unet_forward(sd, cfg, gd['sample_in'], gd['t'], cond=c, null_mask=torch.zeros(B, dtype=torch.bool))
+        nu = O.unet_forward(sd, cfg, gd['sample_in'], gd['t'], cond=c, null_mask=torch.ones(B, dtype=torch.bool))
+    assert rel(nu + (lo - nu) * 3.0, gd['sample_x0']) < 2e-5
