@@ -195,20 +195,27 @@ struct PackEntry {
     int flip, pad_;         // flip: tap_src = taps-1-tap (180-degree rotated kernel for stride-1 dgrad)
 };
 
+// two consecutive packed channels per thread (Cpad is even): 32-bit index arithmetic (the 64-bit divisions of the first
+// version cost more than the memory traffic: 62 us for 83 MB), one 4- or 8-byte store
 template <typename T>
 __global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
     const PackEntry e = table[blockIdx.y];
-    const long long total = (long long)e.N * e.taps * e.Cpad;
+    const unsigned total2 = (unsigned)((long long)e.N * e.taps * e.Cpad / 2);
+    const unsigned cpad = (unsigned)e.Cpad, taps = (unsigned)e.taps;
     T* dst = reinterpret_cast<T*>(e.dst);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % e.Cpad);
-        long long r = i / e.Cpad;
-        int tap = (int)(r % e.taps);
-        long long n = r / e.taps;
-        int ts = e.flip ? e.taps - 1 - tap : tap;
-        float v = (c < e.C) ? e.src[n * e.s_n + (long long)c * e.s_c + ts] : 0.f;
-        Act<T>::st(dst + i, v);
+    for (unsigned i2 = blockIdx.x * blockDim.x + threadIdx.x; i2 < total2; i2 += gridDim.x * blockDim.x) {
+        const unsigned i = 2u * i2;
+        const unsigned r = i / cpad, c = i - r * cpad;
+        const unsigned n = r / taps, tap = r - n * taps;
+        const unsigned ts = e.flip ? taps - 1u - tap : tap;
+        const float* sp = e.src + (long long)n * e.s_n + ts;
+        const float v0 = ((int)c < e.C) ? sp[(long long)c * e.s_c] : 0.f;
+        const float v1 = ((int)c + 1 < e.C) ? sp[(long long)(c + 1) * e.s_c] : 0.f;
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + i) = __floats2bfloat162_rn(v0, v1);
+        } else {
+            *reinterpret_cast<float2*>(reinterpret_cast<float*>(dst) + i) = make_float2(v0, v1);
+        }
     }
 }
 
@@ -263,7 +270,7 @@ extern "C" int pidm_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, 
 // table: device array of n_entries PackEntry records (see pidm.h for the layout).
 extern "C" int pidm_pack_weights(const void* table_dev, int n_entries, int dtype, void* stream) {
     if (n_entries <= 0) return 0;
-    dim3 grid(64, n_entries);
+    dim3 grid(32, n_entries);
     PIDM_DISPATCH_DTYPE(dtype, (pack_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                    (const PackEntry*)table_dev)));
     PIDM_LAUNCH_CHECK("pack_weights");

@@ -13,7 +13,7 @@
 // the boundary), each thread owns 4 consecutive pixels so that the interleaved [P*P,3] residual is
 // written with 128-bit coalesced stores (48 contiguous bytes per thread, 1536 per warp).
 // Loss-fused variants never materialise r: warp-shuffle + one atomic per CTA for the sums, and the
-// gradient is produced in the same pass (adjoint stencils applied to the residual plane held in smem).
+// gradient is produced in the same pass (transposed stencils gathered from five product planes in smem).
 #define PIDM_PDL_GROUP 3
 #include "common.cuh"
 #include "pidm.h"
@@ -166,62 +166,16 @@ __device__ __forceinline__ float adj_d2(F f, int x, float inv_h2) {
     return acc * inv_h2;
 }
 
-// Gradient w.r.t. (p, K) at pixel (i,j) given the cotangent planes in smem:
-//   sg  : cotangent of eq_0 (PxP),  gb0r: cotangent of bc_0 on rows {0,P-1} [2][P],  gb1c: of bc_1 on cols {0,P-1} [2][P]
-__device__ __forceinline__ void adjoint_pixel(const float* sp, const float* sk, const float* sg, const float* gb0r,
-                                              const float* gb1c, int i, int j, const DarcyGeom& g, float& dp, float& dk) {
-    // D00^T(-g K) + D11^T(-g K)
-    auto a_row = [&](int r) { return -sg[r * P + j] * sk[r * P + j]; };
-    auto a_col = [&](int c) { return -sg[i * P + c] * sk[i * P + c]; };
-    dp = adj_d2(a_row, i, g.inv_h0sq) + adj_d2(a_col, j, g.inv_h1sq);
-    // D0^T(-g K_0 + bc0 seed)
-    auto u0 = [&](int r) {
-        float v = -sg[r * P + j] * d_row(sk, r, j, g.inv_h0);
-        if (r == 0) v -= gb0r[j];
-        if (r == P - 1) v += gb0r[P + j];
-        return v;
-    };
-    dp += adj_d1(u0, i, g.inv_h0);
-    auto u1 = [&](int c) {
-        float v = -sg[i * P + c] * d_col(sk, i, c, g.inv_h1);
-        if (c == 0) v += g.bc1_sign * gb1c[i];
-        if (c == P - 1) v -= g.bc1_sign * gb1c[P + i];
-        return v;
-    };
-    dp += adj_d1(u1, j, g.inv_h1);
-    // dK = -g (p_00 + p_11) + D0^T(-g p_0) + D1^T(-g p_1)
-    auto v0 = [&](int r) { return -sg[r * P + j] * d_row(sp, r, j, g.inv_h0); };
-    auto v1 = [&](int c) { return -sg[i * P + c] * d_col(sp, i, c, g.inv_h1); };
-    dk = -sg[i * P + j] * (d2_row(sp, i, j, g.inv_h0sq) + d2_col(sp, i, j, g.inv_h1sq)) + adj_d1(v0, i, g.inv_h0) +
-         adj_d1(v1, j, g.inv_h1);
-}
-
 struct DarcySmem {
     uint64_t bar[2];
-    float red[3][DARCY_THREADS / 32];
-    float gb0r[2 * P];
-    float gb1c[2 * P];
     float planes[2][2 * PP];   // double-buffered (p, K), 16-byte aligned for the bulk copy
-    float g[PP];               // cotangent of eq_0 (backward / fused-loss only; not allocated in MODE 0)
 };
 
-// MODE 0: write residual.  MODE 1: generic backward (cotangent tensor given).  MODE 2: fused PIDM loss
-// (data MSE + residual NLL sums, |r| sum) and its gradient w.r.t. x0_hat / model_out in one pass.
-template <int MODE>
-__global__ void __launch_bounds__(DARCY_THREADS) darcy_kernel(
-    const float* __restrict__ x0hat,      // [B,2,P,P]
-    const float* __restrict__ fs,         // [P*P]
-    float* __restrict__ residual,         // MODE 0: [B,P*P,3]
-    const float* __restrict__ cot,        // MODE 1: [B,P*P,3]
-    float* __restrict__ grad_x0hat,       // MODE 1/2: [B,2,P,P]  (may be null in MODE 2 = loss only)
-    const float* __restrict__ target,     // MODE 2: x0 [B,2,P,P]
-    const float* __restrict__ model_out,  // MODE 2: [B,2,P,P] (data-loss operand; == x0hat in mean mode)
-    float* __restrict__ grad_model_out,   // MODE 2: gradient of data term (== grad_x0hat when same tensor)
-    const long long* __restrict__ t,      // MODE 2: [B]
-    const float* __restrict__ p2w,        // MODE 2: p2_loss_weight table
-    const float* __restrict__ pvar,       // MODE 2: posterior_variance_clipped table
-    float c_data, float c_res, float* __restrict__ sums,  // MODE 2: sums[0]=data loss, [1]=residual loss, [2]=mean|r|
-    int B, DarcyGeom geom) {
+// Residual, materialised: persistent CTAs, one bulk-async copy per sample, double-buffered.
+__global__ void __launch_bounds__(DARCY_THREADS) darcy_fwd_kernel(const float* __restrict__ x0hat /*[B,2,P,P]*/,
+                                                                 const float* __restrict__ fs /*[P*P]*/,
+                                                                 float* __restrict__ residual /*[B,P*P,3]*/, int B,
+                                                                 DarcyGeom geom) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DarcySmem& S = *reinterpret_cast<DarcySmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -235,12 +189,10 @@ __global__ void __launch_bounds__(DARCY_THREADS) darcy_kernel(
     pdl_wait();                 // barriers are set up; x0hat is produced by the previous kernel
     const uint32_t bytes = 2 * PP * sizeof(float);
     int n_local = 0;
-    // prologue: first sample of this CTA
     if (tid == 0 && (int)blockIdx.x < B) {
         mbar_expect_tx(&S.bar[0], bytes);
         bulk_g2s(S.planes[0], x0hat + (size_t)blockIdx.x * 2 * PP, bytes, &S.bar[0]);
     }
-    float acc_data = 0.f, acc_res = 0.f, acc_abs = 0.f;
     for (int b = blockIdx.x; b < B; b += gridDim.x, ++n_local) {
         const int buf = n_local & 1;
         const int nb = b + gridDim.x;
@@ -251,115 +203,227 @@ __global__ void __launch_bounds__(DARCY_THREADS) darcy_kernel(
         mbar_wait(&S.bar[buf], (n_local >> 1) & 1);
         const float* sp = S.planes[buf];
         const float* sk = sp + PP;
+        float* out = residual + (size_t)b * PP * 3;
+#pragma unroll 1
+        for (int q = tid; q < PP / 4; q += DARCY_THREADS) {
+            int i = q / (P / 4), j0 = (q % (P / 4)) * 4;
+            float req[4], rb0[4], rb1[4];
+            residual_quad(sp, sk, fs, i, j0, geom, req, rb0, rb1);
+            float4* o = reinterpret_cast<float4*>(out + (size_t)(i * P + j0) * 3);
+            o[0] = make_float4(req[0], rb0[0], rb1[0], req[1]);
+            o[1] = make_float4(rb0[1], rb1[1], req[2], rb0[2]);
+            o[2] = make_float4(rb1[2], req[3], rb0[3], rb1[3]);
+        }
+        __syncthreads();   // all readers of planes[buf] are done before it is refilled
+    }
+}
 
-        if (MODE == 0) {
-            float* out = residual + (size_t)b * PP * 3;
-#pragma unroll 1
-            for (int q = tid; q < PP / 4; q += DARCY_THREADS) {
-                int i = q / (P / 4), j0 = (q % (P / 4)) * 4;
-                float req[4], rb0[4], rb1[4];
-                residual_quad(sp, sk, fs, i, j0, geom, req, rb0, rb1);
-                float4* o = reinterpret_cast<float4*>(out + (size_t)(i * P + j0) * 3);
-                o[0] = make_float4(req[0], rb0[0], rb1[0], req[1]);
-                o[1] = make_float4(rb0[1], rb1[1], req[2], rb0[2]);
-                o[2] = make_float4(rb1[2], req[3], rb0[3], rb1[3]);
+// ---- backward / fused loss ------------------------------------------------------------------------------------------
+// With g = cotangent of eq_0 the adjoint is a sum of transposed 1-D stencils applied to five per-pixel products:
+//   d p = D00^T A + D11^T A + D0^T U0 + D1^T U1,     A = -g K,  U0 = -g K_0 (+ bc_x0 seeds),  U1 = -g K_1 (+ bc_x1 seeds)
+//   d K = -g (p_00 + p_11) + D0^T V0 + D1^T V1,       V0 = -g p_0,  V1 = -g p_1
+// Phase 1 evaluates the residual of a quad of pixels (all derivatives of p and K are already in registers there) and
+// leaves A, U0, U1, V0, V1 in shared-memory planes; phase 2 gathers the <= 5-point adjoint stencils from those planes.
+// (The first version re-derived K_0 / K_1 / p_0 / p_1 at every neighbour inside the gather -- ~60 shared-memory loads
+// per pixel -- and ran at 18 % of the HBM roofline; it also used 256 threads per sample, 25 us in the training step.)
+constexpr int DG_THREADS = 512;
+constexpr int DG_QUADS = PP / 4 / DG_THREADS;      // quads per thread per sample (2)
+
+struct DarcyGradSmem {
+    uint64_t bar[2];
+    float red[3][DG_THREADS / 32];
+    float planes[2][2 * PP];   // double-buffered (p, K)
+    float aux[5][PP];          // A, U0, U1, V0, V1
+};
+
+// residual of a quad + every derivative it is built from
+__device__ __forceinline__ void residual_quad_full(const float* sp, const float* sk, const float* __restrict__ fs, int i,
+                                                   int j0, const DarcyGeom& g, float req[4], float rb0[4], float rb1[4],
+                                                   float kv[4], float k0[4], float k1[4], float p0[4], float p1[4],
+                                                   float lap[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        kv[q] = sk[i * P + j];
+        p0[q] = d_row(sp, i, j, g.inv_h0);
+        k0[q] = d_row(sk, i, j, g.inv_h0);
+        p1[q] = d_col(sp, i, j, g.inv_h1);
+        k1[q] = d_col(sk, i, j, g.inv_h1);
+        lap[q] = d2_row(sp, i, j, g.inv_h0sq) + d2_col(sp, i, j, g.inv_h1sq);
+        // same association as residual_quad: -K (p_00 + p_11) - K_0 p_0 - K_1 p_1 - f_s
+        req[q] = -kv[q] * lap[q] - k0[q] * p0[q] - k1[q] * p1[q] - source_fs(i, j, fs);
+        rb0[q] = (i == 0) ? -p0[q] : ((i == P - 1) ? p0[q] : 0.f);
+        rb1[q] = (j == 0) ? g.bc1_sign * p1[q] : ((j == P - 1) ? -g.bc1_sign * p1[q] : 0.f);
+    }
+}
+
+// MODE 1: generic backward (cotangent tensor given).  MODE 2: fused PIDM loss (data MSE + residual NLL sums, |r| sum)
+// and its gradient w.r.t. x0_hat / model_out in one pass.
+template <int MODE>
+__global__ void __launch_bounds__(DG_THREADS) darcy_grad_kernel(
+    const float* __restrict__ x0hat,      // [B,2,P,P]
+    const float* __restrict__ fs,         // [P*P]
+    const float* __restrict__ cot,        // MODE 1: [B,P*P,3]
+    float* __restrict__ grad_x0hat,       // [B,2,P,P]  (may be null in MODE 2 = loss only)
+    const float* __restrict__ target,     // MODE 2: x0 [B,2,P,P]
+    const float* __restrict__ model_out,  // MODE 2: [B,2,P,P] (data-loss operand; == x0hat in mean mode)
+    float* __restrict__ grad_model_out,   // MODE 2: gradient of data term (== grad_x0hat when same tensor)
+    const long long* __restrict__ t,      // MODE 2: [B]
+    const float* __restrict__ p2w,        // MODE 2: p2_loss_weight table
+    const float* __restrict__ pvar,       // MODE 2: posterior_variance_clipped table
+    float c_data, float c_res, float* __restrict__ sums,  // MODE 2: sums[0]=data loss, [1]=residual loss, [2]=mean|r|
+    int B, DarcyGeom geom) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DarcyGradSmem& S = *reinterpret_cast<DarcyGradSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_trigger();
+    __syncthreads();
+    pdl_wait();
+    const uint32_t bytes = 2 * PP * sizeof(float);
+    int n_local = 0;
+    if (tid == 0 && (int)blockIdx.x < B) {
+        mbar_expect_tx(&S.bar[0], bytes);
+        bulk_g2s(S.planes[0], x0hat + (size_t)blockIdx.x * 2 * PP, bytes, &S.bar[0]);
+    }
+    float* sA = S.aux[0];
+    float* sU0 = S.aux[1];
+    float* sU1 = S.aux[2];
+    float* sV0 = S.aux[3];
+    float* sV1 = S.aux[4];
+    float acc_data = 0.f, acc_res = 0.f, acc_abs = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, ++n_local) {
+        const int buf = n_local & 1;
+        const int nb = b + gridDim.x;
+        if (tid == 0 && nb < B) {
+            mbar_expect_tx(&S.bar[buf ^ 1], bytes);
+            bulk_g2s(S.planes[buf ^ 1], x0hat + (size_t)nb * 2 * PP, bytes, &S.bar[buf ^ 1]);
+        }
+        mbar_wait(&S.bar[buf], (n_local >> 1) & 1);
+        const float* sp = S.planes[buf];
+        const float* sk = sp + PP;
+        float wr = 0.f, wd = 0.f;
+        if (MODE == 2) {
+            const long long tb = t[b];
+            const float nres = (float)B * (float)PP * 3.f;
+            wr = 0.5f * c_res / (pvar[tb] * nres);
+            wd = c_data * p2w[tb] / ((float)B * 2.f * (float)PP);
+        }
+        float W[DG_QUADS][4];
+        // ---- phase 1: residual (or given cotangent) -> the five product planes
+#pragma unroll
+        for (int u = 0; u < DG_QUADS; ++u) {
+            const int q = tid + u * DG_THREADS;
+            const int i = q / (P / 4), j0 = (q % (P / 4)) * 4;
+            float req[4], rb0[4], rb1[4], kv[4], k0[4], k1[4], p0[4], p1[4], lap[4];
+            residual_quad_full(sp, sk, fs, i, j0, geom, req, rb0, rb1, kv, k0, k1, p0, p1, lap);
+            float ge[4], g0[4], g1[4];
+            if (MODE == 1) {
+                const float4* c = reinterpret_cast<const float4*>(cot + ((size_t)b * PP + i * P + j0) * 3);
+                const float4 c0 = c[0], c1 = c[1], c2 = c[2];
+                ge[0] = c0.x; g0[0] = c0.y; g1[0] = c0.z; ge[1] = c0.w;
+                g0[1] = c1.x; g1[1] = c1.y; ge[2] = c1.z; g0[2] = c1.w;
+                g1[2] = c2.x; ge[3] = c2.y; g0[3] = c2.z; g1[3] = c2.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc_res += wr * (req[k] * req[k] + rb0[k] * rb0[k] + rb1[k] * rb1[k]);
+                    acc_abs += fabsf(req[k]) + fabsf(rb0[k]) + fabsf(rb1[k]);
+                    ge[k] = 2.f * wr * req[k]; g0[k] = 2.f * wr * rb0[k]; g1[k] = 2.f * wr * rb1[k];
+                }
             }
-        } else {
-            float wr = 0.f, wd = 0.f;
+            float a[4], u0[4], u1[4], v0[4], v1[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k;
+                a[k] = -ge[k] * kv[k];
+                u0[k] = -ge[k] * k0[k] + ((i == 0) ? -g0[k] : ((i == P - 1) ? g0[k] : 0.f));
+                u1[k] = -ge[k] * k1[k] + ((j == 0) ? geom.bc1_sign * g1[k] : ((j == P - 1) ? -geom.bc1_sign * g1[k] : 0.f));
+                v0[k] = -ge[k] * p0[k];
+                v1[k] = -ge[k] * p1[k];
+                W[u][k] = -ge[k] * lap[k];
+            }
+            const int o = i * P + j0;
+            *reinterpret_cast<float4*>(sA + o) = make_float4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<float4*>(sU0 + o) = make_float4(u0[0], u0[1], u0[2], u0[3]);
+            *reinterpret_cast<float4*>(sU1 + o) = make_float4(u1[0], u1[1], u1[2], u1[3]);
+            *reinterpret_cast<float4*>(sV0 + o) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+            *reinterpret_cast<float4*>(sV1 + o) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+        }
+        __syncthreads();
+        // ---- phase 2: transposed stencils on the planes (+ data-term gradient in the fused mode)
+        const bool want_grad = (grad_x0hat != nullptr);
+        const bool same = (MODE == 2) && (model_out == x0hat);
+#pragma unroll
+        for (int u = 0; u < DG_QUADS; ++u) {
+            const int q = tid + u * DG_THREADS;
+            const int i = q / (P / 4), j0 = (q % (P / 4)) * 4;
+            float dp[4] = {0, 0, 0, 0}, dk[4] = {0, 0, 0, 0};
+            if (want_grad) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = j0 + k;
+                    auto a_row = [&](int r) { return sA[r * P + j]; };
+                    auto a_col = [&](int c) { return sA[i * P + c]; };
+                    auto u0r = [&](int r) { return sU0[r * P + j]; };
+                    auto u1c = [&](int c) { return sU1[i * P + c]; };
+                    auto v0r = [&](int r) { return sV0[r * P + j]; };
+                    auto v1c = [&](int c) { return sV1[i * P + c]; };
+                    dp[k] = adj_d2(a_row, i, geom.inv_h0sq) + adj_d2(a_col, j, geom.inv_h1sq) + adj_d1(u0r, i, geom.inv_h0) +
+                            adj_d1(u1c, j, geom.inv_h1);
+                    dk[k] = W[u][k] + adj_d1(v0r, i, geom.inv_h0) + adj_d1(v1c, j, geom.inv_h1);
+                }
+            }
             if (MODE == 2) {
-                long long tb = t[b];
-                const float nres = (float)B * (float)PP * 3.f;
-                wr = 0.5f * c_res / (pvar[tb] * nres);
-                wd = c_data * p2w[tb] / ((float)B * 2.f * (float)PP);
-            }
-            // phase 1: cotangent planes into smem
-#pragma unroll 1
-            for (int q = tid; q < PP / 4; q += DARCY_THREADS) {
-                int i = q / (P / 4), j0 = (q % (P / 4)) * 4;
-                float ge[4], g0[4], g1[4];
-                if (MODE == 1) {
-                    const float4* c = reinterpret_cast<const float4*>(cot + ((size_t)b * PP + i * P + j0) * 3);
-                    float4 c0 = c[0], c1 = c[1], c2 = c[2];
-                    ge[0] = c0.x; g0[0] = c0.y; g1[0] = c0.z; ge[1] = c0.w;
-                    g0[1] = c1.x; g1[1] = c1.y; ge[2] = c1.z; g0[2] = c1.w;
-                    g1[2] = c2.x; ge[3] = c2.y; g0[3] = c2.z; g1[3] = c2.w;
+                const size_t off = (size_t)b * 2 * PP + i * P + j0;
+                const float4 tp = *reinterpret_cast<const float4*>(target + off);
+                const float4 tk = *reinterpret_cast<const float4*>(target + off + PP);
+                float4 mp, mk;
+                if (same) {
+                    mp = *reinterpret_cast<const float4*>(sp + i * P + j0);
+                    mk = *reinterpret_cast<const float4*>(sk + i * P + j0);
                 } else {
-                    float req[4], rb0[4], rb1[4];
-                    residual_quad(sp, sk, fs, i, j0, geom, req, rb0, rb1);
+                    mp = *reinterpret_cast<const float4*>(model_out + off);
+                    mk = *reinterpret_cast<const float4*>(model_out + off + PP);
+                }
+                const float ep[4] = {mp.x - tp.x, mp.y - tp.y, mp.z - tp.z, mp.w - tp.w};
+                const float ek[4] = {mk.x - tk.x, mk.y - tk.y, mk.z - tk.z, mk.w - tk.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        acc_res += wr * (req[k] * req[k] + rb0[k] * rb0[k] + rb1[k] * rb1[k]);
-                        acc_abs += fabsf(req[k]) + fabsf(rb0[k]) + fabsf(rb1[k]);
-                        ge[k] = 2.f * wr * req[k]; g0[k] = 2.f * wr * rb0[k]; g1[k] = 2.f * wr * rb1[k];
-                    }
-                }
-                *reinterpret_cast<float4*>(&S.g[i * P + j0]) = make_float4(ge[0], ge[1], ge[2], ge[3]);
-                if (i == 0 || i == P - 1) {
-                    float* d = S.gb0r + (i == 0 ? 0 : P) + j0;
-                    d[0] = g0[0]; d[1] = g0[1]; d[2] = g0[2]; d[3] = g0[3];
-                }
-                if (j0 == 0) S.gb1c[i] = g1[0];
-                if (j0 == P - 4) S.gb1c[P + i] = g1[3];
-            }
-            __syncthreads();
-            // phase 2: adjoint stencils (+ data-term gradient in the fused mode)
-            const bool want_grad = (grad_x0hat != nullptr);
-            const bool same = (MODE == 2) && (model_out == x0hat);
-#pragma unroll 1
-            for (int q = tid; q < PP / 4; q += DARCY_THREADS) {
-                int i = q / (P / 4), j0 = (q % (P / 4)) * 4;
-                float dp[4] = {0, 0, 0, 0}, dk[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 4; ++k) acc_data += wd * (ep[k] * ep[k] + ek[k] * ek[k]);
                 if (want_grad) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) adjoint_pixel(sp, sk, S.g, S.gb0r, S.gb1c, i, j0 + k, geom, dp[k], dk[k]);
-                }
-                if (MODE == 2) {
-                    const size_t off = (size_t)b * 2 * PP + i * P + j0;
-                    float4 tp = *reinterpret_cast<const float4*>(target + off);
-                    float4 tk = *reinterpret_cast<const float4*>(target + off + PP);
-                    float4 mp, mk;
                     if (same) {
-                        mp = *reinterpret_cast<const float4*>(sp + i * P + j0);
-                        mk = *reinterpret_cast<const float4*>(sk + i * P + j0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { dp[k] += 2.f * wd * ep[k]; dk[k] += 2.f * wd * ek[k]; }
                     } else {
-                        mp = *reinterpret_cast<const float4*>(model_out + off);
-                        mk = *reinterpret_cast<const float4*>(model_out + off + PP);
-                    }
-                    float ep[4] = {mp.x - tp.x, mp.y - tp.y, mp.z - tp.z, mp.w - tp.w};
-                    float ek[4] = {mk.x - tk.x, mk.y - tk.y, mk.z - tk.z, mk.w - tk.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc_data += wd * (ep[k] * ep[k] + ek[k] * ek[k]);
-                    if (want_grad) {
-                        if (same) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { dp[k] += 2.f * wd * ep[k]; dk[k] += 2.f * wd * ek[k]; }
-                        } else {
-                            *reinterpret_cast<float4*>(grad_model_out + off) =
-                                make_float4(2.f * wd * ep[0], 2.f * wd * ep[1], 2.f * wd * ep[2], 2.f * wd * ep[3]);
-                            *reinterpret_cast<float4*>(grad_model_out + off + PP) =
-                                make_float4(2.f * wd * ek[0], 2.f * wd * ek[1], 2.f * wd * ek[2], 2.f * wd * ek[3]);
-                        }
+                        *reinterpret_cast<float4*>(grad_model_out + off) =
+                            make_float4(2.f * wd * ep[0], 2.f * wd * ep[1], 2.f * wd * ep[2], 2.f * wd * ep[3]);
+                        *reinterpret_cast<float4*>(grad_model_out + off + PP) =
+                            make_float4(2.f * wd * ek[0], 2.f * wd * ek[1], 2.f * wd * ek[2], 2.f * wd * ek[3]);
                     }
                 }
-                if (want_grad) {
-                    const size_t off = (size_t)b * 2 * PP + i * P + j0;
-                    *reinterpret_cast<float4*>(grad_x0hat + off) = make_float4(dp[0], dp[1], dp[2], dp[3]);
-                    *reinterpret_cast<float4*>(grad_x0hat + off + PP) = make_float4(dk[0], dk[1], dk[2], dk[3]);
-                }
+            }
+            if (want_grad) {
+                const size_t off = (size_t)b * 2 * PP + i * P + j0;
+                *reinterpret_cast<float4*>(grad_x0hat + off) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+                *reinterpret_cast<float4*>(grad_x0hat + off + PP) = make_float4(dk[0], dk[1], dk[2], dk[3]);
             }
         }
-        __syncthreads();   // all readers of planes[buf] (and S.g) are done before it is refilled / rewritten
+        __syncthreads();   // all readers of planes[buf] and of the product planes are done before they are rewritten
     }
     if (MODE == 2) {
         acc_data = warp_sum(acc_data);
         acc_res = warp_sum(acc_res);
         acc_abs = warp_sum(acc_abs);
-        int w = tid >> 5;
+        const int w = tid >> 5;
         if ((tid & 31) == 0) { S.red[0][w] = acc_data; S.red[1][w] = acc_res; S.red[2][w] = acc_abs; }
         __syncthreads();
         if (tid < 3) {
             float s = 0.f;
-            for (int k = 0; k < DARCY_THREADS / 32; ++k) s += S.red[tid][k];
+            for (int k = 0; k < DG_THREADS / 32; ++k) s += S.red[tid][k];
             if (tid == 2) s /= ((float)B * (float)PP * 3.f);
             atomicAdd(&sums[tid], s);
         }
@@ -483,32 +547,59 @@ static DarcyGeom make_geom(float domain_length, int reverse_d1, int pixels_at_bo
     return g;
 }
 
-template <int MODE>
-static int launch_darcy(const float* x0hat, const float* fs, float* residual, const float* cot, float* grad_x0hat,
-                        const float* target, const float* model_out, float* grad_model_out, const long long* t,
-                        const float* p2w, const float* pvar, float c_data, float c_res, float* sums, int B, int pixels,
-                        float domain_length, int reverse_d1, int pixels_at_boundary, cudaStream_t stream) {
-    PIDM_REQUIRE(pixels == P, "darcy kernels are built for %d x %d fields (got %d)", P, P, pixels);
-    PIDM_REQUIRE(B > 0, "empty batch");
-    static int sm_count = 0;
-    if (!sm_count) {
+static int darcy_sm_count(int& sm_count) {
+    static int cached = 0;
+    if (!cached) {
         int dev = 0;
         PIDM_CUDA(cudaGetDevice(&dev));
-        PIDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        PIDM_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
     }
-    const size_t smem = (MODE == 0) ? offsetof(DarcySmem, g) : sizeof(DarcySmem);
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[MODE]) {
-        PIDM_CUDA(cudaFuncSetAttribute(darcy_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[MODE] = true;
+    sm_count = cached;
+    return 0;
+}
+
+static int launch_darcy_fwd(const float* x0hat, const float* fs, float* residual, int B, int pixels, float domain_length,
+                            int reverse_d1, int pixels_at_boundary, cudaStream_t stream) {
+    PIDM_REQUIRE(pixels == P, "darcy kernels are built for %d x %d fields (got %d)", P, P, pixels);
+    PIDM_REQUIRE(B > 0, "empty batch");
+    int sm_count;
+    if (int e = darcy_sm_count(sm_count)) return e;
+    const size_t smem = sizeof(DarcySmem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PIDM_CUDA(cudaFuncSetAttribute(darcy_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
     }
     const int ctas_per_sm = (int)(220 * 1024 / smem);        // smem-limited residency
     int grid = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     if (grid > B) grid = B;
-    PIDM_CUDA(launch_pdl(darcy_kernel<MODE>, dim3(grid), dim3(DARCY_THREADS), (size_t)(smem), stream, x0hat, fs, residual, cot, grad_x0hat, target, model_out,
-                                                             grad_model_out, t, p2w, pvar, c_data, c_res, sums, B,
-                                                             make_geom(domain_length, reverse_d1, pixels_at_boundary)));
-    PIDM_LAUNCH_CHECK("darcy_kernel");
+    PIDM_CUDA(launch_pdl(darcy_fwd_kernel, dim3(grid), dim3(DARCY_THREADS), (size_t)(smem), stream, x0hat, fs, residual, B,
+                         make_geom(domain_length, reverse_d1, pixels_at_boundary)));
+    PIDM_LAUNCH_CHECK("darcy_fwd_kernel");
+    return 0;
+}
+
+template <int MODE>
+static int launch_darcy_grad(const float* x0hat, const float* fs, const float* cot, float* grad_x0hat, const float* target,
+                             const float* model_out, float* grad_model_out, const long long* t, const float* p2w,
+                             const float* pvar, float c_data, float c_res, float* sums, int B, int pixels,
+                             float domain_length, int reverse_d1, int pixels_at_boundary, cudaStream_t stream) {
+    PIDM_REQUIRE(pixels == P, "darcy kernels are built for %d x %d fields (got %d)", P, P, pixels);
+    PIDM_REQUIRE(B > 0, "empty batch");
+    int sm_count;
+    if (int e = darcy_sm_count(sm_count)) return e;
+    const size_t smem = sizeof(DarcyGradSmem);
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[MODE]) {
+        PIDM_CUDA(cudaFuncSetAttribute(darcy_grad_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[MODE] = true;
+    }
+    int grid = sm_count;                                      // 145 KB of shared memory: one CTA of 512 threads per SM
+    if (grid > B) grid = B;
+    PIDM_CUDA(launch_pdl(darcy_grad_kernel<MODE>, dim3(grid), dim3(DG_THREADS), (size_t)(smem), stream, x0hat, fs, cot,
+                         grad_x0hat, target, model_out, grad_model_out, t, p2w, pvar, c_data, c_res, sums, B,
+                         make_geom(domain_length, reverse_d1, pixels_at_boundary)));
+    PIDM_LAUNCH_CHECK("darcy_grad_kernel");
     return 0;
 }
 
@@ -528,17 +619,16 @@ extern "C" int pidm_fd_stencil(const float* u, float* out, int planes, int pixel
 
 extern "C" int pidm_darcy_residual_fwd(const float* x0hat, const float* f_s, float* residual, int B, int pixels,
                                        float domain_length, int reverse_d1, int pixels_at_boundary, void* stream) {
-    return launch_darcy<0>(x0hat, f_s, residual, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                           0.f, 0.f, nullptr, B, pixels, domain_length, reverse_d1, pixels_at_boundary,
-                           (cudaStream_t)stream);
+    return launch_darcy_fwd(x0hat, f_s, residual, B, pixels, domain_length, reverse_d1, pixels_at_boundary,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int pidm_darcy_residual_bwd(const float* x0hat, const float* f_s, const float* grad_residual,
                                        float* grad_x0hat, int B, int pixels, float domain_length, int reverse_d1,
                                        int pixels_at_boundary, void* stream) {
-    return launch_darcy<1>(x0hat, f_s, nullptr, grad_residual, grad_x0hat, nullptr, nullptr, nullptr, nullptr, nullptr,
-                           nullptr, 0.f, 0.f, nullptr, B, pixels, domain_length, reverse_d1, pixels_at_boundary,
-                           (cudaStream_t)stream);
+    return launch_darcy_grad<1>(x0hat, f_s, grad_residual, grad_x0hat, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, 0.f, 0.f, nullptr, B, pixels, domain_length, reverse_d1, pixels_at_boundary,
+                                (cudaStream_t)stream);
 }
 
 extern "C" int pidm_darcy_pidm_loss(const float* x0hat, const float* model_out, const float* target, const float* f_s,
@@ -547,9 +637,9 @@ extern "C" int pidm_darcy_pidm_loss(const float* x0hat, const float* model_out, 
                                     float* grad_model_out, int B, int pixels, float domain_length, int reverse_d1,
                                     int pixels_at_boundary, void* stream) {
     PIDM_CUDA(cudaMemsetAsync(sums3, 0, 3 * sizeof(float), (cudaStream_t)stream));
-    return launch_darcy<2>(x0hat, f_s, nullptr, nullptr, grad_x0hat, target, model_out, grad_model_out, t,
-                           p2_loss_weight, posterior_var_clipped, c_data, c_residual, sums3, B, pixels, domain_length,
-                           reverse_d1, pixels_at_boundary, (cudaStream_t)stream);
+    return launch_darcy_grad<2>(x0hat, f_s, nullptr, grad_x0hat, target, model_out, grad_model_out, t, p2_loss_weight,
+                                posterior_var_clipped, c_data, c_residual, sums3, B, pixels, domain_length, reverse_d1,
+                                pixels_at_boundary, (cudaStream_t)stream);
 }
 
 /* max_dr_dp[b] = largest entry of the Jacobian d residual / d p of sample b (CoCoGen step size, residuals_darcy.py:218-231) */

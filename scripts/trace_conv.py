@@ -52,6 +52,7 @@ print('epilogue chunk 0: [acc_full ok -> ld done, -> stored, -> stats done]')
 for lt in range(9):
     a = t[2048 + lt * 4 + 1]; row = t[3072 + lt * 4: 3072 + lt * 4 + 3]
     if row[0]: print(lt, [row[0] - a, row[1] - row[0], row[2] - row[1]])
+print('split-K: [phase A done, exchange barrier passed, phase B done]', [v - t0 for v in t[3072:3075] if v])
 print('producer tile starts:', [t[i * 2] - t0 for i in range(9) if t[i * 2]])
 print('MMA K-steps: [full-wait done, issued] relative; producer issue time')
 for git in range(40):
