@@ -128,6 +128,10 @@ struct TcParams {
     // distributed shared memory (red_off = byte offset of the exchange buffer behind the operand ring) and CTA r
     // finishes columns [r * BN / splits, (r + 1) * BN / splits) of the tile.  One tile per cluster, no persistence.
     int splits, ksteps_split, red_off, ring_bytes;
+    // A operand by cp.async instead of TMA (a_cpasync = 1, see tc_issue_a_tile): raw input tensor + its spatial size and
+    // the power-of-two tile dimensions as shifts
+    const __nv_bfloat16* x;
+    int Hin, Win, a_cpasync, log2_tw, log2_th, a_rows;
     int m_tiles, n_tiles, n_classes;   // persistent tile walk: tile = (cls * n_tiles + nt) * m_tiles + mt
     const float* bias;
     const __nv_bfloat16* residual;
@@ -205,6 +209,33 @@ __device__ __forceinline__ void st_remote_f4(uint32_t local_addr, uint32_t rank,
     uint32_t raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// A-operand tile of one K-step written by a whole producer warp with 16-byte cp.async (zero fill outside the image),
+// in the canonical K-major swizzled layout the UMMA descriptors expect (row r = pixel, 16-byte chunk c16 stored at
+// chunk position c16 ^ swizzle(r); 128B swizzle: r & 7, 64B swizzle: (r >> 1) & 3 -- stage buffers are 1024-byte aligned).
+// (Experiment, off by default: the clock64 timeline shows a K-step cadence of ~427 cycles whatever the tile width while the
+// four MMAs of a K-step issue in ~190, which pointed at the copy engine; this LSU path turned out 2-4x slower, see tc_run.)  Pixel row r of the box <-> (tn, thb, tw): tw = r % TW, thb = (r / TW) % THb, tn = ...;
+// input pixel (b0 + tn, h_base + thb * s, w_base + tw * s).
+template <int BK>
+__device__ __forceinline__ void tc_issue_a_tile(unsigned char* a_dst, const TcParams& p, int b0, int h_base, int w_base,
+                                                int kcol, int lane) {
+    constexpr int CPR = BK / 8;                    // 16-byte chunks per pixel row
+    constexpr int RPP = 32 / CPR;                  // rows per warp pass
+    const int c16 = lane % CPR;
+    const int tw_mask = p.TW - 1, th_mask = p.TH - 1;
+    const uint32_t dst0 = tc_smem_u32(a_dst);
+    for (int r = lane / CPR; r < p.a_rows; r += RPP) {
+        const int tw = r & tw_mask, t = r >> p.log2_tw;
+        const int thb = p.rg ? t : (t & th_mask), tn = p.rg ? 0 : (t >> p.log2_th);
+        const int h = h_base + thb * p.in_stride, w = w_base + tw * p.in_stride, b = b0 + tn;
+        const bool ok = (unsigned)h < (unsigned)p.Hin && (unsigned)w < (unsigned)p.Win && b < p.B;
+        const __nv_bfloat16* src = ok ? p.x + ((((size_t)b * p.Hin + h) * p.Win + w) * p.Cin + kcol + c16 * 8) : p.x;
+        const int swz = (BK == 64) ? (r & 7) : ((r >> 1) & 3);
+        const uint32_t dst = dst0 + (uint32_t)(r * (BK * 2) + ((c16 ^ swz) << 4));
+        const int nbytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    }
 }
 
 // One epilogue pass over CH accumulator columns held by a warp (one pixel row per lane): + bias, + residual (read coalesced,
@@ -337,7 +368,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < n_stages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+        // full[s]: one arrival (the expect_tx of the issuing thread) when both operands come by TMA; with the cp.async A
+        // producer: 32 lane arrivals (cp.async.mbarrier.arrive.noinc) + the expect_tx arrival for the TMA weights (if any)
+        const int full_count = p.a_cpasync ? 32 + (p.resident ? 0 : 1) : 1;
+        for (int s = 0; s < n_stages; ++s) { tc_mbar_init(&full[s], full_count); tc_mbar_init(&empty[s], 1); }
         for (int s = 0; s < Cfg::ACC_STAGES; ++s) { tc_mbar_init(&acc_full[s], 1); tc_mbar_init(&acc_empty[s], 128); }
         tc_mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -361,8 +395,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // (a single thread can only issue a K-step every ~600 cycles -- wait + expect_tx + 2 TMA -- which starved the
         //  tensor pipe on the small-channel layers; the three issue streams are independent)
         const uint32_t pidx = (warp == 0) ? 0u : (uint32_t)(warp - 1);
-        if (elect_one()) {
-            if (p.resident && pidx == 0) {
+        const bool lead = p.a_cpasync ? (lane == 0) : elect_one();     // the lane that talks to the copy engine
+        if (lead || p.a_cpasync) {
+            if (p.resident && pidx == 0 && lead) {
                 // all K tiles of the (single) n-tile: [tap][kc] boxes of BN x BK
                 const int n_k = p.KH * p.KW * kc_per_tap;
                 tc_mbar_expect_tx(wfull, (uint32_t)(n_k * Cfg::B_BYTES));
@@ -384,7 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int tb = t2 / p.tiles_h, th_idx = t2 - tb * p.tiles_h;
                 const int b0 = tb * p.TN, hh0 = p.in_stride * th_idx * p.TH, ww0 = p.in_stride * tw_idx * p.TW;
                 const int n_groups = (p.mode == 0) ? groups_m0 : cl.n_taps;
-                if (tracing && pidx == 0 && lt < 500) p.trace[lt * 2] = clock64();
+                if (tracing && lead && pidx == 0 && lt < 500) p.trace[lt * 2] = clock64();
                 int r = 0, q = 0;                              // mode 0, plain: tap (r, q) walked incrementally
                 int ks = 0;                                    // K-step index inside the tile (split-K range check)
                 for (int g = 0; g < n_groups; ++g) {
@@ -401,14 +436,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         if (ks < k_lo || ks >= k_hi) continue;           // another CTA of the cluster owns this K-step
                         if (turn == pidx) {
                             tc_mbar_wait(&empty[st], ph ^ 1);
-                            if (tracing && git < 1000) p.trace[6144 + git] = clock64();
-                            tc_mbar_expect_tx(&full[st], (uint32_t)p.stage_bytes);
-                            tma_load_4d(a_dst, &map_x, &full[st], kc * BK, ww0 + dw, hh0 + dh, b0);
-                            if (!p.resident) {
-                                unsigned char* b_dst = a_dst + p.a_bytes;
-                                int kj = kcol;
-                                for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
-                                    tma_load_2d(b_dst, &map_w, &full[st], kj, n0);   // row-group mode: tap (r = j, q = g)
+                            if (tracing && lead && git < 1000) p.trace[6144 + git] = clock64();
+                            if (p.a_cpasync) {
+                                if (lead && !p.resident) {
+                                    tc_mbar_expect_tx(&full[st], (uint32_t)(p.stage_bytes - p.a_bytes));
+                                    unsigned char* b_dst = a_dst + p.a_bytes;
+                                    int kj = kcol;
+                                    for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
+                                        tma_load_2d(b_dst, &map_w, &full[st], kj, n0);
+                                }
+                                tc_issue_a_tile<BK>(a_dst, p, b0, hh0 + dh, ww0 + dw, kc * BK, lane);
+                                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&full[st]))
+                                             : "memory");
+                            } else {
+                                tc_mbar_expect_tx(&full[st], (uint32_t)p.stage_bytes);
+                                tma_load_4d(a_dst, &map_x, &full[st], kc * BK, ww0 + dw, hh0 + dh, b0);
+                                if (!p.resident) {
+                                    unsigned char* b_dst = a_dst + p.a_bytes;
+                                    int kj = kcol;
+                                    for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
+                                        tma_load_2d(b_dst, &map_w, &full[st], kj, n0);   // row-group mode: tap (r = j, q = g)
+                                }
                             }
                         }
                         ++git;
@@ -462,6 +510,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 uint32_t res_lo = wres_lo;                           // resident weights: tile (it) of kernel row 0
                 for (int it = 0; it < n_iters; ++it, res_lo += b_tile_lo) {
                     tc_mbar_wait(&full[st], ph);
+                    // cp.async writes go through the generic proxy, the tensor core reads through the async proxy
+                    if (p.a_cpasync) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (tracing && git < 1000) p.trace[4096 + git * 2] = clock64();
                     uint32_t aj = a_lo;
@@ -869,6 +919,18 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
     }
     p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = (__nv_bfloat16*)y;
+    {   // A operand through the LSU (cp.async) instead of TMA: OPT-IN (PIDM_TC_CPASYNC=1).  Built because the K-step cadence
+        // of the main loop (~427 cycles) looked like a copy-engine limit; measured (profiles/r02_conv_splitk_trace.txt): the
+        // three producer warps need ~2400 cycles per K-step for the 1024 predicated, swizzled 16-byte cp.async of a tile
+        // (address arithmetic + LSU issue), 8x8x256: 12.8 -> 49 us, 64x64x32: 12.0 -> 23.3 us.  TMA stays the default.
+        static int want = -1;
+        if (want < 0) { const char* ev = getenv("PIDM_TC_CPASYNC"); want = ev ? atoi(ev) : 0; }
+        auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return ((1 << l) == v) ? l : -1; };
+        p.x = (const __nv_bfloat16*)x; p.Hin = H; p.Win = W;
+        p.log2_tw = ilog2(pl.TW); p.log2_th = ilog2(pl.TH);
+        p.a_rows = (pl.TH + (pl.rg ? KH - 1 : 0)) * pl.TW * pl.TN;
+        p.a_cpasync = (want && p.log2_tw >= 0 && p.log2_th >= 0) ? 1 : 0;
+    }
     p.trace = g_tc_trace;
     p.gn_sums = gn_sums; p.gn_groups = gn_groups; p.gn_cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     if (gn_sums) {

@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 PT="python -m pytest -q -p no:cacheprovider --timeout 120 --timeout-method=thread"
-timeout 600 $PT tests/test_gpu_ops.py -m gpu -k "conv or wgrad" > gpurun_out/jc_pytest1.log 2>&1; echo "conv tests rc=$?"; tail -4 gpurun_out/jc_pytest1.log
-timeout 600 $PT tests/test_gpu_parity_bench_path.py tests/test_gpu_e2e.py -m gpu > gpurun_out/jc_pytest2.log 2>&1; echo "parity tests rc=$?"; tail -6 gpurun_out/jc_pytest2.log
-for SP in 1 0; do
-  PIDM_TC_SPLIT=$SP timeout 200 python scripts/layer_times.py conv2d_tc_general > gpurun_out/jc_lt_split$SP.txt 2>&1
-  echo "== split=$SP"; head -2 gpurun_out/jc_lt_split$SP.txt; grep " 8, 8, \| 16, 16, 128, 8" gpurun_out/jc_lt_split$SP.txt | head -14
+timeout 300 $PT tests/test_gpu_ops.py -m gpu -k "conv or wgrad" -x > gpurun_out/jc_pytest1.log 2>&1; echo "conv tests rc=$?"; tail -12 gpurun_out/jc_pytest1.log | cut -c1-200
+for CP in 1 0; do
+  echo "== cpasync=$CP"; PIDM_TC_CPASYNC=$CP timeout 120 python scripts/trace_conv.py 32 8 256 256 3 2>&1 | sed -n 1,9p
+  PIDM_TC_CPASYNC=$CP timeout 120 python scripts/trace_conv.py 32 64 32 32 3 x 2>&1 | head -1
 done
