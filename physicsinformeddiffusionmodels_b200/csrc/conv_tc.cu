@@ -27,8 +27,15 @@
 //   warp 2       also allocates TMEM (2 x BN columns: the epilogue of tile i overlaps the mainloop of tile i+1)
 //   warps 4-7    epilogue: tcgen05.ld -> +bias +residual -> GroupNorm sum / sum-of-squares (optional) -> bf16 ->
 //                XOR-swizzled smem transpose -> 64/128-byte coalesced row-segment stores
-// What bounds it (clock64 traces, scripts/trace_conv.py): at Cin = 32 the TMA engine delivers one 64-byte box row per
-// ~4 cycles; an M128 x N32 x K16 MMA takes ~61 cycles (A-operand fetch) whatever N <= 64; a launch costs >= 5.5 us.
+// What bounds it (clock64 traces, scripts/trace_conv.py; profiles/r02_conv_splitk_trace.txt): the K-step cadence of the
+// main loop is set by the copy engine, not by the tensor pipe -- ~427 cycles per (128-row im2col box + weight box) at the
+// 8x8 level whatever the n-tile width, ~770 cycles per 144-row halo box of 64-byte rows at Cin = 32 (5.3 cycles per row) --
+// while the four to six MMAs of a K-step issue in 190-290 cycles; a launch costs >= 4.3 us (1x1 conv at 8x8).
+// Two alternatives were built and measured in round 2 and are NOT in this file (git history: c60b6e5, c86e22a): split-K
+// over a thread-block cluster with a DSMEM exchange of the partial accumulators (main loop 3.3x shorter, but the cluster
+// barrier absorbs ~6.5 k cycles of CTA start skew and the exchange 5-12 k: 11.9 -> 12.8 us per 8x8x256 layer) and
+// cp.async producer warps for the A operand instead of TMA (2100-2400 cycles per K-step: 12.8 -> 44-49 us).  Carrying
+// them as opt-in paths cost the default path 3 % (register pressure in the issue loops), so they were removed.
 #include "common.cuh"
 #include "pidm.h"
 #include <cuda.h>
@@ -123,15 +130,6 @@ struct TcParams {
     //   nb      B (weight) tiles consumed per K-step (KH in row-group mode, else 1)
     //   resident = 1: all weights of the CTA's (single) n-tile are loaded once into shared memory
     int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes;
-    // split-K inside a thread-block cluster (deep, low-resolution layers; see tc_plan): the `splits` CTAs of a cluster own
-    // the same output tile and `ksteps_split` consecutive K-steps each; partial accumulators are exchanged through
-    // distributed shared memory (red_off = byte offset of the exchange buffer behind the operand ring) and CTA r
-    // finishes columns [r * BN / splits, (r + 1) * BN / splits) of the tile.  One tile per cluster, no persistence.
-    int splits, ksteps_split, red_off, ring_bytes;
-    // A operand by cp.async instead of TMA (a_cpasync = 1, see tc_issue_a_tile): raw input tensor + its spatial size and
-    // the power-of-two tile dimensions as shifts
-    const __nv_bfloat16* x;
-    int Hin, Win, a_cpasync, log2_tw, log2_th, a_rows;
     int m_tiles, n_tiles, n_classes;   // persistent tile walk: tile = (cls * n_tiles + nt) * m_tiles + mt
     const float* bias;
     const __nv_bfloat16* residual;
@@ -196,122 +194,6 @@ __device__ __forceinline__ void gn_stats_chunk(const float* f, float* sums_b, in
     if ((lane & (DUP - 1)) == 0) atomicAdd(sums_b + first_group * 2 + idx, total);
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_remote_f4(uint32_t local_addr, uint32_t rank, float a, float b, float c, float d) {
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// A-operand tile of one K-step written by a whole producer warp with 16-byte cp.async (zero fill outside the image),
-// in the canonical K-major swizzled layout the UMMA descriptors expect (row r = pixel, 16-byte chunk c16 stored at
-// chunk position c16 ^ swizzle(r); 128B swizzle: r & 7, 64B swizzle: (r >> 1) & 3 -- stage buffers are 1024-byte aligned).
-// (Experiment, off by default: the clock64 timeline shows a K-step cadence of ~427 cycles whatever the tile width while the
-// four MMAs of a K-step issue in ~190, which pointed at the copy engine; this LSU path turned out 2-4x slower, see tc_run.)  Pixel row r of the box <-> (tn, thb, tw): tw = r % TW, thb = (r / TW) % THb, tn = ...;
-// input pixel (b0 + tn, h_base + thb * s, w_base + tw * s).
-template <int BK>
-__device__ __forceinline__ void tc_issue_a_tile(unsigned char* a_dst, const TcParams& p, int b0, int h_base, int w_base,
-                                                int kcol, int lane) {
-    constexpr int CPR = BK / 8;                    // 16-byte chunks per pixel row
-    constexpr int RPP = 32 / CPR;                  // rows per warp pass
-    const int c16 = lane % CPR;
-    const int tw_mask = p.TW - 1, th_mask = p.TH - 1;
-    const uint32_t dst0 = tc_smem_u32(a_dst);
-    for (int r = lane / CPR; r < p.a_rows; r += RPP) {
-        const int tw = r & tw_mask, t = r >> p.log2_tw;
-        const int thb = p.rg ? t : (t & th_mask), tn = p.rg ? 0 : (t >> p.log2_th);
-        const int h = h_base + thb * p.in_stride, w = w_base + tw * p.in_stride, b = b0 + tn;
-        const bool ok = (unsigned)h < (unsigned)p.Hin && (unsigned)w < (unsigned)p.Win && b < p.B;
-        const __nv_bfloat16* src = ok ? p.x + ((((size_t)b * p.Hin + h) * p.Win + w) * p.Cin + kcol + c16 * 8) : p.x;
-        const int swz = (BK == 64) ? (r & 7) : ((r >> 1) & 3);
-        const uint32_t dst = dst0 + (uint32_t)(r * (BK * 2) + ((c16 ^ swz) << 4));
-        const int nbytes = ok ? 16 : 0;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-    }
-}
-
-// One epilogue pass over CH accumulator columns held by a warp (one pixel row per lane): + bias, + residual (read coalesced,
-// staged, so that it is still added in fp32 before the single rounding), bf16, XOR-swizzled smem transpose, 64/128-byte
-// coalesced row-segment stores, fused GroupNorm statistics.  nglob = global output channel of f[0].
-template <int CH>
-__device__ __forceinline__ void tc_epilogue_pass(float (&f)[CH], const TcParams& p, int nglob, long long row_off, bool row_ok,
-                                                 int b, uint4* stage, int lane) {
-    constexpr int LPR = CH / 8;                   // 16-byte units per staged row = lanes per row when storing
-    constexpr int RPI = 32 / LPR;                 // rows per store instruction
-    const int my_sw = (LPR == 8) ? (lane & 7) : ((lane >> 1) & 3);
-    const int sr = lane / LPR, su = lane % LPR;   // store phase: row within the group of RPI rows, 16-byte unit
-    long long st_off[LPR];                        // offsets of the rows this lane stores (row it * RPI + sr), -1 = masked
-#pragma unroll
-    for (int it = 0; it < LPR; ++it) st_off[it] = __shfl_sync(0xffffffffu, row_off, it * RPI + sr);
-    if (p.bias && row_ok) {
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nglob + j));
-            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-        }
-    }
-    const long long coff = (long long)nglob;      // row_off addresses channel 0 of the row
-    if (p.residual) {
-#pragma unroll
-        for (int it = 0; it < LPR; ++it) {
-            const int r = it * RPI + sr;
-            const int sw = (LPR == 8) ? (r & 7) : ((r >> 1) & 3);
-            uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-            if (st_off[it] >= 0) rv = *reinterpret_cast<const uint4*>(p.residual + st_off[it] + coff + su * 8);
-            stage[r * LPR + (su ^ sw)] = rv;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < LPR; ++u) {
-            const uint4 rv = stage[lane * LPR + (u ^ my_sw)];
-            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                f[u * 8 + 2 * k] += __low2float(hp[k]);
-                f[u * 8 + 2 * k + 1] += __high2float(hp[k]);
-            }
-        }
-        __syncwarp();
-    }
-    // bf16 rows -> swizzled staging tile
-#pragma unroll
-    for (int u = 0; u < LPR; ++u) {
-        uint4 pk;
-        __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hp[k] = __floats2bfloat162_rn(f[u * 8 + 2 * k], f[u * 8 + 2 * k + 1]);
-        stage[lane * LPR + (u ^ my_sw)] = pk;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < LPR; ++it) {
-        const int r = it * RPI + sr;
-        const int sw = (LPR == 8) ? (r & 7) : ((r >> 1) & 3);
-        if (st_off[it] >= 0) *reinterpret_cast<uint4*>(p.y + st_off[it] + coff + su * 8) = stage[r * LPR + (su ^ sw)];
-    }
-    if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
-        float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
-#pragma unroll
-        for (int hh = 0; hh < CH / 32; ++hh) {
-            const int fg = (nglob + hh * 32) / p.gn_cpg;
-            const float* fh = f + hh * 32;
-            if (p.gn_cpg == 4) gn_stats_chunk<4>(fh, sums_b, fg, lane);
-            else if (p.gn_cpg == 8) gn_stats_chunk<8>(fh, sums_b, fg, lane);
-            else if (p.gn_cpg == 16) gn_stats_chunk<16>(fh, sums_b, fg, lane);
-            else gn_stats_chunk<32>(fh, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): one group
-        }
-    }
-    __syncwarp();                                 // staging tile is reused by the next pass
-}
-
 template <int BN, int BK>
 struct TcCfg {
     static constexpr int SW = BK * 2;                                     // swizzle span in bytes (128 or 64)
@@ -341,7 +223,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t pad_bytes = (1024 - (raw_addr & 1023)) & 1023;
     unsigned char* wres = smem_raw + pad_bytes;              // resident weights (res_bytes, may be 0)
     unsigned char* ring = wres + p.res_bytes;
-    float* red = reinterpret_cast<float*>(smem_raw + pad_bytes + p.red_off);   // split-K exchange buffer (splits > 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pad_bytes + TC_OPERAND_BYTES);
     uint64_t* full = bars;                                   // [TC_MAX_STAGES]
     uint64_t* empty = bars + TC_MAX_STAGES;                  // [TC_MAX_STAGES]
@@ -355,12 +236,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kc_per_tap = p.Cin / BK;
     const int total_tiles = p.m_tiles * p.n_tiles * p.n_classes;
-    // split-K: the CTAs of a cluster share tile blockIdx.x / splits; CTA `srank` owns K-steps [k_lo, k_hi)
-    const int S = p.splits;
-    const uint32_t srank = S > 1 ? cluster_ctarank() : 0u;
-    const int tile0 = S > 1 ? (int)blockIdx.x / S : (int)blockIdx.x;      // first (only, when split) tile of this CTA
-    const int tile_stride = S > 1 ? total_tiles : (int)gridDim.x;         // split: exactly one tile per cluster
-    const int k_lo = (int)srank * p.ksteps_split, k_hi = S > 1 ? k_lo + p.ksteps_split : 0x7fffffff;
     pdl_trigger();
 
     if (warp == 0 && lane == 0) {
@@ -368,10 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        // full[s]: one arrival (the expect_tx of the issuing thread) when both operands come by TMA; with the cp.async A
-        // producer: 32 lane arrivals (cp.async.mbarrier.arrive.noinc) + the expect_tx arrival for the TMA weights (if any)
-        const int full_count = p.a_cpasync ? 32 + (p.resident ? 0 : 1) : 1;
-        for (int s = 0; s < n_stages; ++s) { tc_mbar_init(&full[s], full_count); tc_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < n_stages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
         for (int s = 0; s < Cfg::ACC_STAGES; ++s) { tc_mbar_init(&acc_full[s], 1); tc_mbar_init(&acc_empty[s], 128); }
         tc_mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -385,9 +257,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // split-K: a CTA may only write into a peer's shared memory once that peer is running.  Every thread announces
-    // "started" here and checks the announcements right before its first DSMEM access / the exchange barrier.
-    if (S > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     pdl_wait();                 // prologue done; everything below reads what the previous kernel wrote
 
     if (warp == 0 || warp == 2 || warp == 3) {
@@ -395,9 +264,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // (a single thread can only issue a K-step every ~600 cycles -- wait + expect_tx + 2 TMA -- which starved the
         //  tensor pipe on the small-channel layers; the three issue streams are independent)
         const uint32_t pidx = (warp == 0) ? 0u : (uint32_t)(warp - 1);
-        const bool lead = p.a_cpasync ? (lane == 0) : elect_one();     // the lane that talks to the copy engine
-        if (lead || p.a_cpasync) {
-            if (p.resident && pidx == 0 && lead) {
+        if (elect_one()) {
+            if (p.resident && pidx == 0) {
                 // all K tiles of the (single) n-tile: [tap][kc] boxes of BN x BK
                 const int n_k = p.KH * p.KW * kc_per_tap;
                 tc_mbar_expect_tx(wfull, (uint32_t)(n_k * Cfg::B_BYTES));
@@ -408,10 +276,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             unsigned char* a_dst = ring;
             const bool tracing = p.trace != nullptr && blockIdx.x == 0;
             const int groups_m0 = p.rg ? p.KW : p.KH * p.KW;
-            int tile_m = tile0 % p.m_tiles, rest = tile0 / p.m_tiles;      // tile = rest * m_tiles + tile_m
-            const int step_m = tile_stride % p.m_tiles, step_r = tile_stride / p.m_tiles;
+            int tile_m = blockIdx.x % p.m_tiles, rest = blockIdx.x / p.m_tiles;      // tile = rest * m_tiles + tile_m
+            const int step_m = gridDim.x % p.m_tiles, step_r = gridDim.x / p.m_tiles;
             int lt = 0;
-            for (int tile = tile0; tile < total_tiles; tile += tile_stride, ++lt) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
                 const int n0 = (rest % p.n_tiles) * BN;
                 const TcClass& cl = p.cls[rest / p.n_tiles];
                 const int tw_idx = tile_m % p.tiles_w;
@@ -419,9 +287,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int tb = t2 / p.tiles_h, th_idx = t2 - tb * p.tiles_h;
                 const int b0 = tb * p.TN, hh0 = p.in_stride * th_idx * p.TH, ww0 = p.in_stride * tw_idx * p.TW;
                 const int n_groups = (p.mode == 0) ? groups_m0 : cl.n_taps;
-                if (tracing && lead && pidx == 0 && lt < 500) p.trace[lt * 2] = clock64();
+                if (tracing && pidx == 0 && lt < 500) p.trace[lt * 2] = clock64();
                 int r = 0, q = 0;                              // mode 0, plain: tap (r, q) walked incrementally
-                int ks = 0;                                    // K-step index inside the tile (split-K range check)
                 for (int g = 0; g < n_groups; ++g) {
                     int dh, dw, ktap;
                     if (p.mode == 0) {
@@ -432,31 +299,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         dh = cl.dh[g]; dw = cl.dw[g]; ktap = cl.ktap[g];
                     }
                     int kcol = ktap * p.Cin;
-                    for (int kc = 0; kc < kc_per_tap; ++kc, kcol += BK, ++ks) {
-                        if (ks < k_lo || ks >= k_hi) continue;           // another CTA of the cluster owns this K-step
+                    for (int kc = 0; kc < kc_per_tap; ++kc, kcol += BK) {
                         if (turn == pidx) {
                             tc_mbar_wait(&empty[st], ph ^ 1);
-                            if (tracing && lead && git < 1000) p.trace[6144 + git] = clock64();
-                            if (p.a_cpasync) {
-                                if (lead && !p.resident) {
-                                    tc_mbar_expect_tx(&full[st], (uint32_t)(p.stage_bytes - p.a_bytes));
-                                    unsigned char* b_dst = a_dst + p.a_bytes;
-                                    int kj = kcol;
-                                    for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
-                                        tma_load_2d(b_dst, &map_w, &full[st], kj, n0);
-                                }
-                                tc_issue_a_tile<BK>(a_dst, p, b0, hh0 + dh, ww0 + dw, kc * BK, lane);
-                                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&full[st]))
-                                             : "memory");
-                            } else {
-                                tc_mbar_expect_tx(&full[st], (uint32_t)p.stage_bytes);
-                                tma_load_4d(a_dst, &map_x, &full[st], kc * BK, ww0 + dw, hh0 + dh, b0);
-                                if (!p.resident) {
-                                    unsigned char* b_dst = a_dst + p.a_bytes;
-                                    int kj = kcol;
-                                    for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
-                                        tma_load_2d(b_dst, &map_w, &full[st], kj, n0);   // row-group mode: tap (r = j, q = g)
-                                }
+                            if (tracing && git < 1000) p.trace[6144 + git] = clock64();
+                            tc_mbar_expect_tx(&full[st], (uint32_t)p.stage_bytes);
+                            tma_load_4d(a_dst, &map_x, &full[st], kc * BK, ww0 + dw, hh0 + dh, b0);
+                            if (!p.resident) {
+                                unsigned char* b_dst = a_dst + p.a_bytes;
+                                int kj = kcol;
+                                for (int j = 0; j < p.nb; ++j, kj += p.KW * p.Cin, b_dst += Cfg::B_BYTES)
+                                    tma_load_2d(b_dst, &map_w, &full[st], kj, n0);   // row-group mode: tap (r = j, q = g)
                             }
                         }
                         ++git;
@@ -468,7 +321,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (tile_m >= p.m_tiles) { tile_m -= p.m_tiles; ++rest; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
@@ -493,12 +345,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int nb = p.nb;
             const bool resident = p.resident != 0;
             uint32_t st = 0, ph = 0, a_lo = ring_lo, git = 0;
-            int rest = tile0 / p.m_tiles, tile_m = tile0 % p.m_tiles;
-            const int step_m = tile_stride % p.m_tiles, step_r = tile_stride / p.m_tiles;
+            int rest = blockIdx.x / p.m_tiles, tile_m = blockIdx.x % p.m_tiles;
+            const int step_m = gridDim.x % p.m_tiles, step_r = gridDim.x / p.m_tiles;
             int lt = 0;
-            for (int tile = tile0; tile < total_tiles; tile += tile_stride, ++lt) {
-                const int n_iters = S > 1 ? p.ksteps_split
-                                          : ((p.mode == 0) ? groups_m0 : p.cls[rest / p.n_tiles].n_taps) * kc_per_tap;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const int n_iters = ((p.mode == 0) ? groups_m0 : p.cls[rest / p.n_tiles].n_taps) * kc_per_tap;
                 const int as = lt & 1;
                 if (tracing && lt < 64) p.trace[1024 + lt * 4] = clock64();
                 if (lt == 0 && resident) tc_mbar_wait(wfull, 0);
@@ -510,8 +361,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 uint32_t res_lo = wres_lo;                           // resident weights: tile (it) of kernel row 0
                 for (int it = 0; it < n_iters; ++it, res_lo += b_tile_lo) {
                     tc_mbar_wait(&full[st], ph);
-                    // cp.async writes go through the generic proxy, the tensor core reads through the async proxy
-                    if (p.a_cpasync) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (tracing && git < 1000) p.trace[4096 + git * 2] = clock64();
                     uint32_t aj = a_lo;
@@ -553,19 +402,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // A lane owns one accumulator row (pixel).  Writing its row straight to global memory would make every store
         // instruction touch 32 different lines (16 bytes each): the LSU, not HBM, bounds the wide-N layers that way.
         // Instead each warp stages its 32 rows x CH columns in a private, XOR-swizzled shared-memory tile and writes it
-        // back with whole 64/128-byte row segments per quarter-warp (tc_epilogue_pass).
+        // back with LPR lanes per row, i.e. whole 64/128-byte row segments per quarter-warp.  The residual is read the
+        // same way (coalesced -> staged -> own row) so that it is still added in fp32 before the single rounding.
         constexpr int CH = BN >= 64 ? 64 : 32;        // columns per pass
+        constexpr int LPR = CH / 8;                   // 16-byte units per staged row = lanes per row when storing
+        constexpr int RPI = 32 / LPR;                 // rows per store instruction
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         uint4* stage = reinterpret_cast<uint4*>(stage_base) + quarter * (32 * 8);
         const int m = quarter * 32 + lane;            // accumulator row = pixel within the tile
         const int tn = m / (p.TH * p.TW);
         const int rem = m - tn * p.TH * p.TW;
         const int th = rem / p.TW, tw = rem - th * p.TW;
+        const int my_sw = (LPR == 8) ? (lane & 7) : ((lane >> 1) & 3);
+        const int sr = lane / LPR, su = lane % LPR;   // store phase: row within the group of RPI rows, 16-byte unit
         const bool tracing = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
-        int tile_m = tile0 % p.m_tiles, rest = tile0 / p.m_tiles;
-        const int step_m = tile_stride % p.m_tiles, step_r = tile_stride / p.m_tiles;
+        int tile_m = blockIdx.x % p.m_tiles, rest = blockIdx.x / p.m_tiles;
+        const int step_m = gridDim.x % p.m_tiles, step_r = gridDim.x / p.m_tiles;
         int lt = 0;
-        for (int tile = tile0; tile < total_tiles; tile += tile_stride, ++lt) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const int n0 = (rest % p.n_tiles) * BN;
             const TcClass& cl = p.cls[rest / p.n_tiles];
             const int tw_idx = tile_m % p.tiles_w;
@@ -574,22 +428,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int b = tb * p.TN + tn, h = th_idx * p.TH + th, w = tw_idx * p.TW + tw;
             const bool row_ok = (b < p.B) && (h < p.GH);
             const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * w + cl.off_w;
-            // offset of channel 0 of this lane's output pixel, -1 = masked row
-            const long long row_off = row_ok ? (long long)((((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout) : -1ll;
+            const long long row_off = row_ok ? (long long)((((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout + n0) : -1ll;
+            // offsets of the rows this lane stores (row it * RPI + sr), -1 = masked
+            long long st_off[LPR];
+#pragma unroll
+            for (int it = 0; it < LPR; ++it) st_off[it] = __shfl_sync(0xffffffffu, row_off, it * RPI + sr);
             const int as = lt & 1;
             if (tracing && lt < 64) p.trace[2048 + lt * 4] = clock64();
             tc_mbar_wait(&acc_full[as], (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tracing && lt < 64) p.trace[2048 + lt * 4 + 1] = clock64();
-            if (S > 1) {
-                // ---- split-K, phase A: hand every 32-column chunk of the partial accumulator to the CTA that finishes it
-                asm volatile("barrier.cluster.wait.aligned;" ::: "memory");     // all CTAs of the cluster have started
-                const int cpo = BN / S;                               // columns per owner: 32 or 64
-                const int pitch = cpo + 4;                            // floats; rows 16-byte aligned, banks spread
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < BN; c += CH) {
+                float f[CH];
+#pragma unroll
+                for (int hh = 0; hh < CH / 32; ++hh) {
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c + hh * 32);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -601,98 +456,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                           "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    const uint32_t owner = (uint32_t)(c / cpo);
-                    // slot of THIS CTA (srank) in the owner's buffer: red[srank][m][c % cpo ...]
-                    const uint32_t dst = tc_smem_u32(red + ((size_t)srank * TC_BM + m) * pitch + (c % cpo));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        st_remote_f4(dst + j * 4, owner, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; ++j) f[hh * 32 + j] = row_ok ? __uint_as_float(v[j]) : 0.f;
                 }
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < BN; c += CH) {
-                    float f[CH];
+                if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4] = clock64();
+                if (c + CH >= BN) {
+                    // the last columns of this accumulator are in registers: hand the TMEM stage back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&acc_empty[as])) : "memory");
+                }
+                if (p.bias && row_ok) {
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+                        f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                    }
+                }
+                if (p.residual) {
+#pragma unroll
+                    for (int it = 0; it < LPR; ++it) {
+                        const int r = it * RPI + sr;
+                        const int sw = (LPR == 8) ? (r & 7) : ((r >> 1) & 3);
+                        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                        if (st_off[it] >= 0) rv = *reinterpret_cast<const uint4*>(p.residual + st_off[it] + c + su * 8);
+                        stage[r * LPR + (su ^ sw)] = rv;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < LPR; ++u) {
+                        const uint4 rv = stage[lane * LPR + (u ^ my_sw)];
+                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            f[u * 8 + 2 * k] += __low2float(hp[k]);
+                            f[u * 8 + 2 * k + 1] += __high2float(hp[k]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                // bf16 rows -> swizzled staging tile
+#pragma unroll
+                for (int u = 0; u < LPR; ++u) {
+                    uint4 pk;
+                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hp[k] = __floats2bfloat162_rn(f[u * 8 + 2 * k], f[u * 8 + 2 * k + 1]);
+                    stage[lane * LPR + (u ^ my_sw)] = pk;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < LPR; ++it) {
+                    const int r = it * RPI + sr;
+                    const int sw = (LPR == 8) ? (r & 7) : ((r >> 1) & 3);
+                    if (st_off[it] >= 0)
+                        *reinterpret_cast<uint4*>(p.y + st_off[it] + c + su * 8) = stage[r * LPR + (su ^ sw)];
+                }
+                if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 1] = clock64();
+                if (p.gn_sums != nullptr && b < p.B) {        // warp-uniform: the 32 rows of a warp lie in one sample
+                    float* sums_b = p.gn_sums + (size_t)b * p.gn_groups * 2;
 #pragma unroll
                     for (int hh = 0; hh < CH / 32; ++hh) {
-                        uint32_t v[32];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c + hh * 32);
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                              "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                              "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                              "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                            : "r"(taddr));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[hh * 32 + j] = row_ok ? __uint_as_float(v[j]) : 0.f;
+                        const int fg = (n0 + c + hh * 32) / p.gn_cpg;
+                        const float* fh = f + hh * 32;
+                        if (p.gn_cpg == 4) gn_stats_chunk<4>(fh, sums_b, fg, lane);
+                        else if (p.gn_cpg == 8) gn_stats_chunk<8>(fh, sums_b, fg, lane);
+                        else if (p.gn_cpg == 16) gn_stats_chunk<16>(fh, sums_b, fg, lane);
+                        else gn_stats_chunk<32>(fh, sums_b, fg, lane);     // cpg >= 32 (multiple of 32): one group
                     }
-                    if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4] = clock64();
-                    if (c + CH >= BN) {
-                        // the last columns of this accumulator are in registers: hand the TMEM stage back to the MMA warp
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&acc_empty[as])) : "memory");
-                    }
-                    tc_epilogue_pass<CH>(f, p, n0 + c, row_off, row_ok, b, stage, lane);
-                    if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 2] = clock64();
                 }
+                __syncwarp();                                   // staging tile is reused by the next pass
+                if (tracing && lt < 64 && c == 0) p.trace[3072 + lt * 4 + 2] = clock64();
             }
             if (tracing && lt < 64) p.trace[2048 + lt * 4 + 2] = clock64();
             tile_m += step_m; rest += step_r;
             if (tile_m >= p.m_tiles) { tile_m -= p.m_tiles; ++rest; }
-        }
-    }
-    if (S > 1) {
-        // ---- split-K, phase B.  Every thread of every CTA of the cluster meets here: all partial accumulators have been
-        // written into their owners' exchange buffers (release / acquire at cluster scope).
-        __syncwarp();
-        if (warp < 4) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // (the "started" phase; epilogue warps did)
-        const bool tracing_b = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
-        if (tracing_b) p.trace[3072] = clock64();                    // phase A done, entering the exchange barrier
-        cluster_sync_all();
-        if (tracing_b) p.trace[3073] = clock64();                    // barrier passed
-        if (warp >= 4) {
-            const int quarter = warp & 3;
-            uint4* stage = reinterpret_cast<uint4*>(stage_base) + quarter * (32 * 8);
-            const int m = quarter * 32 + lane;
-            const int tn = m / (p.TH * p.TW);
-            const int rem = m - tn * p.TH * p.TW;
-            const int th = rem / p.TW, tw = rem - th * p.TW;
-            const int tile_m = tile0 % p.m_tiles, rest = tile0 / p.m_tiles;
-            const int n0 = (rest % p.n_tiles) * BN;
-            const TcClass& cl = p.cls[rest / p.n_tiles];
-            const int tw_idx = tile_m % p.tiles_w;
-            const int t2 = tile_m / p.tiles_w;
-            const int tb = t2 / p.tiles_h, th_idx = t2 - tb * p.tiles_h;
-            const int b = tb * p.TN + tn, h = th_idx * p.TH + th, w = tw_idx * p.TW + tw;
-            const bool row_ok = (b < p.B) && (h < p.GH) && tile0 < total_tiles;
-            const int oh = p.out_scale * h + cl.off_h, ow = p.out_scale * w + cl.off_w;
-            const long long row_off = row_ok ? (long long)((((size_t)b * p.Ho + oh) * p.Wo + ow) * p.Cout) : -1ll;
-            const int cpo = BN / S, pitch = cpo + 4;
-#pragma unroll 1
-            for (int c = 0; c < cpo; c += 32) {
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                for (int r = 0; r < S; ++r) {                       // fixed order: deterministic sum
-                    const float4* src = reinterpret_cast<const float4*>(red + ((size_t)r * TC_BM + m) * pitch + c);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t = src[j];
-                        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-                    }
-                }
-                if (!row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                }
-                tc_epilogue_pass<32>(f, p, n0 + (int)srank * cpo + c, row_off, row_ok, b, stage, lane);
-            }
-            if (tracing_b) p.trace[3074] = clock64();                // phase B done
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -722,7 +559,6 @@ static EncodeTiledFn get_encode() {
 struct TcPlan {
     int TW, TH, TN, BN, BK;
     int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes;
-    int splits, ksteps_split, red_off;
 };
 
 // GH x GW = pixel grid of the GEMM (output grid for regular convs, input grid for the transposed gather)
@@ -768,37 +604,7 @@ static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int KH, int KW, in
         pl.stage_bytes = stage; pl.stages = stages;
         if (m_tiles * (Cout / bn) >= 148) break;    // widest tile that still fills the machine
     }
-    pl.splits = 1; pl.ksteps_split = 0; pl.red_off = 0;
-    if (pl.BN == 0) return false;
-    // Split-K in a cluster for the deep, low-resolution layers (OPT-IN: PIDM_TC_SPLIT=1).  With <= 64 pixel tiles the plan
-    // above fills the machine only by making the n-tile narrow (BN = 32) and every CTA walks all K-steps.  Here: wide
-    // n-tiles, the K-steps of a tile divided over the `splits` CTAs of a cluster, partial accumulators exchanged through
-    // DSMEM.  Measured on B200 (clock64 timeline of CTA 0, 8x8x256 3x3, B = 32; profiles/r02_conv_splitk_trace.txt): the
-    // main loop shrinks from 16.9 k to 5.2 k cycles, but pushing 64 KB of partials with st.shared::cluster takes 5 k
-    // cycles and the cluster barrier another 6.5 k (it absorbs the start skew of the cluster's CTAs behind the previous
-    // kernel), so the launch goes from 11.9 to 12.8-13.2 us; pulling with ld.shared::cluster is worse (19.7 us).  Only
-    // the 72-K-step layer (8x8, 512 -> 128) gains (20.5 -> 17.3 us).  Hence off by default.
-    static int allow_split = -1;
-    if (allow_split < 0) { const char* ev = getenv("PIDM_TC_SPLIT"); allow_split = ev ? atoi(ev) : 0; }
-    if (allow_split && mode == 0 && classes == 1 && m_tiles <= 64) {
-        const int n_ksteps = (pl.rg ? KW : KH * KW) * (Cin / pl.BK);
-        const int cand[3][2] = {{128, 4}, {128, 2}, {64, 2}};
-        for (int i = 0; i < 3; ++i) {
-            const int bn = cand[i][0], S = cand[i][1];
-            if (Cout % bn != 0 || n_ksteps % S != 0 || n_ksteps / S < 3) continue;
-            const long long ctas = m_tiles * (Cout / bn) * S;
-            if (ctas > 148 || ctas < 48) continue;
-            const int red_bytes = ((S * TC_BM * (bn / S + 4) * 4) + 1023) / 1024 * 1024;
-            const int stage = pl.a_bytes + pl.nb * bn * pl.BK * 2;
-            int stages = (TC_OPERAND_BYTES - red_bytes) / stage;
-            if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-            if (stages < 3) continue;
-            pl.BN = bn; pl.resident = 0; pl.res_bytes = 0; pl.stage_bytes = stage; pl.stages = stages;
-            pl.splits = S; pl.ksteps_split = n_ksteps / S; pl.red_off = TC_OPERAND_BYTES - red_bytes;
-            break;
-        }
-    }
-    return true;
+    return pl.BN != 0;
 }
 
 template <int BN, int BK>
@@ -809,27 +615,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
                                        TC_SMEM_BYTES));
         attr = true;
     }
-    if (p.splits > 1) {          // one cluster of `splits` CTAs per output tile
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = TC_SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute attrs[2];
-        int na = 0;
-        attrs[na].id = cudaLaunchAttributeClusterDimension;
-        attrs[na].val.clusterDim.x = (unsigned)p.splits; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
-        ++na;
-        if (pdl_enabled(PIDM_PDL_GROUP)) {
-            attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attrs[na].val.programmaticStreamSerializationAllowed = 1;
-            ++na;
-        }
-        cfg.attrs = attrs; cfg.numAttrs = na;
-        PIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BK>, mx, mw, p));
-    } else {
-        PIDM_CUDA(launch_pdl(conv_tc_kernel<BN, BK>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mx, mw, p));
-    }
+    PIDM_CUDA(launch_pdl(conv_tc_kernel<BN, BK>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mx, mw, p));
     PIDM_LAUNCH_CHECK("conv2d_tc");
     return 0;
 }
@@ -870,7 +656,6 @@ static bool tc_geometry(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, 
     p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = p.GH / pl.TH; p.tiles_w = p.GW / pl.TW;
     p.rg = pl.rg; p.nb = pl.nb; p.a_bytes = pl.a_bytes; p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
     p.resident = pl.resident; p.res_bytes = pl.res_bytes;
-    p.splits = pl.splits; p.ksteps_split = pl.ksteps_split; p.red_off = pl.red_off; p.ring_bytes = 0;
     return true;
 }
 
@@ -919,18 +704,6 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         PIDM_REQUIRE(r == CUDA_SUCCESS, "conv2d_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
     }
     p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.y = (__nv_bfloat16*)y;
-    {   // A operand through the LSU (cp.async) instead of TMA: OPT-IN (PIDM_TC_CPASYNC=1).  Built because the K-step cadence
-        // of the main loop (~427 cycles) looked like a copy-engine limit; measured (profiles/r02_conv_splitk_trace.txt): the
-        // three producer warps need ~2400 cycles per K-step for the 1024 predicated, swizzled 16-byte cp.async of a tile
-        // (address arithmetic + LSU issue), 8x8x256: 12.8 -> 49 us, 64x64x32: 12.0 -> 23.3 us.  TMA stays the default.
-        static int want = -1;
-        if (want < 0) { const char* ev = getenv("PIDM_TC_CPASYNC"); want = ev ? atoi(ev) : 0; }
-        auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return ((1 << l) == v) ? l : -1; };
-        p.x = (const __nv_bfloat16*)x; p.Hin = H; p.Win = W;
-        p.log2_tw = ilog2(pl.TW); p.log2_th = ilog2(pl.TH);
-        p.a_rows = (pl.TH + (pl.rg ? KH - 1 : 0)) * pl.TW * pl.TN;
-        p.a_cpasync = (want && p.log2_tw >= 0 && p.log2_th >= 0) ? 1 : 0;
-    }
     p.trace = g_tc_trace;
     p.gn_sums = gn_sums; p.gn_groups = gn_groups; p.gn_cpg = gn_groups > 0 ? Cout / gn_groups : 0;
     if (gn_sums) {
@@ -950,7 +723,7 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         PIDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int total_tiles = p.m_tiles * p.n_tiles * p.n_classes;
-    dim3 grid(p.splits > 1 ? total_tiles * p.splits : (total_tiles < sm_count ? total_tiles : sm_count));
+    dim3 grid(total_tiles < sm_count ? total_tiles : sm_count);
 #define TC_CASE(bn, bk) if (pl.BN == bn && pl.BK == bk) return launch_tc<bn, bk>(mx, mw, p, grid, st)
     TC_CASE(256, 64); TC_CASE(128, 64); TC_CASE(64, 64); TC_CASE(32, 64);
     TC_CASE(256, 32); TC_CASE(128, 32); TC_CASE(64, 32); TC_CASE(32, 32);
