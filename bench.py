@@ -261,28 +261,39 @@ def breakdown_one_step(engine, x0):
     return agg
 
 
-def sampling_bench(model, res, dev, n_steps=250, batch=16):
-    """BASELINE.json configs[3]: ancestral sampling loop with per-step Darcy residual evaluation, one CUDA graph per
-    step replayed n_steps times (engine.SampleEngine).  Device-timed; the initial noise is drawn on the device."""
+def sampling_bench(model, dev, n_steps=250, batches=(16, 64, 256)):
+    """BASELINE.json configs[3]: ancestral sampling loop with per-step Darcy residual evaluation (engine.SampleEngine: 10
+    steps per captured CUDA graph, weights packed once per loop, initial noise drawn on the device), device-timed, at
+    three batch sizes in mean mode (x0 = network output) and at batch 16 with `x0_estimation: sample` (two network calls
+    per step + the DDIM jump, reference ddim_steps = 0)."""
     from physicsinformeddiffusionmodels_b200.denoising_utils import DenoisingDiffusion
     from physicsinformeddiffusionmodels_b200.engine import SampleEngine
+    from physicsinformeddiffusionmodels_b200.residuals_darcy import ResidualsDarcy
     was_training = model.training
     model.eval()
     diff = DenoisingDiffusion(n_steps, dev)
-    eng = SampleEngine(model, diff, res, batch=batch)
-    eng.sample()                                      # captures the graph + one full warm-up loop
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    x, r, _ = eng.sample()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+
+    def run(batch, use_ddim_x0):
+        res = ResidualsDarcy(model=model, fd_acc=2, pixels_per_dim=64, pixels_at_boundary=True, reverse_d1=True, device=dev,
+                             bcs='none', domain_length=1., use_ddim_x0=use_ddim_x0, ddim_steps=0)
+        eng = SampleEngine(model, diff, res, batch=batch)
+        eng.sample()                                      # captures the graph + one full warm-up loop
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x, r, _ = eng.sample()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return {'batch': batch, 'ms_per_loop': ms, 'ms_per_step': ms / n_steps, 'samples_per_s': batch / (ms * 1e-3),
+                'final_abs_residual_mean': float(r.abs().mean().item()), 'finite': bool(torch.isfinite(x).all().item())}
+    out = {'workload': f'Darcy 64x64 ancestral sampling (p_sample_loop), {n_steps} steps, Darcy residual evaluated every step, '
+                       'bf16 activations, 10 steps per CUDA graph', 'mean_mode': [run(b, False) for b in batches],
+           'sample_mode_ddim0': run(batches[0], True)}
+    best = max(out['mean_mode'], key=lambda d: d['samples_per_s'])
+    out.update({k: best[k] for k in ('batch', 'ms_per_loop', 'ms_per_step', 'samples_per_s')})      # headline: best batch
     model.train(was_training)
-    return {'workload': f'Darcy 64x64 ancestral sampling (p_sample_loop), {n_steps} steps, batch {batch}, x0 = network '
-                        'output (mean mode), Darcy residual evaluated every step, bf16 activations',
-            'ms_per_loop': ms, 'ms_per_step': ms / n_steps, 'samples_per_s': batch / (ms * 1e-3),
-            'final_abs_residual_mean': float(r.abs().mean().item()), 'finite': bool(torch.isfinite(x).all().item())}
+    return out
 
 
 def mechanics_bench(dev, pk, batch=32, steps=10, warmup=4):
@@ -519,15 +530,18 @@ def main():
                 roof['algorithmic_bytes'] = d['bytes']
                 roof['hbm_view'] = {'achieved': d['bytes'] / (d['ms'] * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                     'frac': d['bytes'] / (d['ms'] * 1e-3) / 1e9 / pk['hbm_gbs']}
-            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_step_traffic.json')
-            if os.path.exists(tpath):
+            prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles')
+            tpath = next((os.path.join(prof, f) for f in ('r02_step_traffic.json', 'r01_step_traffic.json')
+                          if os.path.exists(os.path.join(prof, f))), None)
+            if tpath:
                 prefix = {'pidm_conv2d_tc_general': 'conv_tc_kernel', 'pidm_conv2d_tc': 'conv_tc_kernel',
                           'pidm_conv2d_wgrad_tc': 'wgrad'}.get(name)
                 if prefix:
                     tr = json.load(open(tpath))
                     roof['traffic'] = sum(v['dram_bytes'] for k, v in tr.items() if k.startswith(prefix))
-                    roof['traffic_note'] = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of this '
-                                            'kernel in ONE step (ncu launch list, profiles/r01_step_traffic.json); '
+                    roof['traffic_note'] = ('STATIC, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum summed '
+                                            'over the launches of this kernel in ONE step, from the committed ncu launch '
+                                            f'list profiles/{os.path.basename(tpath)} (same command, scripts/gpu_final.sh); '
                                             'compare with algorithmic_bytes')
         else:
             roof = {'bound': 'hbm', 'kernel': name, 'achieved': None, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
@@ -542,8 +556,8 @@ def main():
         extra['launches_note'] = (f'{calls_per_step} libpidm entry-point calls per step per GPU (each issues 1-3 kernels); '
                                   'replayed from a CUDA graph' if not args.no_graph else 'eager')
         if not args.no_sampling:
-            log('sampling loop (configs[3]): 250 ancestral steps, batch 16')
-            extra['sampling'] = sampling_bench(model, res, dev)
+            log('sampling loop (configs[3]): 250 ancestral steps, batch 16 / 64 / 256, mean and sample mode')
+            extra['sampling'] = sampling_bench(model, dev)
         if not args.no_mechanics:
             log('mechanics workload (configs[2]): Unet3D(dim=128), batch 32')
             try:

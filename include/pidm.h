@@ -37,6 +37,11 @@ int pidm_posterior_step(const float* x_t, const float* x0_pred, const float* z, 
  * (src/denoising_utils.py:755-785) collapses to this form */
 int pidm_axpby_per_sample(const float* a, const float* x, const float* b, const float* y, const float* c,
                           const float* z, float* out, int B, int per_sample, void* stream);
+/* per-sample coefficients of the deterministic DDIM jump t -> t_next (src/denoising_utils.py:755-781, eta = 0):
+ * x' = coef_x0 * x0_pred + coef_x * x  (coef_x0 = 0, coef_x = 1 where t == t_next); tables are the diff_dict entries */
+int pidm_ddim_coefs(const long long* t, const long long* t_next, const float* posterior_mean_coef1,
+                    const float* posterior_mean_coef2, const float* sqrt_recip_alphas, const float* noise_mean_coeff,
+                    const float* alphas_prod, float* coef_x0, float* coef_x, int B, void* stream);
 /* out = x * *alpha_dev  (chain-rule scaling of a precomputed gradient by the upstream scalar; out may alias x) */
 int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream);
 

@@ -141,6 +141,18 @@ def build_port_step(device, batch, channels_last=False):
     v = [torch.zeros_like(p) for p in train]
     ema = [p.detach().clone() for p in train]
     tables = {k: t.to(device) for k, t in O.diffusion_tables(100).items()}
+    if str(device).startswith('cuda'):
+        # the restatement builds the source field on the host at every call: keep one device copy (CUDA-graph capture
+        # cannot contain a pageable host-to-device copy)
+        fs = {}
+        orig_source = O.darcy_source
+
+        def cached_source(pixels=64, w=0.125, r=10.0, dtype=torch.float32):
+            key = (pixels, dtype)
+            if key not in fs:
+                fs[key] = orig_source(pixels, w, r, dtype).to(device)
+            return fs[key]
+        O.darcy_source = cached_source
     torch.manual_seed(0)
     x0 = torch.randn(batch, 2, 64, 64, device=device)
     state = {'it': 0}

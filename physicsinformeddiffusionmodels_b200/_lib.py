@@ -22,6 +22,7 @@ _SIGS = {
     'pidm_qsample': [P, P, P, P, P, P, I, I, P],
     'pidm_posterior_step': [P, P, P, P, F, F, F, L, P],
     'pidm_scale': [P, P, P, L, P],
+    'pidm_ddim_coefs': [P, P, P, P, P, P, P, P, P, I, P],
     'pidm_axpby_per_sample': [P, P, P, P, P, P, P, I, I, P],
     'pidm_toy_pidm_loss': [P, P, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, I, I, P],
     'pidm_fd_stencil': [P, P, I, I, I, F, F, P],

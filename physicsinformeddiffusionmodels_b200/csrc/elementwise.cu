@@ -237,6 +237,25 @@ __global__ void toy_loss_kernel(const float* __restrict__ target, const float* _
     }
 }
 
+// ---- DDIM jump coefficients (eta = 0) of ddim_sample_x0 (reference denoising_utils.py:755-781), per sample:
+//   mean = c1 x0 + c2 x;  eps = (sra x - mean) / nmc;  x' = sqrt(a') x0 + sqrt(1 - a') eps,  a' = alphas_prod[t_next]
+//   => x' = coef_x0 * x0 + coef_x * x   (identity where t == t_next).  One launch instead of ~20 gather / arithmetic kernels.
+__global__ void ddim_coefs_kernel(const long long* __restrict__ t, const long long* __restrict__ t_next,
+                                  const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ sra,
+                                  const float* __restrict__ nmc, const float* __restrict__ aprod, float* __restrict__ coef_x0,
+                                  float* __restrict__ coef_x, int B) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const long long tt = t[b], tn = t_next[b];
+    if (tt == tn) { coef_x0[b] = 0.f; coef_x[b] = 1.f; return; }
+    const float an = aprod[tn < 0 ? 0 : tn];
+    const float c = sqrtf(1.f - an);
+    coef_x0[b] = sqrtf(an) - c * c1[tt] / nmc[tt];
+    coef_x[b] = c * (sra[tt] - c2[tt]) / nmc[tt];
+}
+
 // ---- GELU (exact erf form, nn.GELU()) on activations: the residual-gradient embedding emb_conv of the guidance branch
 //      (reference unet_model.py:520-524).  n8 = number of 8-element vectors.
 template <typename T, bool BWD>
@@ -453,6 +472,16 @@ extern "C" int pidm_axpby_per_sample(const float* a, const float* x, const float
 extern "C" int pidm_scale(const float* x, const float* alpha_dev, float* out, long long n, void* stream) {
     PIDM_CUDA(launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, alpha_dev, out, n));
     PIDM_LAUNCH_CHECK("scale");
+    return 0;
+}
+
+extern "C" int pidm_ddim_coefs(const long long* t, const long long* t_next, const float* posterior_mean_coef1,
+                               const float* posterior_mean_coef2, const float* sqrt_recip_alphas, const float* noise_mean_coeff,
+                               const float* alphas_prod, float* coef_x0, float* coef_x, int B, void* stream) {
+    PIDM_CUDA(launch_pdl(ddim_coefs_kernel, dim3(grid_for(B, 128)), dim3(128), (size_t)0, (cudaStream_t)stream, t, t_next,
+                         posterior_mean_coef1, posterior_mean_coef2, sqrt_recip_alphas, noise_mean_coeff, alphas_prod, coef_x0,
+                         coef_x, B));
+    PIDM_LAUNCH_CHECK("ddim_coefs");
     return 0;
 }
 

@@ -383,15 +383,14 @@ class DenoisingDiffusion(nn.Module):
             if idx == n_pts - 1:                       # t_next == -1 for every sample: the walk ends on x0_pred
                 cur_x = x0_pred
                 continue
-            # mean = c1 x0 + c2 x ; eps = (sra x - mean)/nmc ; x' = sqrt(a_next) x0 + sqrt(1-a_next) eps   (eta = 0)
-            c1, c2 = dd['posterior_mean_coef1'][tt], dd['posterior_mean_coef2'][tt]
-            sra, nmc = dd['sqrt_recip_alphas'][tt], dd['noise_mean_coeff'][tt]
-            a_next = dd['alphas_prod'][tn.clamp_min(0)]
-            c = (1 - a_next).sqrt()
-            keep = (tt == tn).float()
-            coef_x0 = (1 - keep) * (a_next.sqrt() - c * c1 / nmc)
-            coef_x = keep + (1 - keep) * (c * (sra - c2) / nmc)
+            # mean = c1 x0 + c2 x ; eps = (sra x - mean)/nmc ; x' = sqrt(a_next) x0 + sqrt(1-a_next) eps   (eta = 0):
+            # the per-sample coefficients of x0 and x in ONE launch (pidm_ddim_coefs)
+            from ._lib import call, stream
+            coef_x0 = torch.empty(batch, device=dev, dtype=torch.float32)
+            coef_x = torch.empty(batch, device=dev, dtype=torch.float32)
+            call('pidm_ddim_coefs', tt, tn, dd['posterior_mean_coef1'], dd['posterior_mean_coef2'], dd['sqrt_recip_alphas'],
+                 dd['noise_mean_coeff'], dd['alphas_prod'], coef_x0, coef_x, batch, stream())
             _ = torch.randn_like(cur_x)                # RNG parity: the reference draws noise even when sigma = 0
-            cur_x = _AxpbyPerSample.apply(coef_x0.contiguous(), x0_pred, coef_x.contiguous(), cur_x)
+            cur_x = _AxpbyPerSample.apply(coef_x0, x0_pred, coef_x, cur_x)
         assert model_out is not None, 'Model output not given.'
         return cur_x, model_out
