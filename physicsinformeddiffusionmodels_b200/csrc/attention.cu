@@ -435,6 +435,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
 bool la_small_supported(int N, int dtype);
 int la_small_fwd(const void* qkv, void* out, float* ctx, float* kmax, float* kzinv, int B, int N, int heads, float scale,
                  cudaStream_t st);
+// attention_mid.cu: the 64-token softmax attention on mma.sync (bf16)
+bool attn_mid_supported(int n_tokens, int dtype);
+int attn_mid_fwd(const void* qkv, void* out, int B, int heads, float scale, cudaStream_t st);
+int attn_mid_bwd(const void* qkv, const void* dout, void* dqkv, int B, int heads, float scale, cudaStream_t st);
 int la_mma_ctx(int mode, const void* qkv, const void* dout, const float* part, int n_stat_chunks, float* kmax,
                float* kzinv, float* ctx, int B, int N, float scale, cudaStream_t st);
 int la_mma_out(const void* qkv, const float* ctx, void* out, int B, int N, float scale, cudaStream_t st);
@@ -519,6 +523,7 @@ extern "C" int pidm_linattn_bwd(const void* qkv, const void* dout, const float* 
 extern "C" int pidm_attn_fwd(const void* qkv, void* out, int B, int n_tokens, int heads, int dtype, void* stream) {
     PIDM_REQUIRE(n_tokens >= 1 && n_tokens <= AT_N, "attn: at most %d tokens supported (got %d)", AT_N, n_tokens);
     const float scale = 0.17677669529663687f;
+    if (attn_mid_supported(n_tokens, dtype)) return attn_mid_fwd(qkv, out, B, heads, scale, (cudaStream_t)stream);
     static bool set0 = false, set1 = false;
     PIDM_DISPATCH_DTYPE(dtype, {
         bool& flag = (sizeof(T) == 4) ? set0 : set1;
@@ -538,6 +543,7 @@ extern "C" int pidm_attn_bwd(const void* qkv, const void* dout, void* dqkv, int 
                              void* stream) {
     PIDM_REQUIRE(n_tokens >= 1 && n_tokens <= AT_N, "attn: at most %d tokens supported (got %d)", AT_N, n_tokens);
     const float scale = 0.17677669529663687f;
+    if (attn_mid_supported(n_tokens, dtype)) return attn_mid_bwd(qkv, dout, dqkv, B, heads, scale, (cudaStream_t)stream);
     static bool set0 = false, set1 = false;
     PIDM_DISPATCH_DTYPE(dtype, {
         bool& flag = (sizeof(T) == 4) ? set0 : set1;

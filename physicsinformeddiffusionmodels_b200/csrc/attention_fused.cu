@@ -99,7 +99,8 @@ __device__ __forceinline__ void load_cols(float (&v)[8], const float* __restrict
 }
 
 // ---- pass 1: per-chunk column maxima of k = xn Wk^T (the exp-sums are accumulated by the context kernel) -------------
-constexpr int LFS_STAGES = 4;
+constexpr int LFS_STAGES = 2;      // a tile is consumed into registers at once: one tile of look-ahead is enough,
+                                   // and 41 KB per CTA lets five CTAs share an SM
 __global__ void __launch_bounds__(256) laf_kmax_kernel(const __nv_bfloat16* __restrict__ xn,
                                                        const __nv_bfloat16* __restrict__ W, float* __restrict__ part,
                                                        int N, int rows_per_chunk) {
@@ -173,7 +174,7 @@ struct LfcCfg {
     static constexpr size_t SMEM = (size_t)LM_HEADS * STAGES * STAGE_ELEMS * 2 + (size_t)LM_HEADS * 2 * LM_D * 4;
 };
 template <int MODE>
-__global__ void __launch_bounds__(256) laf_ctx_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __restrict__ W,
+__global__ void __launch_bounds__(256, 2) laf_ctx_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __restrict__ W,
                                                       const __nv_bfloat16* __restrict__ dout, const float* __restrict__ part,
                                                       int n_stat_chunks, float* __restrict__ kmax, float* __restrict__ kzinv,
                                                       float* __restrict__ ctx, int N, int chunk_px, float scale) {
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__(256) laf_ctx_kernel(const __nv_bfloat16* __res
 }
 
 // ---- out[n,h,e] = sum_d softmax_d(q[n,:])[d] * s * ctx[h][d][e],  q projected from xn --------------------------------
-constexpr int LFO_STAGES = 4;
+constexpr int LFO_STAGES = 2;      // 61 KB per CTA: three CTAs (24 warps) per SM -- ncu (r02): the kernel is bound by
+                                   // fixed-latency dependencies (stall_wait 2.0 per issue at 16 warps per SM)
 __global__ void __launch_bounds__(256) laf_out_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __restrict__ W,
                                                       const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out, int N,
                                                       int chunk_px, float scale) {
@@ -559,7 +561,7 @@ static int laf_chunk_px(int B, int N, int ctas_per_sm) {
 static int laf_stat_chunks(int N) {
     int c = N / 128;
     if (c < 1) c = 1;
-    if (c > 32) c = 32;
+    if (c > 16) c = 16;                 // B * chunks CTAs: one wave at batch 32
     return c;
 }
 
@@ -592,7 +594,7 @@ extern "C" int pidm_linattn_fused_fwd(const void* xn, const void* w_qkv, void* o
     PIDM_CUDA(launch_pdl(laf_ctx_kernel<0>, dim3(dim3((N + cpx - 1) / cpx, B)), dim3(256), (size_t)(LfcCfg<0>::SMEM), st, x, w, nullptr, workspace, chunks, kmax, kzinv,
                                                                              ctx, N, cpx, scale));
     PIDM_CUDA(launch_pdl(laf_finalize_kernel, dim3((B * LM_HID + 7) / 8), dim3(256), (size_t)(0), st, ctx, kzinv, B * LM_HID));
-    const int opx = laf_chunk_px(B, N, 2);
+    const int opx = laf_chunk_px(B, N, 3);
     PIDM_CUDA(launch_pdl(laf_out_kernel, dim3(dim3((N + opx - 1) / opx, B)), dim3(256), (size_t)(LAF_OUT_SMEM), st, x, w, ctx, (__nv_bfloat16*)out, N, opx, scale));
     PIDM_LAUNCH_CHECK("linattn_fused_fwd");
     return 0;

@@ -376,6 +376,86 @@ __global__ void head_bwd_kernel(const T* __restrict__ x, const float* __restrict
     if (threadIdx.x < O) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
 }
 
+// Same backward, lanes laid out over (pixel, channel octet): a warp instruction moves whole 16-byte octets of C/8-lane
+// pixel rows (8 pixels x 64 B at C = 32: fully coalesced), a thread keeps the weight-gradient partials of ITS octet in
+// registers over all its pixels and the lanes that share an octet are combined ONCE at the end (log2(32 / LPP) shuffles
+// per value) -- the kernel above reduces every (o, c) product over the warp for every 32 pixels (320 shuffles + 64
+// shared-memory atomics per warp iteration: 25 us for the 9 MB head of the Darcy model; this one is a streaming pass).
+// Requires LPP = C / 8 to be a power of two <= 32.
+template <typename T, int O>
+__global__ void __launch_bounds__(256) head_bwd_octet_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ y, const float* __restrict__ dy,
+                                                             T* __restrict__ dx, float* __restrict__ dw,
+                                                             float* __restrict__ db, int C, int HW, long long M,
+                                                             int sigmoid_last) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float sm[];   // sdw[O*C] | sdb[O]
+    float* sdw = sm;
+    float* sdb = sm + O * C;
+    for (int i = threadIdx.x; i < O * C + O; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int lpp = C >> 3;                                  // lanes per pixel
+    const int q = threadIdx.x & (lpp - 1);                   // this thread's octet (blockDim % lpp == 0)
+    float wq[O][8], acc[O][8], accb[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+        accb[o] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wq[o][k] = w[o * C + q * 8 + k]; acc[o][k] = 0.f; }
+    }
+    const long long items = M * lpp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / lpp;                         // lpp is a power of two: shifts
+        const long long b = m / HW;
+        const int hw = (int)(m - b * HW);
+        float dz[O];
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            float g = dy[(b * O + o) * HW + hw];
+            if (sigmoid_last && o == O - 1) {
+                const float sgm = y[(b * O + o) * HW + hw];
+                g *= sgm * (1.f - sgm);
+            }
+            dz[o] = g;
+        }
+        float v[8], d[8];
+        ld8(x + m * C + q * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float a = 0.f;
+#pragma unroll
+            for (int o = 0; o < O; ++o) { a += dz[o] * wq[o][k]; acc[o][k] += dz[o] * v[k]; }
+            d[k] = a;
+        }
+        st8(dx + m * C + q * 8, d);
+        if (q == 0) {
+#pragma unroll
+            for (int o = 0; o < O; ++o) accb[o] += dz[o];
+        }
+    }
+    // lanes with equal q: lane bits >= log2(lpp)
+    for (int off = lpp; off < 32; off <<= 1) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            accb[o] += __shfl_xor_sync(0xffffffffu, accb[o], off);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[o][k] += __shfl_xor_sync(0xffffffffu, acc[o][k], off);
+        }
+    }
+    if ((threadIdx.x & 31) < lpp) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&sdw[o * C + q * 8 + k], acc[o][k]);
+            if (q == 0) atomicAdd(&sdb[o], accb[o]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < O * C; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+    if (threadIdx.x < O) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
+}
+
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
     long long g = (n + block - 1) / block;
     if (g > cap) g = cap;
@@ -533,6 +613,17 @@ extern "C" int pidm_head_bwd(const void* x, const float* w, const float* y, cons
     PIDM_REQUIRE(C % 8 == 0 && O >= 1 && O <= 4, "head: C%%8==0 and 1<=O<=4 required (C=%d O=%d)", C, O);
     long long M = (long long)B * HW;
     size_t smem = (size_t)(2 * O * C + O) * sizeof(float);
+    const int lpp = C / 8;
+    if (lpp <= 32 && (lpp & (lpp - 1)) == 0) {
+        const long long items = M * lpp;
+#define HEAD_BO(OO)                                                                                    \
+    PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(head_bwd_octet_kernel<T, OO>, dim3(grid_for(items, 256, 148 * 4)), dim3(256), (size_t)(smem), (cudaStream_t)stream, \
+                                   (const T*)x, w, y, dy, (T*)dx, dw, db, C, HW, M, sigmoid_last)))
+        switch (O) { case 1: HEAD_BO(1); break; case 2: HEAD_BO(2); break; case 3: HEAD_BO(3); break; default: HEAD_BO(4); }
+#undef HEAD_BO
+        PIDM_LAUNCH_CHECK("head_bwd");
+        return 0;
+    }
 #define HEAD_B(OO)                                                                                     \
     PIDM_DISPATCH_DTYPE(dtype, PIDM_CUDA(launch_pdl(head_bwd_kernel<T, OO>, dim3(grid_for(M, 256, 148 * 2)), dim3(256), (size_t)(smem), (cudaStream_t)stream, \
                                    (const T*)x, w, y, dy, (T*)dx, dw, db, C, HW, M, sigmoid_last)))

@@ -102,8 +102,9 @@ struct MlpEntry {
 };
 
 constexpr int MLP_BCHUNK = 32;      // samples per pass = lanes of a warp
-constexpr int MLP_ROWS = 32;        // output rows per CTA (fwd / wgrad)
-constexpr int MLP_DG_ROWS = 128;    // rows per CTA (dgrad)
+constexpr int MLP_ROWS = 8;         // output rows per CTA (fwd / wgrad): one per warp -- the problem is latency-bound,
+                                    // ~500 small CTAs finish in one batch of weight loads each
+constexpr int MLP_DG_ROWS = 32;     // rows per CTA (dgrad)
 
 // out[b, j] = bias[j] + W[j,:] . s[b,:].  grid (entries, row chunks of MLP_ROWS), 256 threads.  A warp owns a row j,
 // its lanes are 32 samples: W[j,k] is one broadcast load per k, s[b,k] comes from a (td+1)-padded shared tile, and
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) block_mlps_fwd_kernel(const MlpEntry* __r
         for (int j = r0 + warp; j < r1; j += nw) {
             const float4* wr = reinterpret_cast<const float4*>(e.W + (size_t)j * td);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
+#pragma unroll 16
             for (int k4 = 0; k4 < td / 4; ++k4) {
                 const float4 w = __ldg(wr + k4);
                 a0 += w.x * sl[4 * k4]; a1 += w.y * sl[4 * k4 + 1]; a2 += w.z * sl[4 * k4 + 2]; a3 += w.w * sl[4 * k4 + 3];
@@ -186,54 +187,51 @@ __global__ void __launch_bounds__(256) block_mlps_wgrad_kernel(const MlpEntry* _
     }
 }
 
-// d_s[b,k] += sum_e sum_j dout_e[b,j] W_e[j,k].  grid (MLP_DG_GROUPS, sample chunks of 32), block td.  The 128-row chunks
-// of all entries form one list; CTA g takes every MLP_DG_GROUPS-th chunk and keeps 32 sample accumulators per thread
-// (thread = k) across its chunks: W rows are read once (coalesced over k), dout comes from shared memory as broadcast
-// float4 reads, and only ONE atomicAdd per (sample, k) and CTA is issued at the end.  ds zeroed by the caller.
-constexpr int MLP_DG_GROUPS = 37;       // x sample chunks: a quarter of the SMs -- the whole problem is ~20 MFLOP
-__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, int n_entries, float* __restrict__ ds,
-                                        int B, int td) {
+// d_s[b,k] += sum_e sum_j dout_e[b,j] W_e[j,k].  grid (entries, row chunks of MLP_DG_ROWS, sample chunks of 32), block td.
+// Thread = k keeps 32 sample accumulators; W rows are read once (coalesced over k), dout comes from shared memory as
+// broadcast float4 reads, one atomicAdd per (sample, k) and CTA at the end.  ds zeroed by the caller.  (The first version
+// gave each of 37 CTAs a 128-row chunk found by scanning the table: 18 dependent table loads + 16 serial batches of
+// weight loads per CTA = 27 us for a 30 MFLOP problem; now ~120 CTAs with 4 batches each, addressed directly.)
+__global__ void block_mlps_dgrad_kernel(const MlpEntry* __restrict__ table, float* __restrict__ ds, int B, int td) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) float sd[MLP_DG_ROWS][MLP_BCHUNK];
-    const int b0 = blockIdx.y * MLP_BCHUNK;
+    const MlpEntry e = table[blockIdx.x];
+    const int r0 = blockIdx.y * MLP_DG_ROWS;
+    if (r0 >= e.n) return;
+    const int nr = min(MLP_DG_ROWS, e.n - r0);
+    const int b0 = blockIdx.z * MLP_BCHUNK;
     const int nb = min(MLP_BCHUNK, B - b0);
     const int k = threadIdx.x;
+    for (int i = threadIdx.x; i < nr * MLP_BCHUNK; i += blockDim.x) {
+        const int b = i / nr, j = i - b * nr;      // consecutive threads walk j: coalesced reads of dout[b, r0 + j]
+        sd[j][b] = b < nb ? e.dout[(size_t)(b0 + b) * e.n + r0 + j] : 0.f;
+    }
     float acc[MLP_BCHUNK];
 #pragma unroll
     for (int b = 0; b < MLP_BCHUNK; ++b) acc[b] = 0.f;
-    int chunk_id = 0;
-    for (int ei = 0; ei < n_entries; ++ei) {
-        const MlpEntry e = table[ei];
-        for (int r0 = 0; r0 < e.n; r0 += MLP_DG_ROWS, ++chunk_id) {
-            if (chunk_id % MLP_DG_GROUPS != (int)blockIdx.x) continue;      // block-uniform
-            const int nr = min(MLP_DG_ROWS, e.n - r0);
-            __syncthreads();
-            for (int i = threadIdx.x; i < nr * MLP_BCHUNK; i += blockDim.x) {
-                const int b = i / nr, j = i - b * nr;      // consecutive threads walk j: coalesced reads of dout[b, r0 + j]
-                sd[j][b] = b < nb ? e.dout[(size_t)(b0 + b) * e.n + r0 + j] : 0.f;
-            }
-            __syncthreads();
-            const float* wp = e.W + (size_t)r0 * td + k;
-            // 8 weight rows are fetched before they are used: the loop is bound by the latency of these loads, not by
-            // the 32 FMAs per row
-            for (int j0 = 0; j0 < nr; j0 += 8) {
-                float w8[8];
+    const float* wp = e.W + (size_t)r0 * td + k;
+    float w8[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w8[u] = (j0 + u < nr) ? __ldg(wp + (size_t)(j0 + u) * td) : 0.f;
+    for (int u = 0; u < 8; ++u) w8[u] = (u < nr) ? __ldg(wp + (size_t)u * td) : 0.f;      // in flight across the barrier
+    __syncthreads();
+    for (int j0 = 0; j0 < nr; j0 += 8) {
+        float wn[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (j0 + u >= nr) break;
-                    const float w = w8[u];
-                    const float4* dj = reinterpret_cast<const float4*>(sd[j0 + u]);
+        for (int u = 0; u < 8; ++u) wn[u] = (j0 + 8 + u < nr) ? __ldg(wp + (size_t)(j0 + 8 + u) * td) : 0.f;
 #pragma unroll
-                    for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
-                        const float4 d = dj[q];
-                        acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
-                    }
-                }
+        for (int u = 0; u < 8; ++u) {
+            if (j0 + u >= nr) break;
+            const float w = w8[u];
+            const float4* dj = reinterpret_cast<const float4*>(sd[j0 + u]);
+#pragma unroll
+            for (int q = 0; q < MLP_BCHUNK / 4; ++q) {
+                const float4 d = dj[q];
+                acc[4 * q] += d.x * w; acc[4 * q + 1] += d.y * w; acc[4 * q + 2] += d.z * w; acc[4 * q + 3] += d.w * w;
             }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w8[u] = wn[u];
     }
 #pragma unroll
     for (int b = 0; b < MLP_BCHUNK; ++b)
@@ -312,8 +310,8 @@ extern "C" int pidm_block_mlps_bwd(const void* table_dev, int n_entries, int max
     }
     if (parts & 2) {
         PIDM_CUDA(cudaMemsetAsync(d_silu_t, 0, (size_t)B * td * sizeof(float), st));
-        dim3 dgrid(MLP_DG_GROUPS, ceil_div(B, MLP_BCHUNK));
-        PIDM_CUDA(launch_pdl(block_mlps_dgrad_kernel, dim3(dgrid), dim3(td), (size_t)(0), st, (const MlpEntry*)table_dev, n_entries, d_silu_t, B, td));
+        dim3 dgrid(n_entries, ceil_div(max_rows, MLP_DG_ROWS), ceil_div(B, MLP_BCHUNK));
+        PIDM_CUDA(launch_pdl(block_mlps_dgrad_kernel, dim3(dgrid), dim3(td), (size_t)(0), st, (const MlpEntry*)table_dev, d_silu_t, B, td));
     }
     PIDM_LAUNCH_CHECK("block_mlps_bwd");
     return 0;

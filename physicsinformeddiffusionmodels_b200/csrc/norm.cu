@@ -696,6 +696,9 @@ extern "C" int pidm_groupnorm_silu_fwd(const void* x, const float* gamma, const 
         int ach = ceil_div(HW, rpp * GN_APPLY_UNR);
         for (int u = GN_APPLY_UNR; u > 1 && (long long)B * ach < 148 * 2; u /= 2) ach = ceil_div(HW, rpp * (u / 2));
         while (ach > 1 && (long long)B * ach > 148 * 8) ach = (ach + 1) / 2;
+        // ~123 registers: two CTAs per SM are resident.  Between one and two waves the second wave runs mostly empty
+        // (ncu r02: 512 CTAs = 1.73 waves at 64x64x32, batch 32): size the grid to one wave and let the CTAs loop
+        if ((long long)B * ach > 148 * 2 && (long long)B * ach < 148 * 4 && B <= 148 * 2) ach = (148 * 2) / B;
         PIDM_CUDA(launch_pdl(gn_apply_kernel<T>, dim3(ach, B), dim3(NORM_THREADS), 0, st, (const T*)x, (const float*)sums,
                              gamma, beta, scale_shift, (const T*)residual, (T*)y, HW, C, G, eps));
     });

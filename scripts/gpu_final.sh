@@ -18,9 +18,9 @@ cap() {   # cap <file tag> <demangled-name regex> <skip> <count>
   timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 -f \
       -o gpurun_out/${TAG}_prof_$1 $B > gpurun_out/${TAG}_prof_$1.log 2>&1; echo "ncu $1 rc=$?"
 }
-cap conv_32_64 'conv_tc_kernel<32, 64>' 250 2
-cap conv_32_32 'conv_tc_kernel<32, 32>' 90 2
-cap conv_64_64 'conv_tc_kernel<64, 64>' 55 1
+cap conv_32_64 'conv_tc_kernel<.int.32, .int.64>' 250 2
+cap conv_32_32 'conv_tc_kernel<.int.32, .int.32>' 90 2
+cap conv_64_64 'conv_tc_kernel<.int.64, .int.64>' 55 1
 cap wgrad3 'wgrad3_kernel' 60 2
 cap gn_bwd_piece 'gn_bwd_piece_kernel' 120 3
 cap gn_apply 'gn_apply_kernel' 120 1
