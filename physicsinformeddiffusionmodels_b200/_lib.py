@@ -39,6 +39,8 @@ _SIGS = {
     'pidm_split_channels': [P, P, P, L, I, I, I, P],
     'pidm_pack_entry_size': [],
     'pidm_pack_weights': [P, I, I, P],
+    'pidm_pack_pair_entry_size': [],
+    'pidm_pack_weights_pairs': [P, P, I, I, I, P],
     'pidm_conv2d_simt': [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     'pidm_conv2d_wgrad_simt': [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, L, L, I, P],
     'pidm_conv2d_tc': [P, P, P, P, P, I, I, I, I, I, I, I, I, P],
@@ -79,7 +81,7 @@ _SIGS = {
     'pidm_version': [],
 }
 # functions whose int return value is a result, not an error code
-_VALUE_RETURN = {'pidm_pack_entry_size', 'pidm_mlp_entry_size', 'pidm_linattn_workspace_floats', 'pidm_version',
+_VALUE_RETURN = {'pidm_pack_entry_size', 'pidm_pack_pair_entry_size', 'pidm_mlp_entry_size', 'pidm_linattn_workspace_floats', 'pidm_version',
                  'pidm_linattn_fused_supported', 'pidm_linattn_fused_workspace_floats',
                  'pidm_conv2d_tc_supported', 'pidm_conv2d_wgrad_tc_supported', 'pidm_conv2d_tc_general_supported'}
 

@@ -219,6 +219,97 @@ __global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
     }
 }
 
+// ---- weight packing, both operand variants from ONE read ---------------------------------------------------------
+// For layers with Cin, Cout multiples of 32 and <= 16 taps a CTA owns a 32 (co) x 32 (ci) x taps block of the fp32
+// master weights: it reads the block as 32 contiguous runs of 32 * taps floats, keeps it in shared memory in the
+// activation dtype and writes the forward operand Wp_f[co][tap * Cin + ci] and the dgrad operand
+// Wp_d[ci][tap' * Cout + co] (tap' = taps - 1 - tap for stride-1 layers) as 64 / 128-byte row segments.  The generic
+// kernel above reads every source element twice with a stride of `taps` floats between neighbouring threads
+// (68 us per step for 10.4 M parameters); this one moves 41.5 MB in and 2 x 20.8 MB out once.
+struct PackPairEntry {
+    const float* src;
+    void* dst_f;
+    void* dst_d;             // null: no dgrad operand
+    long long s_co, s_ci;    // src index = co * s_co + ci * s_ci + tap; the inner one equals taps
+    int Cout, Cin, taps, flip;
+    int tile0, pad_;         // index of this entry's first 32 x 32 block in the launch's block list
+};
+
+template <typename T>
+__device__ __forceinline__ void pack_store2(T* p, T a, T b);
+template <>
+__device__ __forceinline__ void pack_store2<__nv_bfloat16>(__nv_bfloat16* p, __nv_bfloat16 a, __nv_bfloat16 b) {
+    __nv_bfloat162 v; v.x = a; v.y = b;
+    *reinterpret_cast<__nv_bfloat162*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void pack_store2<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <typename T>
+__device__ __forceinline__ T pack_cvt(float v);
+template <>
+__device__ __forceinline__ __nv_bfloat16 pack_cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ float pack_cvt<float>(float v) { return v; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_pair_kernel(const PackPairEntry* __restrict__ table,
+                                                        const int* __restrict__ tile_map /*[n_tiles] -> entry*/) {
+    extern __shared__ __align__(16) unsigned char pack_raw[];
+    T* tile = reinterpret_cast<T*>(pack_raw);        // [32 co][32 ci][taps], pitches p_i (odd) and p_o = 32 * p_i + 2
+    const PackPairEntry e = table[tile_map[blockIdx.x]];
+    const int local = (int)blockIdx.x - e.tile0;
+    const int tiles_ci = e.Cin >> 5;
+    const int co0 = (local / tiles_ci) << 5, ci0 = (local % tiles_ci) << 5;
+    const int taps = e.taps, run = 32 * taps, total = 32 * run;
+    const int p_i = taps | 1, p_o = 32 * p_i + 2;
+    // x / taps and x / run by multiply-high with a rounded-up reciprocal (exact for x * d < 2^32): with plain integer
+    // divisions the index arithmetic (~35 instructions each, 4-5 per element) cost 3x the memory time of the whole kernel
+    const uint32_t inv_taps = (uint32_t)(((1ull << 32) + (uint32_t)taps - 1) / (uint32_t)taps);
+    const uint32_t inv_run = (uint32_t)(((1ull << 32) + (uint32_t)run - 1) / (uint32_t)run);
+    auto div_taps = [&](int x) { return taps == 1 ? x : (int)__umulhi((uint32_t)x, inv_taps); };
+    auto div_run = [&](int x) { return (int)__umulhi((uint32_t)x, inv_run); };
+    const bool ci_inner = e.s_ci == (long long)taps;   // Conv layout [co][ci][tap]; otherwise ConvTranspose [ci][co][tap]
+    const long long s_outer = ci_inner ? e.s_co : e.s_ci;
+    const float* src0 = e.src + (long long)(ci_inner ? co0 : ci0) * s_outer + (long long)(ci_inner ? ci0 : co0) * taps;
+    // 32 runs of 32 * taps contiguous floats; eight loads in flight per thread (a plain loop serialises on the load latency)
+    for (int base = threadIdx.x; base < total; base += 8 * 256) {
+        float v[8];
+        int uu[8], rr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base + q * 256;
+            uu[q] = div_run(idx);
+            rr[q] = idx - uu[q] * run;
+            v[q] = idx < total ? __ldg(src0 + (long long)uu[q] * s_outer + rr[q]) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (base + q * 256 < total) {
+                const int w = div_taps(rr[q]), t = rr[q] - w * taps;
+                tile[ci_inner ? (uu[q] * p_o + w * p_i + t) : (w * p_o + uu[q] * p_i + t)] = pack_cvt<T>(v[q]);
+            }
+        }
+    }
+    __syncthreads();
+    T* df = reinterpret_cast<T*>(e.dst_f);
+    for (int idx = threadIdx.x; idx < run * 16; idx += 256) {            // (co, tap) rows of 32 ci: 16 pairs each
+        const int i2 = idx & 15, r = idx >> 4;
+        const int o = div_taps(r), t = r - o * taps;
+        const T* sp = tile + o * p_o + (2 * i2) * p_i + t;
+        pack_store2<T>(df + (size_t)(co0 + o) * ((size_t)taps * e.Cin) + (size_t)t * e.Cin + ci0 + 2 * i2, sp[0], sp[p_i]);
+    }
+    if (e.dst_d != nullptr) {
+        T* dd = reinterpret_cast<T*>(e.dst_d);
+        for (int idx = threadIdx.x; idx < run * 16; idx += 256) {        // (ci, tap) rows of 32 co
+            const int o2 = idx & 15, r = idx >> 4;
+            const int i = div_taps(r), t = r - i * taps;
+            const int td = e.flip ? taps - 1 - t : t;
+            const T* sp = tile + (2 * o2) * p_o + i * p_i + t;
+            pack_store2<T>(dd + (size_t)(ci0 + i) * ((size_t)taps * e.Cout) + (size_t)td * e.Cout + co0 + 2 * o2, sp[0], sp[p_o]);
+        }
+    }
+}
+
 static int check_geom(const ConvGeom& g) {
     PIDM_REQUIRE(g.Cin % 4 == 0 && g.Cout % 4 == 0, "conv: Cin and Cout must be multiples of 4 (Cin=%d Cout=%d)", g.Cin,
                  g.Cout);
@@ -278,3 +369,24 @@ extern "C" int pidm_pack_weights(const void* table_dev, int n_entries, int dtype
 }
 
 extern "C" int pidm_pack_entry_size(void) { return (int)sizeof(PackEntry); }
+
+// table: device array of PackPairEntry records (Cin % 32 == 0, Cout % 32 == 0, taps <= 16); tile_map[i] = entry that owns
+// the i-th 32 x 32 channel block (entry e owns blocks [tile0, tile0 + (Cout / 32) * (Cin / 32))); max_taps over the table.
+extern "C" int pidm_pack_weights_pairs(const void* table_dev, const int* tile_map_dev, int n_tiles, int max_taps, int dtype,
+                                       void* stream) {
+    if (n_tiles <= 0) return 0;
+    PIDM_REQUIRE(max_taps >= 1 && max_taps <= 16, "pack_weights_pairs: taps must be 1..16 (got %d)", max_taps);
+    const size_t esz = dtype == PIDM_BF16 ? 2 : 4;
+    const size_t smem = (size_t)32 * (32 * (max_taps | 1) + 2) * esz;
+    static bool attr = false;
+    if (!attr) {
+        PIDM_CUDA(cudaFuncSetAttribute(pack_pair_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 17 + 2) * 4));
+        attr = true;
+    }
+    PIDM_DISPATCH_DTYPE(dtype, (pack_pair_kernel<T><<<n_tiles, 256, smem, (cudaStream_t)stream>>>((const PackPairEntry*)table_dev,
+                                                                                                    tile_map_dev)));
+    PIDM_LAUNCH_CHECK("pack_weights_pairs");
+    return 0;
+}
+
+extern "C" int pidm_pack_pair_entry_size(void) { return (int)sizeof(PackPairEntry); }

@@ -130,6 +130,7 @@ struct TcParams {
     //   nb      B (weight) tiles consumed per K-step (KH in row-group mode, else 1)
     //   resident = 1: all weights of the CTA's (single) n-tile are loaded once into shared memory
     int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes;
+    int operand_bytes;       // resident weights + ring, rounded up to 1 KB: the barriers / epilogue staging follow it
     int m_tiles, n_tiles, n_classes;   // persistent tile walk: tile = (cls * n_tiles + nt) * m_tiles + mt
     const float* bias;
     const __nv_bfloat16* residual;
@@ -204,6 +205,7 @@ struct TcCfg {
 // persistent kernel, one CTA per SM: the operand ring takes (almost) all shared memory so that the TMA producers
 // run many K-steps (and tiles) ahead of the tensor pipe; latency is hidden by the ring, not by co-resident CTAs
 constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_RING_STAGES = 12;      // default ring depth (PIDM_TC_STAGES overrides)
 constexpr int TC_OPERAND_BYTES = 200 * 1024;                              // resident weights + ring
 constexpr int TC_SMEM_BYTES = TC_OPERAND_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
 
@@ -223,14 +225,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t pad_bytes = (1024 - (raw_addr & 1023)) & 1023;
     unsigned char* wres = smem_raw + pad_bytes;              // resident weights (res_bytes, may be 0)
     unsigned char* ring = wres + p.res_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pad_bytes + TC_OPERAND_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + pad_bytes + p.operand_bytes);
     uint64_t* full = bars;                                   // [TC_MAX_STAGES]
     uint64_t* empty = bars + TC_MAX_STAGES;                  // [TC_MAX_STAGES]
     uint64_t* acc_full = bars + 2 * TC_MAX_STAGES;           // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + Cfg::ACC_STAGES;        // [ACC_STAGES]
     uint64_t* wfull = acc_empty + Cfg::ACC_STAGES;           // resident weights have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
-    unsigned char* stage_base = smem_raw + pad_bytes + TC_OPERAND_BYTES + 512;   // 4 warps x 4 KB epilogue staging
+    unsigned char* stage_base = smem_raw + pad_bytes + p.operand_bytes + 512;   // 4 warps x 4 KB epilogue staging
     const int n_stages = p.stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -558,7 +560,7 @@ static EncodeTiledFn get_encode() {
 
 struct TcPlan {
     int TW, TH, TN, BN, BK;
-    int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes;
+    int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes, operand_bytes;
 };
 
 // GH x GW = pixel grid of the GEMM (output grid for regular convs, input grid for the transposed gather)
@@ -600,8 +602,12 @@ static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int KH, int KW, in
         int stages = (int)((TC_OPERAND_BYTES - (resident ? wbytes : 0)) / stage);
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         if (stages < 3) continue;
+        static int stage_cap = -1;                  // tuning aid: PIDM_TC_STAGES caps the ring depth
+        if (stage_cap < 0) { const char* ev = getenv("PIDM_TC_STAGES"); stage_cap = ev ? atoi(ev) : TC_RING_STAGES; }
+        if (stage_cap >= 3 && stages > stage_cap) stages = stage_cap;
         pl.BN = bn; pl.resident = resident; pl.res_bytes = resident ? (int)wbytes : 0;
         pl.stage_bytes = stage; pl.stages = stages;
+        pl.operand_bytes = (int)(((resident ? wbytes : 0) + (long long)stages * stage + 1023) / 1024 * 1024);
         if (m_tiles * (Cout / bn) >= 148) break;    // widest tile that still fills the machine
     }
     return pl.BN != 0;
@@ -615,7 +621,8 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
                                        TC_SMEM_BYTES));
         attr = true;
     }
-    PIDM_CUDA(launch_pdl(conv_tc_kernel<BN, BK>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mx, mw, p));
+    const size_t smem = (size_t)p.operand_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
+    PIDM_CUDA(launch_pdl(conv_tc_kernel<BN, BK>, grid, dim3(TC_THREADS), smem, st, mx, mw, p));
     PIDM_LAUNCH_CHECK("conv2d_tc");
     return 0;
 }
@@ -655,7 +662,7 @@ static bool tc_geometry(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, 
     if (!tc_plan(B, p.GH, p.GW, Cin, Cout, KH, KW, p.mode, p.in_stride, classes, pl)) return false;
     p.TW = pl.TW; p.TH = pl.TH; p.TN = pl.TN; p.tiles_h = p.GH / pl.TH; p.tiles_w = p.GW / pl.TW;
     p.rg = pl.rg; p.nb = pl.nb; p.a_bytes = pl.a_bytes; p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
-    p.resident = pl.resident; p.res_bytes = pl.res_bytes;
+    p.resident = pl.resident; p.res_bytes = pl.res_bytes; p.operand_bytes = pl.operand_bytes;
     return true;
 }
 

@@ -36,13 +36,33 @@ __global__ void time_embed_fwd_kernel(const long long* __restrict__ t, const flo
         emb[(size_t)b * dim + j] = v;
     }
     __syncthreads();
+    // thread j owns output row j: its weight row is read as 16-byte vectors, 16 loads in flight (the scalar loop issued
+    // td dependent-latency batches: 13 us for two 128-wide products)
     float acc = b1[j];
-    for (int k = 0; k < dim; ++k) acc += W1[(size_t)j * dim + k] * e[k];
+    {
+        const float4* wr = reinterpret_cast<const float4*>(W1 + (size_t)j * dim);
+        float a0 = 0.f, a1_ = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int k4 = 0; k4 < dim / 4; ++k4) {
+            const float4 w = __ldg(wr + k4);
+            a0 += w.x * e[4 * k4]; a1_ += w.y * e[4 * k4 + 1]; a2 += w.z * e[4 * k4 + 2]; a3 += w.w * e[4 * k4 + 3];
+        }
+        acc += (a0 + a1_) + (a2 + a3);
+    }
     h1[(size_t)b * td + j] = acc;
     a1[j] = gelu_erf(acc);
     __syncthreads();
     float o = b2[j];
-    for (int k = 0; k < td; ++k) o += W2[(size_t)j * td + k] * a1[k];
+    {
+        const float4* wr = reinterpret_cast<const float4*>(W2 + (size_t)j * td);
+        float a0 = 0.f, a1_ = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 16
+        for (int k4 = 0; k4 < td / 4; ++k4) {
+            const float4 w = __ldg(wr + k4);
+            a0 += w.x * a1[4 * k4]; a1_ += w.y * a1[4 * k4 + 1]; a2 += w.z * a1[4 * k4 + 2]; a3 += w.w * a1[4 * k4 + 3];
+        }
+        o += (a0 + a1_) + (a2 + a3);
+    }
     temb[(size_t)b * td + j] = o;
     silu_t[(size_t)b * td + j] = silu_f(o);
 }
@@ -63,8 +83,8 @@ __global__ void time_embed_bwd_act_kernel(const float* __restrict__ d_silu, cons
     __syncthreads();
     // da1[j] = sum_i dt[i] W2[i][j]  (column read: coalesced across threads j)
     float da = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < td; ++i) da += dt[i] * W2[(size_t)i * td + j];
+#pragma unroll 32
+    for (int i = 0; i < td; ++i) da += dt[i] * __ldg(W2 + (size_t)i * td + j);
     dh_out[(size_t)b * td + j] = da * gelu_erf_grad(h1[(size_t)b * td + j]);
 }
 
@@ -102,8 +122,8 @@ struct MlpEntry {
 };
 
 constexpr int MLP_BCHUNK = 32;      // samples per pass = lanes of a warp
-constexpr int MLP_ROWS = 8;         // output rows per CTA (fwd / wgrad): one per warp -- the problem is latency-bound,
-                                    // ~500 small CTAs finish in one batch of weight loads each
+constexpr int MLP_ROWS = 16;        // output rows per CTA (fwd / wgrad): two per warp.  The problem is latency-bound: ~240
+                                    // CTAs (one wave at two CTAs per SM) each pay one table + one tile + four weight batches
 constexpr int MLP_DG_ROWS = 32;     // rows per CTA (dgrad)
 
 // out[b, j] = bias[j] + W[j,:] . s[b,:].  grid (entries, row chunks of MLP_ROWS), 256 threads.  A warp owns a row j,
@@ -119,23 +139,44 @@ __global__ void __launch_bounds__(256) block_mlps_fwd_kernel(const MlpEntry* __r
     const int r0 = blockIdx.y * MLP_ROWS;
     if (r0 >= e.n) return;
     const int r1 = min(r0 + MLP_ROWS, e.n);
-    const int ld = td + 1;
+    const int ld = td + 1, tq = td >> 2;
     for (int b0 = 0; b0 < B; b0 += MLP_BCHUNK) {
         const int nb = min(MLP_BCHUNK, B - b0);
         __syncthreads();
-        for (int i = threadIdx.x; i < MLP_BCHUNK * td; i += blockDim.x) {
-            const int b = i / td, k = i - b * td;
-            ss[b * ld + k] = b < nb ? s[(size_t)(b0 + b) * td + k] : 0.f;
+        // the [32][td] input tile: 16-byte loads, four in flight per thread
+        for (int i0 = threadIdx.x; i0 < MLP_BCHUNK * tq; i0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x, b = i / tq, k4 = i - b * tq;
+                v[u] = (i < MLP_BCHUNK * tq && b < nb) ? __ldg(reinterpret_cast<const float4*>(s + (size_t)(b0 + b) * td) + k4)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x, b = i / tq, k4 = i - b * tq;
+                if (i < MLP_BCHUNK * tq) {
+                    float* d = ss + b * ld + 4 * k4;
+                    d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                }
+            }
         }
         __syncthreads();
         const float* sl = ss + lane * ld;
         for (int j = r0 + warp; j < r1; j += nw) {
             const float4* wr = reinterpret_cast<const float4*>(e.W + (size_t)j * td);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 16
-            for (int k4 = 0; k4 < td / 4; ++k4) {
-                const float4 w = __ldg(wr + k4);
-                a0 += w.x * sl[4 * k4]; a1 += w.y * sl[4 * k4 + 1]; a2 += w.z * sl[4 * k4 + 2]; a3 += w.w * sl[4 * k4 + 3];
+            for (int k0 = 0; k0 < tq; k0 += 16) {        // 16 weight vectors (one broadcast load each) in flight
+                float4 w[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) w[u] = (k0 + u < tq) ? __ldg(wr + k0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    if (k0 + u < tq) {
+                        const float* sp = sl + 4 * (k0 + u);
+                        a0 += w[u].x * sp[0]; a1 += w[u].y * sp[1]; a2 += w[u].z * sp[2]; a3 += w[u].w * sp[3];
+                    }
+                }
             }
             if (lane < nb) e.out[(size_t)(b0 + lane) * e.n + j] = (a0 + a1) + (a2 + a3) + __ldg(e.b + j);
         }
@@ -244,7 +285,7 @@ using namespace pidm;
 extern "C" int pidm_time_embed_fwd(const long long* t, const float* W1, const float* b1, const float* W2,
                                    const float* b2, float* emb, float* h1, float* temb, float* silu_t, int B, int dim,
                                    int td, void* stream) {
-    PIDM_REQUIRE(td <= 1024 && dim <= td && dim % 2 == 0 && dim >= 4, "time_embed: need 4<=dim<=td<=1024, dim even");
+    PIDM_REQUIRE(td <= 1024 && dim <= td && dim % 4 == 0 && td % 4 == 0 && dim >= 4, "time_embed: need 4<=dim<=td<=1024, dim and td multiples of 4");
     PIDM_CUDA(launch_pdl(time_embed_fwd_kernel, dim3(B), dim3(td), (size_t)((dim + td) * sizeof(float)), (cudaStream_t)stream, t, W1, b1, W2, b2, emb, h1, temb,
                                                                                       silu_t, dim, td));
     PIDM_LAUNCH_CHECK("time_embed_fwd");

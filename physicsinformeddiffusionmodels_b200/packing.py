@@ -13,6 +13,8 @@ from ._lib import call, stream
 
 _PACK_DT = np.dtype([('src', '<u8'), ('dst', '<u8'), ('s_n', '<i8'), ('s_c', '<i8'), ('N', '<i4'), ('C', '<i4'),
                      ('Cpad', '<i4'), ('taps', '<i4'), ('flip', '<i4'), ('pad_', '<i4')])
+_PAIR_DT = np.dtype([('src', '<u8'), ('dst_f', '<u8'), ('dst_d', '<u8'), ('s_co', '<i8'), ('s_ci', '<i8'), ('Cout', '<i4'),
+                     ('Cin', '<i4'), ('taps', '<i4'), ('flip', '<i4'), ('tile0', '<i4'), ('pad_', '<i4')])
 _MLP_DT = np.dtype([('W', '<u8'), ('b', '<u8'), ('dW', '<u8'), ('db', '<u8'), ('out', '<u8'), ('dout', '<u8'),
                     ('n', '<i4'), ('pad_', '<i4')])
 
@@ -68,6 +70,7 @@ class WeightPacker:
         self._table = None
         self._buf = None
         self._n = 0
+        self._n_pairs = 0
         self._packed_for = None
 
     def add(self, spec):
@@ -86,19 +89,40 @@ class WeightPacker:
             v = self._buf[off:off + n]
             off += (n + 127) // 128 * 128
             return v
+        pairs, tile_map = [], []
         for s in self.specs:
             s.wp_fwd = take(s.fwd_elems())
+            if s.need_dgrad:
+                s.wp_dgrad = take(s.dgrad_elems())
+            flip = 1 if (s.stride == 1 and not s.transposed) else 0
+            # layers with whole 32-channel blocks and <= 16 taps: both operands from one read (pidm_pack_weights_pairs);
+            # the rest (channel-padded stem / emb_conv, 7x7) through the generic strided kernel
+            if (s.cin == s.cin_real and s.cin % 32 == 0 and s.cout % 32 == 0 and s.taps <= 16
+                    and s.taps in (s.w_stride_n, s.w_stride_c)):
+                pairs.append((s.weight.data_ptr(), s.wp_fwd.data_ptr(), s.wp_dgrad.data_ptr() if s.need_dgrad else 0,
+                              s.w_stride_n, s.w_stride_c, s.cout, s.cin, s.taps, flip, len(tile_map), 0))
+                tile_map += [len(pairs) - 1] * ((s.cout // 32) * (s.cin // 32))
+                continue
             rows.append((s.weight.data_ptr(), s.wp_fwd.data_ptr(), s.w_stride_n, s.w_stride_c, s.cout, s.cin_real,
                          s.cin, s.taps, 0, 0))
             if s.need_dgrad:
-                s.wp_dgrad = take(s.dgrad_elems())
-                flip = 1 if (s.stride == 1 and not s.transposed) else 0
                 rows.append((s.weight.data_ptr(), s.wp_dgrad.data_ptr(), s.w_stride_c, s.w_stride_n, s.cin, s.cout,
                              s.cout, s.taps, flip, 0))
-        arr = np.array(rows, dtype=_PACK_DT)
-        assert arr.dtype.itemsize == call('pidm_pack_entry_size')
-        self._table, self._host = _to_device_bytes(arr, device)
         self._n = len(rows)
+        self._table = self._host = None
+        if rows:
+            arr = np.array(rows, dtype=_PACK_DT)
+            assert arr.dtype.itemsize == call('pidm_pack_entry_size')
+            self._table, self._host = _to_device_bytes(arr, device)
+        self._n_pairs = len(pairs)
+        self._pair_table = self._pair_host = None
+        if pairs:
+            arr = np.array(pairs, dtype=_PAIR_DT)
+            assert arr.dtype.itemsize == call('pidm_pack_pair_entry_size')
+            self._pair_table, self._pair_host = _to_device_bytes(arr, device)
+            self._pair_map, self._pair_map_host = _to_device_bytes(np.array(tile_map, dtype=np.int32), device)
+            self._pair_tiles = len(tile_map)
+            self._pair_taps = int(max(r[7] for r in pairs))
 
     def _versions(self, dtype):
         return (tuple(s.weight.data_ptr() for s in self.specs), tuple(s.weight._version for s in self.specs), dtype)
@@ -123,7 +147,11 @@ class WeightPacker:
         if key != self._key:
             self._build(w0.device, dtype)
             self._key = key
-        call('pidm_pack_weights', self._table, self._n, _lib.DTYPE_CODE[dtype], stream())
+        if self._n_pairs:
+            call('pidm_pack_weights_pairs', self._pair_table, self._pair_map, self._pair_tiles, self._pair_taps,
+                 _lib.DTYPE_CODE[dtype], stream())
+        if self._n:
+            call('pidm_pack_weights', self._table, self._n, _lib.DTYPE_CODE[dtype], stream())
         self._packed_for = self._versions(dtype)
 
 
