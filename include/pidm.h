@@ -103,10 +103,11 @@ int pidm_pack_weights(const void* table_dev, int n_entries, int dtype, void* str
  *   { const float* src; void* dst_f; void* dst_d (may be null); long long s_co, s_ci; int Cout, Cin, taps, flip;
  *     int tile0, pad_; }
  *   src index = co*s_co + ci*s_ci + tap;  dst_f[co][tap*Cin + ci];  dst_d[ci][(flip ? taps-1-tap : tap)*Cout + co]
- *   entry e owns blocks [tile0, tile0 + (Cout/32)*(Cin/32)); tile_map_dev[i] = index of the entry that owns block i. */
+ *   entry e owns blocks [tile0, tile0 + (Cout/32)*(Cin/32)); tile_map_dev[i] = index of the entry that owns block i;
+ *   one launch packs blocks [tile_base, tile_base + n_tiles). */
 int pidm_pack_pair_entry_size(void);
-int pidm_pack_weights_pairs(const void* table_dev, const int* tile_map_dev, int n_tiles, int max_taps, int dtype,
-                            void* stream);
+int pidm_pack_weights_pairs(const void* table_dev, const int* tile_map_dev, int tile_base, int n_tiles, int max_taps,
+                            int dtype, void* stream);
 /* y[b,oh,ow,n] = sum A(m,k) Wp[n,k] + bias[n] + residual;  transposed=0: A gathers x at (oh*s-p+r, ow*s-p+q);
  * transposed=1: at ((oh+p-r)/s, (ow+p-q)/s) when divisible (ConvTranspose forward / strided-conv dgrad).
  * CUDA-core fp32-accumulate kernel for every geometry (parity anchor + layers the tensor-core kernel skips). */

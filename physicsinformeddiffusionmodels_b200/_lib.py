@@ -40,7 +40,7 @@ _SIGS = {
     'pidm_pack_entry_size': [],
     'pidm_pack_weights': [P, I, I, P],
     'pidm_pack_pair_entry_size': [],
-    'pidm_pack_weights_pairs': [P, P, I, I, I, P],
+    'pidm_pack_weights_pairs': [P, P, I, I, I, I, P],
     'pidm_conv2d_simt': [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     'pidm_conv2d_wgrad_simt': [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, L, L, I, P],
     'pidm_conv2d_tc': [P, P, P, P, P, I, I, I, I, I, I, I, I, P],

@@ -253,11 +253,13 @@ __device__ __forceinline__ float pack_cvt<float>(float v) { return v; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_pair_kernel(const PackPairEntry* __restrict__ table,
-                                                        const int* __restrict__ tile_map /*[n_tiles] -> entry*/) {
+                                                        const int* __restrict__ tile_map /*[all tiles] -> entry*/,
+                                                        int tile_base) {
     extern __shared__ __align__(16) unsigned char pack_raw[];
     T* tile = reinterpret_cast<T*>(pack_raw);        // [32 co][32 ci][taps], pitches p_i (odd) and p_o = 32 * p_i + 2
-    const PackPairEntry e = table[tile_map[blockIdx.x]];
-    const int local = (int)blockIdx.x - e.tile0;
+    const int tile_id = (int)blockIdx.x + tile_base;
+    const PackPairEntry e = table[tile_map[tile_id]];
+    const int local = tile_id - e.tile0;
     const int tiles_ci = e.Cin >> 5;
     const int co0 = (local / tiles_ci) << 5, ci0 = (local % tiles_ci) << 5;
     const int taps = e.taps, run = 32 * taps, total = 32 * run;
@@ -372,8 +374,9 @@ extern "C" int pidm_pack_entry_size(void) { return (int)sizeof(PackEntry); }
 
 // table: device array of PackPairEntry records (Cin % 32 == 0, Cout % 32 == 0, taps <= 16); tile_map[i] = entry that owns
 // the i-th 32 x 32 channel block (entry e owns blocks [tile0, tile0 + (Cout / 32) * (Cin / 32))); max_taps over the table.
-extern "C" int pidm_pack_weights_pairs(const void* table_dev, const int* tile_map_dev, int n_tiles, int max_taps, int dtype,
-                                       void* stream) {
+// The launch packs blocks [tile_base, tile_base + n_tiles): a caller can pack the layers it needs first in a first launch.
+extern "C" int pidm_pack_weights_pairs(const void* table_dev, const int* tile_map_dev, int tile_base, int n_tiles, int max_taps,
+                                       int dtype, void* stream) {
     if (n_tiles <= 0) return 0;
     PIDM_REQUIRE(max_taps >= 1 && max_taps <= 16, "pack_weights_pairs: taps must be 1..16 (got %d)", max_taps);
     const size_t esz = dtype == PIDM_BF16 ? 2 : 4;
@@ -384,7 +387,7 @@ extern "C" int pidm_pack_weights_pairs(const void* table_dev, const int* tile_ma
         attr = true;
     }
     PIDM_DISPATCH_DTYPE(dtype, (pack_pair_kernel<T><<<n_tiles, 256, smem, (cudaStream_t)stream>>>((const PackPairEntry*)table_dev,
-                                                                                                    tile_map_dev)));
+                                                                                                    tile_map_dev, tile_base)));
     PIDM_LAUNCH_CHECK("pack_weights_pairs");
     return 0;
 }

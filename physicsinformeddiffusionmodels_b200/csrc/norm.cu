@@ -945,6 +945,8 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
                 // packed variant spills and is SLOWER than streaming (64x64x32: 15.5 -> 29 us), so those stay streaming
                 if (!keep && v <= 4 && packed_ok) {
                     PIDM_DISPATCH_DTYPE(dtype, { GN_PACKED_CASE(4); });
+                } else if (!keep && v <= 8 && packed_ok == 2) {      // PIDM_GN_PACKED=2: profiling aid
+                    PIDM_DISPATCH_DTYPE(dtype, { GN_PACKED_CASE(8); });
                 } else {
                     PIDM_DISPATCH_DTYPE(dtype, { GN_PIECE_CASE(1, true) else GN_PIECE_CASE(2, true) else GN_PIECE_CASE(2, false) });
                 }

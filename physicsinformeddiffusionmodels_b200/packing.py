@@ -90,7 +90,9 @@ class WeightPacker:
             off += (n + 127) // 128 * 128
             return v
         pairs, tile_map = [], []
+        self._tiles_before_spec = []           # number of pair tiles owned by the specs in front of spec i
         for s in self.specs:
+            self._tiles_before_spec.append(len(tile_map))
             s.wp_fwd = take(s.fwd_elems())
             if s.need_dgrad:
                 s.wp_dgrad = take(s.dgrad_elems())
@@ -138,21 +140,31 @@ class WeightPacker:
         if self.specs and self.stale(dtype):
             self.refresh(dtype)
 
-    def refresh(self, dtype):
-        """Re-pack all weights (one launch).  Rebuilds the table if parameters moved (e.g. .to(device))."""
+    def refresh(self, dtype, early_specs=0):
+        """Re-pack all weights.  Rebuilds the tables if parameters moved (e.g. .to(device)).
+        early_specs > 0: the operands of the first `early_specs` layers (registration order = execution order) are packed by
+        a first launch and a CUDA event recorded behind it is returned, so a consumer can start on them while the second
+        launch packs the rest; otherwise returns None."""
         if not self.specs:
-            return
+            return None
         w0 = self.specs[0].weight
         key = (tuple(s.weight.data_ptr() for s in self.specs), dtype)
         if key != self._key:
             self._build(w0.device, dtype)
             self._key = key
-        if self._n_pairs:
-            call('pidm_pack_weights_pairs', self._pair_table, self._pair_map, self._pair_tiles, self._pair_taps,
-                 _lib.DTYPE_CODE[dtype], stream())
+        code, event = _lib.DTYPE_CODE[dtype], None
         if self._n:
-            call('pidm_pack_weights', self._table, self._n, _lib.DTYPE_CODE[dtype], stream())
+            call('pidm_pack_weights', self._table, self._n, code, stream())
+        if self._n_pairs:
+            first = self._tiles_before_spec[early_specs] if 0 < early_specs < len(self.specs) else 0
+            if first > 0:
+                call('pidm_pack_weights_pairs', self._pair_table, self._pair_map, 0, first, self._pair_taps, code, stream())
+                event = torch.cuda.Event()
+                event.record(torch.cuda.current_stream())
+            call('pidm_pack_weights_pairs', self._pair_table, self._pair_map, first, self._pair_tiles - first, self._pair_taps,
+                 code, stream())
         self._packed_for = self._versions(dtype)
+        return event
 
 
 class MlpTable:

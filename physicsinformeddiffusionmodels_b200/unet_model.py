@@ -237,8 +237,11 @@ class Unet3D(nn.Module):
         def plan_la(res):
             conv(res.fn.fn.to_qkv, 1, 1, 0)
             conv(res.fn.fn.to_out, 1, 1, 0)
+        self._early_specs = 0
         for b1, b2, la, down in self.downs:
             plan_rb(b1); plan_rb(b2); plan_la(la)
+            if self._early_specs == 0:
+                self._early_specs = len(pk.specs)      # stem + first resolution level: packed by a first launch
             if not isinstance(down, nn.Identity):
                 conv(down, 4, 2, 1)
         plan_rb(self.mid_block1)
@@ -394,9 +397,10 @@ class Unet3D(nn.Module):
         # engine.TrainEngine invalidates explicitly because its optimizer kernel writes the flat buffer directly), so a
         # 250-step sampling loop packs once instead of 250 times.
         pack_stream = ops.fork_stream()
+        early_packed = None
         if torch.is_grad_enabled() or self._packer.stale(dt):
             with torch.cuda.stream(pack_stream):
-                self._packer.refresh(dt)
+                early_packed = self._packer.refresh(dt, early_specs=0 if exists(cond) else self._early_specs)
         # pre-zeroed scratch for the GroupNorm statistics that the conv epilogues accumulate (<= 64 norms)
         ops.zero_pool_begin(64 * (x.shape[0] * self.groups * 2 + 32), x.device)
         h = ops.nchw_to_nhwc(x.float(), self._cin_pad, dt)
@@ -405,7 +409,11 @@ class Unet3D(nn.Module):
             time = time.reshape(1).expand(x.shape[0])
         silu_t, _ = ops.time_embed(time, tm[1].weight, tm[1].bias, tm[3].weight, tm[3].bias)
         ss = ops.block_mlps(silu_t, self._mlp_table)
-        torch.cuda.current_stream().wait_stream(pack_stream)
+        # the stem and the first resolution level only need the first pack launch; the rest is joined below
+        if early_packed is not None:
+            torch.cuda.current_stream().wait_event(early_packed)
+        else:
+            torch.cuda.current_stream().wait_stream(pack_stream)
         h = self._conv(self.init_conv, h)
         if exists(cond):
             h = self._cond_embedding(h, cond, null_cond_prob)
@@ -418,6 +426,8 @@ class Unet3D(nn.Module):
             h = self._resblock(b2, h, ss)
             h = self._linear_attention(la, h)
             skips.append(h)
+            if lvl == 0 and early_packed is not None:
+                torch.cuda.current_stream().wait_stream(pack_stream)
             if not isinstance(down, nn.Identity):
                 h = self._conv(down, h)
         h = self._resblock(self.mid_block1, h, ss)
