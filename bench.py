@@ -180,7 +180,8 @@ def breakdown_one_step(engine, x0):
     """Per-entry-point device time of the libpidm calls of ONE step.  The calls (with their live operands) are recorded
     during an eager step; every distinct call is then timed by CUDA-graph replay with CUDA events on its stream
     (_graph_time_ms).  Calls that must not be repeated (the in-place optimizer update) keep the eager event time."""
-    from physicsinformeddiffusionmodels_b200 import _lib, ops, packing, denoising_utils, engine as eng_mod, residuals_darcy
+    from physicsinformeddiffusionmodels_b200 import (_lib, ops, packing, denoising_utils, engine as eng_mod, residuals_darcy,
+                                                     residuals_mechanics_K)
     records = []
     orig = _lib.call
 
@@ -193,7 +194,7 @@ def breakdown_one_step(engine, x0):
         e1.record()
         records.append((name, a, e0, e1))
         return r
-    mods = [ops, packing, denoising_utils, eng_mod]
+    mods = [mo for mo in (ops, packing, denoising_utils, eng_mod, residuals_darcy, residuals_mechanics_K) if hasattr(mo, 'call')]
     for mo in mods:
         mo.call = timed
     world = engine.world
@@ -337,6 +338,24 @@ def mechanics_bench(dev, pk, batch=32, steps=10, warmup=4):
          'trainable_parameters': n_params, 'ms_per_step': ms, 'samples_per_s': batch / (ms * 1e-3),
          'model_tflops_at_value': gf_sample * batch / (ms * 1e-3) / 1e3, 'last_loss': float(out[0].item()),
          'finite': bool(torch.isfinite(out[0]).item())}
+    try:      # the same convolution kernels at 128 .. 1024 channels: per-entry-point device time of one step
+        agg = breakdown_one_step(eng, inp)
+        peak = pk['bf16_sustained'] or pk['bf16_tflops']
+        conv = agg.get('pidm_conv2d_tc_general')
+        if conv and conv['flop']:
+            tf = conv['flop'] / (conv['ms'] * 1e-3) / 1e12
+            r['roofline_conv'] = {'bound': 'tensor', 'kernel': 'pidm_conv2d_tc_general (the convolution kernels of the headline '
+                                  'workload, here at 128-1024 channels)', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s',
+                                  'frac': tf / peak, 'ms': conv['ms'], 'launches_per_step': conv['calls'], 'traffic': None,
+                                  'how': 'as roofline.how: algorithmic FLOPs / CUDA-graph-replayed device time of every launch'}
+        tot = sum(v['ms'] for v in agg.values())
+        r['kernel_time_breakdown_ms'] = {k: {'ms': round(v['ms'], 4), 'calls': v['calls'],
+                                             'tflops': (v['flop'] / (v['ms'] * 1e-3) / 1e12) if v['flop'] else None}
+                                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:8]}
+        r['kernel_time_total_ms'] = tot
+    except Exception as ex:
+        r['roofline_conv'] = {'error': repr(ex)[:300]}
+    eng.close()
     del eng, model
     torch.cuda.empty_cache()
     # ---- residual kernel alone, B = 8192 (1.24 GB working set >> 126 MB L2)
@@ -441,6 +460,10 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)'
+    if world > 1:
+        # the secondary workloads and the CPU / stock-PyTorch baselines are single-GPU legs (reported at N = 1 only): at
+        # N > 1 the other ranks would sit in a barrier for minutes while rank 0 runs them
+        args.no_cpu_baseline = args.no_sampling = args.no_mechanics = args.no_torch_cuda_baseline = True
     ops.set_precision('bf16')
     torch.manual_seed(0)                              # identical initial weights on every rank
     model = Unet3D(dim=32, channels=2).to(dev)
