@@ -382,6 +382,9 @@ __global__ void __launch_bounds__(256) laf_out_kernel(const __nv_bfloat16* __res
 }
 
 // ---- backward per pixel: dq | dk | dv from xn, dout, ctx, dctx and the saved column statistics -------------------------
+// 217 registers (the nine loop-invariant 32x32 B-operand fragment sets live in registers): one CTA = 8 warps per SM.
+// Capping the kernel at 128 registers for two CTAs per SM was measured (round 2): ptxas spills ~70 fragment registers to
+// local memory and the 64x64 layer goes from 104 to 154 us -- occupancy does not pay for re-reading the operands.
 constexpr int LFB_ROWS = 16;
 constexpr int LFB_STAGES = 4;
 constexpr int LFB_STAGE_ELEMS = 2 * LFB_ROWS * LW_PITCH;          // xn tile | dout tile
