@@ -229,10 +229,7 @@ def breakdown_one_step(engine, x0):
         nbytes = 0.0
         detail.append((round(ms * 1e3, 1), name, [x for x in a if isinstance(x, int) and not isinstance(x, bool) and x < (1 << 24)][:14]))
         flop = 0.0
-        if name in ('pidm_conv2d_tc',):
-            B, H, W, Cin, Cout, KH, KW = a[5], a[6], a[7], a[8], a[9], a[10], a[11]
-            flop = 2.0 * B * H * W * Cout * KH * KW * Cin
-        elif name == 'pidm_conv2d_tc_general':
+        if name == 'pidm_conv2d_tc_general':
             B, Hin, Win, Cin, Ho, Wo, Cout, KH, KW, stride, tr = (a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13],
                                                                  a[14], a[16])
             taps = KH * KW / (stride * stride) if tr else KH * KW
@@ -537,7 +534,7 @@ def main():
         total_ms = sum(d['ms'] for d in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
         name, d = top[0]
-        tensor_names = ('pidm_conv2d_tc', 'pidm_conv2d_tc_general', 'pidm_conv2d_simt', 'pidm_conv2d_wgrad_simt',
+        tensor_names = ('pidm_conv2d_tc_general', 'pidm_conv2d_simt', 'pidm_conv2d_wgrad_simt',
                         'pidm_conv2d_wgrad_tc')
         if name in tensor_names and d['flop'] > 0:
             ach = d['flop'] / (d['ms'] * 1e-3) / 1e12
@@ -557,7 +554,7 @@ def main():
             tpath = next((os.path.join(prof, f) for f in ('r02_step_traffic.json', 'r01_step_traffic.json')
                           if os.path.exists(os.path.join(prof, f))), None)
             if tpath:
-                prefix = {'pidm_conv2d_tc_general': 'conv_tc_kernel', 'pidm_conv2d_tc': 'conv_tc_kernel',
+                prefix = {'pidm_conv2d_tc_general': 'conv_tc_kernel',
                           'pidm_conv2d_wgrad_tc': 'wgrad'}.get(name)
                 if prefix:
                     tr = json.load(open(tpath))

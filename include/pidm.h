@@ -118,14 +118,10 @@ int pidm_conv2d_simt(const void* x, const void* w_packed, const float* bias, con
 int pidm_conv2d_wgrad_simt(const void* x, const void* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
                            int Cin_real, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int transposed,
                            long long w_stride_n, long long w_stride_c, int dtype, void* stream);
-/* tcgen05 + TMA tile kernel: stride-1 KxK convolution (pad = K/2) / dgrad of it, bf16 operands, fp32 TMEM accumulate.
- * Same contract as pidm_conv2d_simt with stride=1, transposed=0; requires dtype=PIDM_BF16, Cin%16==0, Cout%16==0. */
-int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y, int B, int H,
-                   int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
-int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad);
 /* debugging aid: device buffer (>= 4096 int64) receiving a clock64 timeline of CTA 0 of every tensor-core conv launch */
 int pidm_debug_set_trace(void* buf);
-/* General tensor-core path: stride-1/2 regular convolution (input sampled through TMA elementStrides) and the
+/* tcgen05 + TMA implicit-GEMM convolution, bf16 operands, fp32 TMEM accumulation; same contract as pidm_conv2d_simt
+ * (requires Cin % 32 == 0, Cout % 32 == 0): stride-1/2 regular convolution (input sampled through TMA elementStrides) and the
  * stride-2 transposed gather (ConvTranspose forward / dgrad of the stride-2 conv) as 4 output-parity classes.
  * gn_sums (optional, [B, gn_groups, 2]): per-(sample, group) sum and sum of squares of the fp32 output, accumulated in
  * the epilogue so that the following GroupNorm needs no statistics pass.  It is zeroed here (one memset node) unless

@@ -747,17 +747,6 @@ extern "C" int pidm_debug_set_trace(void* buf) {
     return 0;
 }
 
-extern "C" int pidm_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad) {
-    TcParams p; TcPlan pl; int classes;
-    return (2 * pad == KH - 1 && tc_geometry(B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, p, pl, classes)) ? 1 : 0;
-}
-
-extern "C" int pidm_conv2d_tc(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
-                              int B, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
-    return tc_run(x, w_packed, bias, residual, y, B, H, W, Cin, H, W, Cout, KH, KW, 1, pad, 0, nullptr, 0, 0,
-                  (cudaStream_t)stream);
-}
-
 extern "C" int pidm_conv2d_tc_general_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
                                                 int stride, int pad, int transposed) {
     TcParams p; TcPlan pl; int classes;

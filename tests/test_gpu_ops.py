@@ -116,7 +116,7 @@ def test_conv_tcgen05_matches_reference(pk, case):
     ops, packing = pk
     from physicsinformeddiffusionmodels_b200._lib import call
     B, H, Cin, Cout, k, has_bias, has_res = case
-    assert call('pidm_conv2d_tc_supported', B, H, H, Cin, Cout, k, k, k // 2) == 1
+    assert call('pidm_conv2d_tc_general_supported', B, H, H, Cin, H, H, Cout, k, k, 1, k // 2, 0) == 1
     g = torch.Generator().manual_seed(2)
     x = (torch.randn(B, Cin, H, H, generator=g)).bfloat16().float()
     w = (torch.randn(Cout, Cin, 1, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16().float()
