@@ -293,6 +293,208 @@ __global__ void __launch_bounds__(NORM_THREADS, 2) gn_bwd_piece_packed_kernel(
     }
 }
 
+// The piece kernel for pieces of MORE than 4 vectors per thread (the 64x64 levels): x and dy are streamed twice (the second
+// pass hits L2).  Compared with gn_bwd_piece_kernel<T, 2, false>, which it replaces, the loops are written for instruction
+// count -- ncu (r02) shows that variant issue-bound as much as latency-bound: 29 instructions per element and phase, a third
+// of them 64-bit address arithmetic and predicate bookkeeping.  Here a thread walks its vectors with three running
+// pointers, per-channel constants are folded (xhat = x * rs - mr, z = xhat * A + Bc, dx = dz * Ap - m1p - xhat * m2p), the
+// next two vector pairs are fetched (raw, 16 registers) while the current two are processed, and the first pass parks dz in
+// the dx buffer (activation dtype) so that the second pass needs no SiLU' (it reads x and dz, overwrites dz with dx).
+// SiLU'(z) for the streaming kernel: bf16 activations take the one-MUFU form through tanh.approx (abs. error ~5e-4, below
+// the bf16 resolution of the stored result; the exp + rcp form costs two MUFU operations per element and the kernel is
+// bound by the XU pipe as much as by issue slots), fp32 activations keep the exact form.
+template <typename T> __device__ __forceinline__ float silu_grad_t(float z) { return silu_grad_f(z); }
+template <> __device__ __forceinline__ float silu_grad_t<__nv_bfloat16>(float z) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    const float sg = fmaf(0.5f, t, 0.5f);                 // sigmoid(z)
+    return sg * fmaf(z, fmaf(-0.5f, t, 0.5f), 1.f);       // s * (1 + z * (1 - s))
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS, 2) gn_bwd_piece_stream_kernel(
+        const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums, const float* __restrict__ gamma,
+        const float* __restrict__ beta, const float* __restrict__ ss, T* __restrict__ dx, float* __restrict__ dss,
+        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int HW, int C, int G, float eps,
+        int S /*channels per slab*/, int CL /*CTAs per (sample, slab)*/, int rows_per_cta) {
+    namespace cg = cooperative_groups;
+    constexpr int VE = Vec<T>::N, NH = VE / 4;
+    extern __shared__ float rsm[];
+    float* part = rsm;                 // [S][2] partial sums of this CTA
+    float* Sf = part + 2 * S;          // [S][2] sums over the whole (sample, slab)
+    float* gm = Sf + 2 * S;            // [S / cpg][2]
+    float* cs = gm + 2 * (S / (C / G));// [S] column sums of dx
+    const int cpg = C / G, so = S / VE, nslab = C / S;
+    const int piece = blockIdx.x / CL, rank = blockIdx.x - piece * CL;
+    const int b = piece / nslab, slab = piece - b * nslab;
+    const int c0 = slab * S;
+    const int o = threadIdx.x % so, r0 = threadIdx.x / so;
+    const int rpp = blockDim.x / so;
+    const int row_begin = rank * rows_per_cta;
+    const int row_end = min(HW, row_begin + rows_per_cta);
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 5 * S + 2 * (S / cpg); i += blockDim.x) rsm[i] = 0.f;
+    pdl_wait();
+    // vectors of this thread: rows row_begin + r0 + i * rpp, i = 0 .. nvec - 1
+    const int first = row_begin + r0;
+    const int nvec = first < row_end ? (row_end - first + rpp - 1) / rpp : 0;
+    const size_t off0 = (size_t)b * HW * C + c0 + (size_t)o * VE + (size_t)first * C;
+    const size_t vstride = (size_t)rpp * C;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    auto ldr = [](const T* p) { return *reinterpret_cast<const uint4*>(p); };
+    const T* xp = x + off0;
+    const T* dp = dy + off0;
+    uint4 cx0 = zero4, cd0 = zero4, cx1 = zero4, cd1 = zero4;
+    if (nvec > 0) { cx0 = ldr(xp); cd0 = ldr(dp); }
+    if (nvec > 1) { cx1 = ldr(xp + vstride); cd1 = ldr(dp + vstride); }
+    float A[VE], Bc[VE], rs[NH], mr[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        float m, r;
+        gn_mean_rstd(sums, b, (c0 + o * VE + 4 * h) / cpg, G, inv_n, eps, m, r);
+        rs[h] = r; mr[h] = m * r;
+    }
+#pragma unroll
+    for (int k = 0; k < VE; ++k) {
+        const int c = c0 + o * VE + k;
+        const float s1p = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        const float sh = ss ? ss[(size_t)b * 2 * C + C + c] : 0.f;
+        A[k] = gamma[c] * s1p; Bc[k] = beta[c] * s1p + sh;
+    }
+    // ---- phase 1: sums of dz and dz * xhat
+    float a1[VE], a2[VE];
+#pragma unroll
+    for (int k = 0; k < VE; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+    T* op = dx + off0;                                         // phase 1 parks dz here, phase 2 overwrites it with dx
+    for (int i = 0; i < nvec; i += 2) {
+        xp += 2 * vstride; dp += 2 * vstride;
+        uint4 nx0 = zero4, nd0 = zero4, nx1 = zero4, nd1 = zero4;
+        if (i + 2 < nvec) { nx0 = ldr(xp); nd0 = ldr(dp); }
+        if (i + 3 < nvec) { nx1 = ldr(xp + vstride); nd1 = ldr(dp + vstride); }
+        const bool two = i + 1 < nvec;
+        {
+            float xv[VE], dv[VE];
+            unpack_vec<T>(cx0, xv); unpack_vec<T>(cd0, dv);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) {
+                const float xh = fmaf(xv[k], rs[k >> 2], -mr[k >> 2]);
+                dv[k] *= silu_grad_t<T>(fmaf(xh, A[k], Bc[k]));
+                a1[k] += dv[k]; a2[k] = fmaf(dv[k], xh, a2[k]);
+            }
+            stv<T>(op, dv);
+        }
+        if (two) {
+            float xv[VE], dv[VE];
+            unpack_vec<T>(cx1, xv); unpack_vec<T>(cd1, dv);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) {
+                const float xh = fmaf(xv[k], rs[k >> 2], -mr[k >> 2]);
+                dv[k] *= silu_grad_t<T>(fmaf(xh, A[k], Bc[k]));
+                a1[k] += dv[k]; a2[k] = fmaf(dv[k], xh, a2[k]);
+            }
+            stv<T>(op + vstride, dv);
+        }
+        op += 2 * vstride;
+        cx0 = nx0; cd0 = nd0; cx1 = nx1; cd1 = nd1;
+    }
+    // the second pass re-reads x (L2) and the parked dz (written by this very thread): issue its first loads before the
+    // reduction chain
+    xp = x + off0;
+    const T* zp = dx + off0;
+    if (nvec > 0) { cx0 = ldr(xp); cd0 = ldr(zp); }
+    if (nvec > 1) { cx1 = ldr(xp + vstride); cd1 = ldr(zp + vstride); }
+    __syncthreads();                                           // zero-fill of the shared sums is complete
+    const bool pub1 = reduce_same_octet(a1, so);
+    reduce_same_octet(a2, so);
+    if (pub1) {
+#pragma unroll
+        for (int k = 0; k < VE; ++k) { atomicAdd(&part[(o * VE + k) * 2], a1[k]); atomicAdd(&part[(o * VE + k) * 2 + 1], a2[k]); }
+    }
+    if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) {
+            float t = 0.f;
+            for (int r = 0; r < CL; ++r) t += cluster.map_shared_rank(part, r)[i];
+            Sf[i] = t;
+        }
+        cluster.sync();
+    } else {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) Sf[i] = part[i];
+        __syncthreads();
+    }
+    for (int cl = threadIdx.x; cl < S; cl += blockDim.x) {
+        const int c = c0 + cl;
+        const float s1 = Sf[cl * 2], s2 = Sf[cl * 2 + 1];
+        const float f = ss ? ss[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        atomicAdd(&gm[(cl / cpg) * 2], gamma[c] * f * s1);
+        atomicAdd(&gm[(cl / cpg) * 2 + 1], gamma[c] * f * s2);
+        if (rank == 0) {
+            if (dss) {
+                dss[(size_t)b * 2 * C + c] = gamma[c] * s2 + beta[c] * s1;   // d scale
+                dss[(size_t)b * 2 * C + C + c] = s1;                          // d shift
+            }
+            atomicAdd(&dgamma[c], f * s2);
+            atomicAdd(&dbeta[c], f * s1);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: dx = rstd * (A dz - mean(A dz) - xhat mean(A dz xhat)), folded
+    float Ap[VE], m1p[NH], m2p[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        const int gl = (o * VE + 4 * h) / cpg;
+        m1p[h] = rs[h] * gm[gl * 2] * inv_n; m2p[h] = rs[h] * gm[gl * 2 + 1] * inv_n;
+    }
+#pragma unroll
+    for (int k = 0; k < VE; ++k) Ap[k] = rs[k >> 2] * A[k];
+    float colsum[VE];
+#pragma unroll
+    for (int k = 0; k < VE; ++k) colsum[k] = 0.f;
+    op = dx + off0;
+    for (int i = 0; i < nvec; i += 2) {
+        xp += 2 * vstride; zp += 2 * vstride;
+        uint4 nx0 = zero4, nd0 = zero4, nx1 = zero4, nd1 = zero4;
+        if (i + 2 < nvec) { nx0 = ldr(xp); nd0 = ldr(zp); }
+        if (i + 3 < nvec) { nx1 = ldr(xp + vstride); nd1 = ldr(zp + vstride); }
+        const bool two = i + 1 < nvec;
+        {
+            float xv[VE], dv[VE], g[VE];
+            unpack_vec<T>(cx0, xv); unpack_vec<T>(cd0, dv);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) {
+                const float xh = fmaf(xv[k], rs[k >> 2], -mr[k >> 2]);
+                g[k] = fmaf(-xh, m2p[k >> 2], fmaf(dv[k], Ap[k], -m1p[k >> 2]));
+                colsum[k] += g[k];
+            }
+            stv<T>(op, g);
+        }
+        if (two) {
+            float xv[VE], dv[VE], g[VE];
+            unpack_vec<T>(cx1, xv); unpack_vec<T>(cd1, dv);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) {
+                const float xh = fmaf(xv[k], rs[k >> 2], -mr[k >> 2]);
+                g[k] = fmaf(-xh, m2p[k >> 2], fmaf(dv[k], Ap[k], -m1p[k >> 2]));
+                colsum[k] += g[k];
+            }
+            stv<T>(op + vstride, g);
+        }
+        op += 2 * vstride;
+        cx0 = nx0; cd0 = nd0; cx1 = nx1; cd1 = nd1;
+    }
+    if (dbias) {
+        if (reduce_same_octet(colsum, so)) {
+#pragma unroll
+            for (int k = 0; k < VE; ++k) atomicAdd(&cs[o * VE + k], colsum[k]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < S; i += blockDim.x) atomicAdd(&dbias[c0 + i], cs[i]);
+    }
+}
+
 // backward pass 1: S[b][c][0] += sum_pix dz, S[b][c][1] += sum_pix dz*xhat, dz = dy * silu'(z)
 template <typename T>
 __global__ void gn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ sums,
@@ -947,6 +1149,12 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
                     PIDM_DISPATCH_DTYPE(dtype, { GN_PACKED_CASE(4); });
                 } else if (!keep && v <= 8 && packed_ok == 2) {      // PIDM_GN_PACKED=2: profiling aid
                     PIDM_DISPATCH_DTYPE(dtype, { GN_PACKED_CASE(8); });
+                } else if (!keep && packed_ok != 3) {               // PIDM_GN_PACKED=3: the round-1 streaming loops (A/B aid)
+                    PIDM_DISPATCH_DTYPE(dtype, {
+                        PIDM_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_piece_stream_kernel<T>, (const T*)x, (const T*)dy, sums, gamma,
+                                                     beta, scale_shift, (T*)dx, d_scale_shift, dgamma, dbeta, dbias_of_producer,
+                                                     HW, C, G, eps, S, cl, rows_per_cta));
+                    });
                 } else {
                     PIDM_DISPATCH_DTYPE(dtype, { GN_PIECE_CASE(1, true) else GN_PIECE_CASE(2, true) else GN_PIECE_CASE(2, false) });
                 }
