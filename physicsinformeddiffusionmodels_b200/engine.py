@@ -182,8 +182,9 @@ class TrainEngine:
             self._ar_stream = torch.cuda.Stream()
         ar = self._ar_stream
         ar.wait_stream(torch.cuda.current_stream())
-        if ops._SIDE['active'] and ops._SIDE['stream'] is not None:
-            ar.wait_stream(ops._SIDE['stream'])
+        if ops._SIDE['active']:
+            for st in ops._SIDE['streams']:
+                ar.wait_stream(st)
         lo, hi = self.fp.group_bounds[group]
         with torch.cuda.stream(ar):
             dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM)

@@ -271,21 +271,25 @@ class _Conv2d(torch.autograd.Function):
 # Weight-gradient kernels only feed the optimizer: inside TrainEngine they are launched on a side stream so that they
 # overlap the (latency-bound) dgrad / normalisation chain of the remaining layers.  Operand tensors are kept alive until
 # the join (they were allocated on the main stream).
-_SIDE = {'stream': None, 'keep': [], 'active': False}
+_SIDE = {'streams': [], 'next': 0, 'keep': [], 'active': False}
+_N_SIDE = max(1, int(os.environ.get('PIDM_SIDE_STREAMS', '1')))      # tuning aid: weight-gradient launches round-robin over
+                                                                      # this many side streams
 
 
 def side_stream_begin():
     if os.environ.get('PIDM_NO_SIDE_STREAM') == '1':      # debugging aid: everything on one stream
         return
-    if _SIDE['stream'] is None:
-        _SIDE['stream'] = torch.cuda.Stream()
+    while len(_SIDE['streams']) < _N_SIDE:
+        _SIDE['streams'].append(torch.cuda.Stream())
     _SIDE['active'] = True
+    _SIDE['next'] = 0
     _SIDE['keep'] = []
 
 
 def side_stream_join():
     if _SIDE['active']:
-        torch.cuda.current_stream().wait_stream(_SIDE['stream'])
+        for st in _SIDE['streams']:
+            torch.cuda.current_stream().wait_stream(st)
         _SIDE['keep'] = []
         _SIDE['active'] = False
 
@@ -305,7 +309,8 @@ def _wgrad_stream(*operands):
     """stream handle for a wgrad-type launch whose operands are ready on the current stream"""
     if not _SIDE['active']:
         return stream()
-    side = _SIDE['stream']
+    side = _SIDE['streams'][_SIDE['next']]
+    _SIDE['next'] = (_SIDE['next'] + 1) % len(_SIDE['streams'])
     side.wait_stream(torch.cuda.current_stream())
     _SIDE['keep'].extend(operands)
     return side.cuda_stream
