@@ -561,6 +561,7 @@ static EncodeTiledFn get_encode() {
 struct TcPlan {
     int TW, TH, TN, BN, BK;
     int rg, nb, a_bytes, stage_bytes, stages, resident, res_bytes, operand_bytes;
+    int cps;                 // CTAs per SM the launch is sized for (grid = SMs * cps persistent CTAs)
 };
 
 // GH x GW = pixel grid of the GEMM (output grid for regular convs, input grid for the transposed gather)
@@ -605,6 +606,19 @@ static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int KH, int KW, in
         static int stage_cap = -1;                  // tuning aid: PIDM_TC_STAGES caps the ring depth
         if (stage_cap < 0) { const char* ev = getenv("PIDM_TC_STAGES"); stage_cap = ev ? atoi(ev) : TC_RING_STAGES; }
         if (stage_cap >= 3 && stages > stage_cap) stages = stage_cap;
+        // Two CTAs per SM for the narrow layers with resident weights (BN = 32: 126 registers, 64 TMEM columns): these
+        // layers are bound by per-CTA issue chains as much as by the SM's copy engine -- measured (B200, batch 32) 64x64x32
+        // 3x3 10.5 -> 8.0 us, 4x4/s2 32->32 10.7 -> 7.7 us, 1x1 256->32 13.8 -> 11.1 us with two half-size rings, while
+        // layers that stream their weights (several n-tiles) or already run wide tiles do not gain.  PIDM_TC_CTAS=1 disables.
+        static int max_cps = -1;
+        if (max_cps < 0) { const char* ev = getenv("PIDM_TC_CTAS"); max_cps = ev ? atoi(ev) : 2; if (max_cps < 1) max_cps = 1; }
+        int cps = 1;
+        if (max_cps >= 2 && bn == 32 && resident) {
+            const long long fixed = (long long)wbytes + 1024 + 512 + 4 * 4096 + 1024;       // + 1 KB reserved per CTA
+            const int s2 = (int)(((227 * 1024) / 2 - fixed) / stage);
+            if (s2 >= 3) { cps = 2; if (stages > s2) stages = s2; }
+        }
+        pl.cps = cps;
         pl.BN = bn; pl.resident = resident; pl.res_bytes = resident ? (int)wbytes : 0;
         pl.stage_bytes = stage; pl.stages = stages;
         pl.operand_bytes = (int)(((resident ? wbytes : 0) + (long long)stages * stage + 1023) / 1024 * 1024);
@@ -730,7 +744,8 @@ static int tc_run(const void* x, const void* w_packed, const float* bias, const 
         PIDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int total_tiles = p.m_tiles * p.n_tiles * p.n_classes;
-    dim3 grid(total_tiles < sm_count ? total_tiles : sm_count);
+    const int slots = sm_count * pl.cps;
+    dim3 grid(total_tiles < slots ? total_tiles : slots);
 #define TC_CASE(bn, bk) if (pl.BN == bn && pl.BK == bk) return launch_tc<bn, bk>(mx, mw, p, grid, st)
     TC_CASE(256, 64); TC_CASE(128, 64); TC_CASE(64, 64); TC_CASE(32, 64);
     TC_CASE(256, 32); TC_CASE(128, 32); TC_CASE(64, 32); TC_CASE(32, 32);
