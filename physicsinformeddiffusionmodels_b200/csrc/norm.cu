@@ -1141,22 +1141,19 @@ extern "C" int pidm_groupnorm_silu_bwd(const void* x, const void* dy, const floa
     PIDM_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_piece_packed_kernel<T, NVV>, (const T*)x, (const T*)dy, sums, gamma, beta, \
                                  scale_shift, (T*)dx, d_scale_shift, dgamma, dbeta, dbias_of_producer, HW, C, G, eps,    \
                                  S, cl, rows_per_cta))
-                static int packed_ok = -1;          // tuning aid: PIDM_GN_PACKED=0 keeps the streaming variant
-                if (packed_ok < 0) { const char* ev = getenv("PIDM_GN_PACKED"); packed_ok = ev ? atoi(ev) : 1; }
-                // measured (B200, batch 32): 3-4 vectors per thread 11.6 -> 10.5 us (32x32x64); with 8 vectors per thread the
-                // packed variant spills and is SLOWER than streaming (64x64x32: 15.5 -> 29 us), so those stay streaming
-                if (!keep && v <= 4 && packed_ok) {
+                // three shapes of a piece: <= 2 vectors per thread stay in registers unpacked between the phases; 3-4 vectors are
+                // held packed (measured 11.6 -> 10.5 us at 32x32x64; with 8 vectors that variant spills: 15.5 -> 29 us at
+                // 64x64x32); larger pieces are streamed twice (12.5 us at 64x64x32)
+                if (keep) {
+                    PIDM_DISPATCH_DTYPE(dtype, { GN_PIECE_CASE(1, true) else GN_PIECE_CASE(2, true) });
+                } else if (v <= 4) {
                     PIDM_DISPATCH_DTYPE(dtype, { GN_PACKED_CASE(4); });
-                } else if (!keep && v <= 8 && packed_ok == 2) {      // PIDM_GN_PACKED=2: profiling aid
-                    PIDM_DISPATCH_DTYPE(dtype, { GN_PACKED_CASE(8); });
-                } else if (!keep && packed_ok != 3) {               // PIDM_GN_PACKED=3: the round-1 streaming loops (A/B aid)
+                } else {
                     PIDM_DISPATCH_DTYPE(dtype, {
                         PIDM_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_piece_stream_kernel<T>, (const T*)x, (const T*)dy, sums, gamma,
                                                      beta, scale_shift, (T*)dx, d_scale_shift, dgamma, dbeta, dbias_of_producer,
                                                      HW, C, G, eps, S, cl, rows_per_cta));
                     });
-                } else {
-                    PIDM_DISPATCH_DTYPE(dtype, { GN_PIECE_CASE(1, true) else GN_PIECE_CASE(2, true) else GN_PIECE_CASE(2, false) });
                 }
 #undef GN_PACKED_CASE
 #undef GN_PIECE_CASE
