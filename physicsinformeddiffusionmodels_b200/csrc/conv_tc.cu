@@ -622,7 +622,9 @@ static bool tc_plan(int B, int GH, int GW, int Cin, int Cout, int KH, int KW, in
         pl.BN = bn; pl.resident = resident; pl.res_bytes = resident ? (int)wbytes : 0;
         pl.stage_bytes = stage; pl.stages = stages;
         pl.operand_bytes = (int)(((resident ? wbytes : 0) + (long long)stages * stage + 1023) / 1024 * 1024);
-        if (m_tiles * (Cout / bn) >= 148) break;    // widest tile that still fills the machine
+        // widest tile that still (nearly) fills the machine: 128 tiles of N = 64 beat 256 tiles of N = 32 = 1.7 waves
+        // (16x16x128 3x3: 8.5 -> 6.2 us), while 64 tiles of N = 64 lose to 128 of N = 32 (8x8x256: 11.5 vs 11.6 us)
+        if (m_tiles * (Cout / bn) >= 128) break;
     }
     return pl.BN != 0;
 }
